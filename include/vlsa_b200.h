@@ -1,0 +1,78 @@
+/* vlsa_b200 — C ABI of the B200 (sm_100a) language-guided patch-aggregation path of VLSA.
+ *
+ * The reference (liupei101/VLSA @ 915f37a) is pure Python/PyTorch and has no FFI; the boundary this
+ * library replaces is the arithmetic inside
+ *     model/vlsa.py:181-198       VLSA.forward
+ *     model/deepmil.py:170-215    VLFAN.forward          (+ :16-67 logit_pooling / FeatMIL)
+ *     utils/func.py:40-48         softmax output converter
+ *     loss/loss_surv.py:144-169   SurvIFMLE.forward
+ *     loss/loss_surv_ext.py:42-109 SurvEMD.forward
+ * Each entry point names the reference lines it stands in for.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *   - the library never allocates device memory: scratch comes in through `workspace`
+ *     (size from the matching *_workspace_bytes query) and must stay alive until the stream reaches
+ *     the end of the call;
+ *   - no global mutable state: calls on different streams are independent;
+ *   - return value: 0 on success, a negative VLSA_E* code for argument errors, a positive
+ *     cudaError_t for CUDA failures (vlsa_error_string decodes both).
+ *   - feature dim D is fixed at 512 (vlsa_img_encoder_dim_in, config/IFMLE/tcga_blca/cfg_vlsa_conch.yaml:47);
+ *     1 <= P <= 16 text prototypes (num_query), 1 <= R <= 32 ordinal ranks (time_bins).
+ */
+#ifndef VLSA_B200_H_
+#define VLSA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLSA_D 512
+#define VLSA_MAX_P 16
+#define VLSA_MAX_R 32
+
+#define VLSA_DTYPE_F32 0
+#define VLSA_DTYPE_BF16 1
+
+#define VLSA_EINVAL (-1)      /* bad argument (null pointer, P/R/D out of range, ...) */
+#define VLSA_EWORKSPACE (-2)  /* workspace too small */
+#define VLSA_EUNSUPPORTED (-3)
+
+#define VLSA_POOL_MEAN 0 /* 'logit_mean'  (deepmil.py:29-30) */
+#define VLSA_POOL_TOPK 1 /* 'logit_topK' / 'logit_max' = top-1 (deepmil.py:24-28) */
+
+int vlsa_version(void);
+const char* vlsa_error_string(int code);
+
+/* Host-only helper: split the bags of one call into row chunks for the streaming kernels.
+ * cu_rows_host[B+1] are the row offsets of the bags inside the packed X.  Writes chunk_start_host[B+1]
+ * (first chunk id of every bag; chunk_start_host[B] = total chunks) and *chunk_rows_out (rows per
+ * chunk, a multiple of the kernel's row tile).  sm_count <= 0 means "query the current device". */
+int vlsa_agg_plan(const int64_t* cu_rows_host, int B, int sm_count, int* chunk_rows_out,
+                  int32_t* chunk_start_host);
+
+/* Scratch bytes needed by vlsa_agg_fwd / vlsa_agg_bwd for a plan with total_chunks chunks. */
+size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P);
+
+/* Fused forward of VLSA.forward (model/vlsa.py:181-198) on B packed bags:
+ *   Qn = Q/|Q|; s = scale * Qn.(x/|x|); A = softmax_N(s); O = A@X      (deepmil.py:187-200)
+ *   v = mean_P(O); f = W v + b                                         (deepmil.py:136,204)
+ *   g = f/|f|; Tn = T/|T|; logits = (exp(logit_scale) g) @ Tn^T        (vlsa.py:185-192)
+ *   IF = softmax(logits)                                               (utils/func.py:44)
+ * X is read exactly once.  out_ml / out_O / out_v / out_f are what vlsa_agg_bwd needs later
+ * (out_O may be NULL when no backward follows).  out_if and out_Tn may be NULL. */
+int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
+                 size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
+                 float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLSA_B200_H_ */

@@ -1,0 +1,293 @@
+// Fused language-guided aggregation, streaming pass over X (replaces model/deepmil.py:187-200 of
+// liupei101/VLSA).  One read of X; per chunk of rows the kernel produces an
+// online-softmax partial (m, l, O[P,D]) (forward) or a partial dQn[P,D] (backward).
+//
+// CUDA-core (fp32 FFMA) variant: TMA bulk copies stage [TN,D] tiles of X in shared memory behind an
+// mbarrier ring; phase A = P+1 dot products per row with a transposed-butterfly warp reduction,
+// phase S = per-tile softmax bookkeeping, phase B = P-way weighted accumulation with one thread per
+// two feature columns.  Deterministic: a chunk's partial depends only on the chunk.
+#pragma once
+#include "common.cuh"
+
+namespace vlsa {
+
+struct AggParams {
+    const void* X;              // [total_rows, D] fp32 or bf16
+    const long long* cu_rows;   // [B+1] row offsets of bags (device)
+    const int* chunk_start;     // [B+1] first chunk id of each bag (device)
+    int B;
+    int chunk_rows;             // rows per chunk (multiple of TN)
+    int total_chunks;
+    const float* Q;             // [P, D] un-normalised queries
+    float scale;                // exp(fp32(log 100)), deepmil.py:122
+    // forward outputs: per-chunk partials
+    float* part_m;              // [chunks, P]
+    float* part_l;              // [chunks, P]
+    float* part_O;              // [chunks, P, D]  (backward: partial dQn)
+    // backward inputs (per bag)
+    const float* dv;            // [B, D]   d loss / d pooled  (already divided by P inside the kernel)
+    const float* ml;            // [B, P, 2] (max, sum) from forward
+    const float* delta;         // [B, P]   dO_p . O_p
+};
+
+template <int P, bool BWD, typename XT>
+struct AggCfg {
+    static constexpr int D = VLSA_D;
+    static constexpr int THREADS = 256;
+    static constexpr int TN = 32;                      // rows per tile (8 warps x 4 rows)
+    static constexpr int STAGES = 2;
+    static constexpr int NQ = BWD ? P + 1 : P;         // query rows resident in smem
+    static constexpr int NRED = NQ + 1;                // + sum of squares
+    static constexpr int PP = (P + 3) & ~3;            // weights per row, float4-padded
+    static constexpr int NV = 4 * NRED;                // values reduced per warp per tile
+    static constexpr size_t XS_BYTES = size_t(STAGES) * TN * D * sizeof(XT);
+    static constexpr size_t QS_BYTES = size_t(NQ) * D * sizeof(float);
+    static constexpr size_t RED_BYTES = size_t(TN) * NRED * sizeof(float);
+    static constexpr size_t WT_BYTES = size_t(TN) * PP * sizeof(float);
+    static constexpr size_t SC_BYTES = 6 * VLSA_MAX_P * sizeof(float);
+    static constexpr size_t SMEM = XS_BYTES + QS_BYTES + RED_BYTES + WT_BYTES + SC_BYTES + STAGES * 8 + 128;
+};
+
+// chunk id -> (bag, first row, one-past-last row); chunk_start is monotone, bags with 0 rows have 0 chunks
+__device__ __forceinline__ void chunk_info(const AggParams& p, int c, int& bag, long long& r0, long long& r1) {
+    int lo = 0, hi = p.B;            // find bag with chunk_start[bag] <= c < chunk_start[bag+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.chunk_start + mid) <= c) lo = mid; else hi = mid;
+    }
+    bag = lo;
+    const long long b0 = __ldg(p.cu_rows + lo), b1 = __ldg(p.cu_rows + lo + 1);
+    r0 = b0 + (long long)(c - __ldg(p.chunk_start + lo)) * p.chunk_rows;
+    r1 = r0 + p.chunk_rows < b1 ? r0 + p.chunk_rows : b1;
+}
+
+template <int P, bool BWD, typename XT>
+__global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
+    using C = AggCfg<P, BWD, XT>;
+    constexpr int D = C::D, TN = C::TN, STAGES = C::STAGES, NQ = C::NQ, NRED = C::NRED, PP = C::PP, NV = C::NV;
+    constexpr bool BF16 = sizeof(XT) == 2;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    XT* xs = reinterpret_cast<XT*>(smem_raw);
+    float* qs = reinterpret_cast<float*>(smem_raw + C::XS_BYTES);
+    float* red = reinterpret_cast<float*>(smem_raw + C::XS_BYTES + C::QS_BYTES);
+    float* wt = reinterpret_cast<float*>(smem_raw + C::XS_BYTES + C::QS_BYTES + C::RED_BYTES);
+    float* sc = reinterpret_cast<float*>(smem_raw + C::XS_BYTES + C::QS_BYTES + C::RED_BYTES + C::WT_BYTES);
+    float* s_m = sc;                       // running max        (fwd) | saved max        (bwd)
+    float* s_l = sc + VLSA_MAX_P;          // running sum        (fwd) | 1 / saved sum    (bwd)
+    float* s_alpha = sc + 2 * VLSA_MAX_P;  // per-tile rescale   (fwd) | delta_p          (bwd)
+    uint64_t* full = reinterpret_cast<uint64_t*>(
+        (reinterpret_cast<uintptr_t>(sc + 6 * VLSA_MAX_P) + 7) & ~uintptr_t(7));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (int(blockIdx.x) >= prm.total_chunks) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    // Qn = Q / max(||Q||, eps)  (deepmil.py:187): warp w normalises rows w, w+8
+    for (int p = warp; p < P; p += 8) {
+        const float* q = prm.Q + size_t(p) * D;
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = __ldg(q + d); ss += v * v; }
+        ss = warp_sum(ss);
+        const float inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+        for (int d = lane; d < D; d += 32) qs[p * D + d] = __ldg(q + d) * inv;
+    }
+    if (tid < P) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_alpha[tid] = 0.f; }
+    __syncthreads();
+
+    const uint64_t policy = make_evict_first_policy();
+
+    // ---- producer cursor (thread 0) and consumer cursor (all threads, uniform) ---------------
+    int pc = blockIdx.x; long long pr0 = 0, pr1 = 0; int pbag = 0; long long prow = 0;
+    bool phas = pc < prm.total_chunks;
+    if (phas) { chunk_info(prm, pc, pbag, pr0, pr1); prow = pr0; }
+    int issued = 0;
+    auto produce = [&]() {      // thread 0 only
+        if (!phas) return;
+        const int stage = issued % STAGES;
+        const long long left = pr1 - prow;
+        const int n = left < TN ? int(left) : TN;
+        const uint32_t bytes = uint32_t(n) * D * sizeof(XT);
+        mbar_expect_tx(full + stage, bytes);
+        bulk_g2s_evict_first(xs + size_t(stage) * TN * D, reinterpret_cast<const XT*>(prm.X) + prow * D, bytes,
+                             full + stage, policy);
+        ++issued;
+        prow += n;
+        if (prow >= pr1) {
+            pc += gridDim.x;
+            phas = pc < prm.total_chunks;
+            if (phas) { chunk_info(prm, pc, pbag, pr0, pr1); prow = pr0; }
+        }
+    };
+    if (tid == 0) for (int s = 0; s < STAGES - 1; ++s) produce();
+
+    float acc2[P][2];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { acc2[p][0] = 0.f; acc2[p][1] = 0.f; }
+
+    int it = 0;
+    for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
+        int bag; long long r0, r1;
+        chunk_info(prm, c, bag, r0, r1);
+        if (BWD) {
+            // per-bag operands: extra query row dv_b / P, saved (m, 1/l), delta_p = (dv . O_p) / P
+            __syncthreads();
+            const float invP = 1.f / float(P);
+            for (int d = tid; d < D; d += C::THREADS) qs[P * D + d] = __ldg(prm.dv + size_t(bag) * D + d) * invP;
+            if (tid < P) {
+                s_m[tid] = __ldg(prm.ml + (size_t(bag) * P + tid) * 2);
+                s_l[tid] = 1.f / __ldg(prm.ml + (size_t(bag) * P + tid) * 2 + 1);
+                s_alpha[tid] = __ldg(prm.delta + size_t(bag) * P + tid);
+            }
+            __syncthreads();
+        }
+        for (long long row = r0; row < r1; row += TN, ++it) {
+            const int stage = it % STAGES;
+            const uint32_t parity = (it / STAGES) & 1;
+            if (tid == 0) produce();          // tile it+STAGES-1 -> stage freed by the previous trailing barrier
+            const int nvalid = (r1 - row) < TN ? int(r1 - row) : TN;
+            const XT* xt = xs + size_t(stage) * TN * D;
+            mbar_wait(full + stage, parity);
+
+            // ---------------- phase A: NQ dots + sum of squares for rows 4*warp .. 4*warp+3 --------
+            float acc[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+            if (!BF16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 xv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        xv[r] = *reinterpret_cast<const float4*>(
+                            reinterpret_cast<const float*>(xt) + size_t(4 * warp + r) * D + j * 128 + lane * 4);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        acc[r * NRED + NQ] += xv[r].x * xv[r].x + xv[r].y * xv[r].y + xv[r].z * xv[r].z + xv[r].w * xv[r].w;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 qv = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            acc[r * NRED + q] += qv.x * xv[r].x + qv.y * xv[r].y + qv.z * xv[r].z + qv.w * xv[r].w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float xf[4][8];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const uint4 u = *reinterpret_cast<const uint4*>(
+                            reinterpret_cast<const __nv_bfloat16*>(xt) + size_t(4 * warp + r) * D + j * 256 + lane * 8);
+                        xf[r][0] = bf16_lo(u.x); xf[r][1] = bf16_hi(u.x); xf[r][2] = bf16_lo(u.y); xf[r][3] = bf16_hi(u.y);
+                        xf[r][4] = bf16_lo(u.z); xf[r][5] = bf16_hi(u.z); xf[r][6] = bf16_lo(u.w); xf[r][7] = bf16_hi(u.w);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[r * NRED + NQ] += xf[r][k] * xf[r][k];
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 qa = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
+                        const float4 qb = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            acc[r * NRED + q] += qa.x * xf[r][0] + qa.y * xf[r][1] + qa.z * xf[r][2] + qa.w * xf[r][3] +
+                                                 qb.x * xf[r][4] + qb.y * xf[r][5] + qb.z * xf[r][6] + qb.w * xf[r][7];
+                    }
+                }
+            }
+            // transposed butterfly in groups of 32 values; lane L of group g ends with value 32g+L
+#pragma unroll
+            for (int g = 0; g * 32 < NV; ++g) {
+                constexpr int dummy = 0; (void)dummy;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = (g * 32 + i < NV) ? acc[(g * 32 + i < NV) ? g * 32 + i : 0] : 0.f;
+                float tot;
+                if (NV - g * 32 >= 32) tot = warp_reduce_transpose<32>(v);
+                else tot = warp_reduce_transpose<(NV % 32 == 0 ? 32 : NV % 32)>(v);
+                const int idx = g * 32 + lane;
+                if (idx < NV) red[(4 * warp + idx / NRED) * NRED + idx % NRED] = tot;
+            }
+            __syncthreads();
+
+            // ---------------- phase S: per-(row, p) weights; lane = row, warp handles p = warp, warp+8 ----
+            for (int p = warp; p < P; p += 8) {
+                const float dot = red[lane * NRED + p], ss = red[lane * NRED + NQ];
+                const float nrm = fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+                const bool live = lane < nvalid;
+                const float s = live ? prm.scale * (dot / nrm) : -INFINITY;
+                if (!BWD) {
+                    const float tmax = warp_max(s);
+                    const float mo = s_m[p];
+                    const float mn = fmaxf(mo, tmax);
+                    const float w = expf(s - mn);
+                    const float wsum = warp_sum(w);
+                    wt[lane * PP + p] = w;
+                    if (lane == 0) {
+                        const float a = expf(mo - mn);
+                        s_alpha[p] = a;
+                        s_l[p] = s_l[p] * a + wsum;
+                        s_m[p] = mn;
+                    }
+                } else {
+                    const float a = expf(s - s_m[p]) * s_l[p];                 // A_pn (deepmil.py:198)
+                    const float u = red[lane * NRED + P];                       // (dv . x_n) / P
+                    wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
+                }
+            }
+            __syncthreads();
+
+            // ---------------- phase B: acc2[p][:] (+)= sum_r w[r][p] * x[r][2*tid .. 2*tid+1] -------------
+            if (!BWD) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) { const float a = s_alpha[p]; acc2[p][0] *= a; acc2[p][1] *= a; }
+            }
+#pragma unroll 4
+            for (int r = 0; r < nvalid; ++r) {
+                float x0, x1;
+                if (!BF16) {
+                    const float2 xv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(xt) + size_t(r) * D + 2 * tid);
+                    x0 = xv.x; x1 = xv.y;
+                } else {
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(xt) + size_t(r) * D + 2 * tid);
+                    x0 = bf16_lo(u); x1 = bf16_hi(u);
+                }
+#pragma unroll
+                for (int k = 0; k < PP / 4; ++k) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wt + r * PP + 4 * k);
+                    if (4 * k + 0 < P) { acc2[4 * k + 0 < P ? 4 * k + 0 : 0][0] += w4.x * x0; acc2[4 * k + 0 < P ? 4 * k + 0 : 0][1] += w4.x * x1; }
+                    if (4 * k + 1 < P) { acc2[4 * k + 1 < P ? 4 * k + 1 : 0][0] += w4.y * x0; acc2[4 * k + 1 < P ? 4 * k + 1 : 0][1] += w4.y * x1; }
+                    if (4 * k + 2 < P) { acc2[4 * k + 2 < P ? 4 * k + 2 : 0][0] += w4.z * x0; acc2[4 * k + 2 < P ? 4 * k + 2 : 0][1] += w4.z * x1; }
+                    if (4 * k + 3 < P) { acc2[4 * k + 3 < P ? 4 * k + 3 : 0][0] += w4.w * x0; acc2[4 * k + 3 < P ? 4 * k + 3 : 0][1] += w4.w * x1; }
+                }
+            }
+
+            if (row + TN >= r1) {
+                // ---------------- chunk done: write the partial and reset ------------------------------
+                float* o = prm.part_O + size_t(c) * P * D;
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    *reinterpret_cast<float2*>(o + size_t(p) * D + 2 * tid) = make_float2(acc2[p][0], acc2[p][1]);
+                    acc2[p][0] = 0.f; acc2[p][1] = 0.f;
+                }
+                if (!BWD) {
+                    __syncthreads();           // phase-B readers of s_alpha are done before the reset below
+                    if (tid < P) {
+                        prm.part_m[size_t(c) * P + tid] = s_m[tid];
+                        prm.part_l[size_t(c) * P + tid] = s_l[tid];
+                        s_m[tid] = -INFINITY; s_l[tid] = 0.f;
+                    }
+                }
+            }
+            __syncthreads();    // stage `stage`, red and wt are free again
+        }
+    }
+}
+
+}  // namespace vlsa

@@ -1,0 +1,275 @@
+"""Torch-facing wrappers of the C-ABI (device memory, streams and autograd glue only).
+
+``aggregate(...)`` is the differentiable fused forward of ``VLSA.forward`` (model/vlsa.py:181-198
++ model/deepmil.py:170-215 of the reference) over a *packed* batch of bags.  All arithmetic runs
+in libvlsa_b200.so; there is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+D_FEAT = 512
+MAX_P = 16
+MAX_R = 32
+
+
+def coattn_scale() -> float:
+    """exp(fp32(log 100)) as the reference computes it (model/deepmil.py:122,125)."""
+    return float((torch.ones([]) * np.log(100)).exp())
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_cuda(t: torch.Tensor, name: str, dtype=torch.float32) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (vlsa_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+_SM_COUNT: dict[int, int] = {}
+
+
+def sm_count(device=None) -> int:
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+@dataclass
+class BagPlan:
+    """Row offsets of a packed batch of bags plus the chunk schedule of the streaming kernels."""
+    cu_rows_host: np.ndarray        # int64 [B+1]
+    chunk_start_host: np.ndarray    # int32 [B+1]
+    chunk_rows: int
+    cu_rows: torch.Tensor           # device int64 [B+1]
+    chunk_start: torch.Tensor       # device int32 [B+1]
+
+    @property
+    def num_bags(self) -> int:
+        return len(self.cu_rows_host) - 1
+
+    @property
+    def total_rows(self) -> int:
+        return int(self.cu_rows_host[-1])
+
+    @property
+    def total_chunks(self) -> int:
+        return int(self.chunk_start_host[-1])
+
+
+def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
+    """Host-side schedule for a batch of bags with the given row counts (vlsa_agg_plan)."""
+    sizes = np.asarray(list(bag_sizes), dtype=np.int64)
+    if (sizes < 0).any():
+        raise ValueError("negative bag size")
+    cu = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=cu[1:])
+    cs = np.zeros(len(sizes) + 1, dtype=np.int32)
+    chunk_rows = C.c_int(0)
+    if sms is None:
+        sms = sm_count(device)
+    rc = _lib.lib().vlsa_agg_plan(cu.ctypes.data_as(C.POINTER(C.c_int64)), len(sizes), int(sms), C.byref(chunk_rows),
+                                  cs.ctypes.data_as(C.POINTER(C.c_int32)))
+    _lib.check(rc, "vlsa_agg_plan")
+    # one small pinned staging buffer -> async H2D on the current stream
+    stage = torch.empty(len(cu) * 2, dtype=torch.int64).pin_memory()
+    stage[: len(cu)] = torch.from_numpy(cu)
+    stage[len(cu):].view(torch.int32)[: len(cs)] = torch.from_numpy(cs)
+    dev = stage.to(device, non_blocking=True)
+    return BagPlan(cu, cs, int(chunk_rows.value), dev[: len(cu)], dev[len(cu):].view(torch.int32)[: len(cs)])
+
+
+def _x_dtype_code(x: torch.Tensor) -> int:
+    if x.dtype == torch.float32:
+        return 0
+    if x.dtype == torch.bfloat16:
+        return 1
+    raise ValueError(f"X must be float32 or bfloat16, got {x.dtype}")
+
+
+def _workspace(plan: BagPlan, P: int, device) -> torch.Tensor:
+    nbytes = _lib.lib().vlsa_agg_workspace_bytes(plan.total_chunks, plan.num_bags, P)
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd: bool = True, scale: float | None = None,
+                          workspace: torch.Tensor | None = None, want_if: bool = True):
+    """Launch vlsa_agg_fwd.  Returns a dict of fresh output tensors (no autograd)."""
+    L = _lib.lib()
+    B, P, R = plan.num_bags, Q.shape[0], T.shape[0]
+    if X.dim() != 2 or X.shape[1] != D_FEAT:
+        raise ValueError(f"packed X must be [total_rows, {D_FEAT}], got {tuple(X.shape)}")
+    if X.shape[0] != plan.total_rows:
+        raise ValueError(f"packed X has {X.shape[0]} rows but the plan covers {plan.total_rows}")
+    if not (1 <= P <= MAX_P):
+        raise ValueError(f"num_query P={P} outside 1..{MAX_P}")
+    if not (1 <= R <= MAX_R):
+        raise ValueError(f"num_ranks R={R} outside 1..{MAX_R}")
+    _check_cuda(X, "X", None)
+    for name, t in (("Q", Q), ("W", W), ("bias", bias), ("T", T), ("logit_scale", logit_scale)):
+        _check_cuda(t, name)
+    if Q.shape[1] != D_FEAT or T.shape[1] != D_FEAT or tuple(W.shape) != (D_FEAT, D_FEAT) or bias.numel() != D_FEAT:
+        raise ValueError("parameter shapes do not match D=512")
+    dev = X.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    out = {
+        "v": torch.empty(B, D_FEAT, **f32), "f": torch.empty(B, D_FEAT, **f32), "g": torch.empty(B, D_FEAT, **f32),
+        "logits": torch.empty(B, R, **f32), "incidence": torch.empty(B, R, **f32) if want_if else None,
+        "ml": torch.empty(B, P, 2, **f32), "O": torch.empty(B, P, D_FEAT, **f32) if need_bwd else None,
+        "Tn": torch.empty(R, D_FEAT, **f32),
+    }
+    ws = workspace if workspace is not None else _workspace(plan, P, dev)
+    rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+                        plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P,
+                        coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
+                        T.data_ptr(), R, logit_scale.data_ptr(), ws.data_ptr(), ws.numel(),
+                        out["v"].data_ptr(), out["f"].data_ptr(), out["g"].data_ptr(), out["logits"].data_ptr(),
+                        _ptr(out["incidence"]), out["ml"].data_ptr(), _ptr(out["O"]), out["Tn"].data_ptr(), _stream())
+    _lib.check(rc, "vlsa_agg_fwd")
+    out["_workspace"] = ws
+    return out
+
+
+class _AggregateFn(torch.autograd.Function):
+    """Differentiable w.r.t. (Q, W, bias, T, logit_scale).  X is data (the reference never asks for dX)."""
+
+    @staticmethod
+    def forward(ctx, X, plan, Q, W, bias, T, logit_scale, scale):
+        Qc, Wc, bc, Tc, lsc = (t.detach().contiguous() for t in (Q, W, bias, T, logit_scale))
+        need_bwd = any(t.requires_grad for t in (Q, W, bias, T, logit_scale))
+        out = aggregate_forward_raw(X, plan, Qc, Wc, bc, Tc, lsc, need_bwd=need_bwd, scale=scale)
+        ctx.plan, ctx.scale, ctx.need_bwd = plan, scale, need_bwd
+        ctx.ws = out["_workspace"]
+        if need_bwd:
+            ctx.save_for_backward(X, Qc, Wc, Tc, lsc, out["v"], out["f"], out["g"], out["logits"], out["ml"], out["O"])
+        ctx.mark_non_differentiable(out["incidence"], out["ml"])
+        return out["logits"], out["g"], out["Tn"], out["incidence"], out["ml"]
+
+    @staticmethod
+    def backward(ctx, d_logits, d_g, d_Tn, _d_if, _d_ml):
+        if d_Tn is not None and bool((d_Tn != 0).any()):
+            raise NotImplementedError("gradient through the returned normalised text features is not supported")
+        X, Q, W, T, ls, v, f, g, logits, ml, O = ctx.saved_tensors
+        plan = ctx.plan
+        L = _lib.lib()
+        B, P, R = plan.num_bags, Q.shape[0], T.shape[0]
+        dev = X.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_logits = (torch.zeros(B, R, **f32) if d_logits is None else d_logits.contiguous().float())
+        d_g = None if d_g is None else d_g.contiguous().float()
+        dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
+        dT, dls = torch.empty(R, D_FEAT, **f32), torch.empty((), **f32)
+        rc = L.vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+                            plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P,
+                            coattn_scale() if ctx.scale is None else float(ctx.scale), W.data_ptr(), T.data_ptr(), R,
+                            ls.data_ptr(), v.data_ptr(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), ml.data_ptr(),
+                            O.data_ptr(), d_logits.data_ptr(), _ptr(d_g), ctx.ws.data_ptr(), ctx.ws.numel(),
+                            dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), dT.data_ptr(), dls.data_ptr(), _stream())
+        _lib.check(rc, "vlsa_agg_bwd")
+        return None, None, dQ, dW, db, dT, dls, None
+
+
+def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None):
+    """Fused VLSA forward on a packed batch.  Returns (logits [B,R], g [B,D], Tn [R,D], incidence [B,R], ml)."""
+    return _AggregateFn.apply(X, plan, Q, W, bias, T, logit_scale, scale)
+
+
+def attention_scores(X, Q, ml, scale: float | None = None):
+    """A [P,N] = softmax_N(scale * cos(Q, X)) for ONE bag, from the (max, sum) saved by the forward
+    (the ``ret_with_attn=True`` output of VLFAN.forward, model/deepmil.py:206-213)."""
+    L = _lib.lib()
+    _check_cuda(X, "X", None)
+    _check_cuda(Q, "Q")
+    _check_cuda(ml, "ml")
+    N, P = X.shape[0], Q.shape[0]
+    A = torch.empty(P, N, dtype=torch.float32, device=X.device)
+    rc = L.vlsa_attn_fwd(X.data_ptr(), _x_dtype_code(X), N, Q.data_ptr(), P,
+                         coattn_scale() if scale is None else float(scale), ml.data_ptr(), A.data_ptr(), _stream())
+    _lib.check(rc, "vlsa_attn_fwd")
+    return A
+
+
+class _SurvLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, t, e, logit_scale, w_ifmle, w_emd, alpha, eps, inv_norm):
+        L = _lib.lib()
+        B, R = logits.shape
+        lg = logits.detach().contiguous().float()
+        dev = lg.device
+        loss = torch.empty(3, dtype=torch.float32, device=dev)
+        inc = torch.empty(B, R, dtype=torch.float32, device=dev)
+        dlog = torch.empty(B, R, dtype=torch.float32, device=dev)
+        per = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        rc = L.vlsa_surv_loss_fwd_bwd(lg.data_ptr(), t.data_ptr(), e.data_ptr(), B, R, logit_scale.data_ptr(),
+                                      float(w_ifmle), float(w_emd), float(alpha), float(eps), float(inv_norm),
+                                      loss.data_ptr(), inc.data_ptr(), dlog.data_ptr(), per.data_ptr(), _stream())
+        _lib.check(rc, "vlsa_surv_loss_fwd_bwd")
+        ctx.save_for_backward(dlog)
+        ctx.mark_non_differentiable(inc, per)
+        return loss[0], loss[1], loss[2], inc, per
+
+    @staticmethod
+    def backward(ctx, d_total, d_ifmle, d_emd, _a, _b):
+        (dlog,) = ctx.saved_tensors
+        if (d_ifmle is not None and bool((d_ifmle != 0).any())) or (d_emd is not None and bool((d_emd != 0).any())):
+            raise NotImplementedError("differentiate the total loss, not its components")
+        return dlog * d_total, None, None, None, None, None, None, None, None
+
+
+def surv_loss(logits, t, e, logit_scale, w_ifmle: float = 1.0, w_emd: float = 1.0, alpha: float = 0.0,
+              eps: float = 1e-7, norm: int | None = None):
+    """softmax -> w_ifmle * SurvIFMLE + w_emd * SurvEMD with mean over ``norm`` samples (default: B), fused
+    forward + gradient (runner/vlsa_handler.py:241-258, loss/loss_surv.py:144-169, loss/loss_surv_ext.py:70-109).
+    ``logit_scale`` is the log-space parameter; SurvEMD uses exp(logit_scale).detach().
+    Returns (total, ifmle, emd, incidence [B,R], per_sample [B,2])."""
+    _check_cuda(logits, "logits")
+    t = t.reshape(-1).to(device=logits.device, dtype=torch.int64).contiguous()
+    e = e.reshape(-1).to(device=logits.device, dtype=torch.int64).contiguous()
+    B = logits.shape[0]
+    if t.numel() != B or e.numel() != B:
+        raise ValueError("t and e must have one entry per row of logits")
+    ls = logit_scale.detach().reshape(()).float().contiguous()
+    inv_norm = 1.0 / float(B if norm is None else norm)
+    return _SurvLossFn.apply(logits, t, e, ls, w_ifmle, w_emd, alpha, eps, inv_norm)
+
+
+def logit_pool(X, T, logit_scale, pooling: str):
+    """Zero-shot arm: per-patch logits exp(ls) * cos(x_n, T_r) pooled over N per class
+    (model/vlsa.py:189-196 with FeatMIL identity + model/deepmil.py:16-37).  Returns (preds [1] int64, pooled [1,R])."""
+    L = _lib.lib()
+    _check_cuda(X, "X", None)
+    _check_cuda(T, "T")
+    if pooling[:9] in ("logit_max", "logit_top"):
+        k = 1 if pooling == "logit_max" else int(pooling.split("top")[-1])
+        mode = 1
+    elif pooling == "logit_mean":
+        k, mode = 0, 0
+    else:
+        raise NotImplementedError(f"The pooling ({pooling}) is not implemented.")
+    N, R = X.shape[0], T.shape[0]
+    nbytes = L.vlsa_logit_pool_workspace_bytes(N, R, k)
+    ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=X.device)
+    pooled = torch.empty(1, R, dtype=torch.float32, device=X.device)
+    pred = torch.empty(1, dtype=torch.int64, device=X.device)
+    ls = logit_scale.detach().reshape(()).float().contiguous()
+    rc = L.vlsa_logit_pool_fwd(X.data_ptr(), _x_dtype_code(X), N, T.data_ptr(), R, ls.data_ptr(), mode, k,
+                               ws.data_ptr(), ws.numel(), pooled.data_ptr(), pred.data_ptr(), _stream())
+    _lib.check(rc, "vlsa_logit_pool_fwd")
+    return pred, pooled
