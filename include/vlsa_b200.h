@@ -72,6 +72,44 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
                  float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream);
 
+/* Backward of vlsa_agg_fwd w.r.t. (Q, W, bias, T, logit_scale) — what torch autograd computes for
+ * model/vlsa.py:181-198 when `pred_loss.backward()` runs (runner/vlsa_handler.py:281).  X is data: no dX.
+ * Second (and last) read of X: dQn_p = sum_n scale * A_pn (u_n - delta_p) x_n / |x_n| with
+ * u_n = dv.x_n / P, delta_p = dv.O_p / P, A recomputed from the saved (max, sum) in `ml`.
+ * v, f, g, logits, ml, O are the tensors vlsa_agg_fwd wrote; d_logits [B,R] is the incoming
+ * gradient; d_g [B,D] (gradient w.r.t. the returned image features) may be NULL.
+ * Outputs are overwritten (not accumulated): dQ [P,D], dW [D,D], db [D], dT [R,D], dlogit_scale [1]. */
+int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
+                 const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
+                 void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db, float* dT,
+                 float* dlogit_scale, void* stream);
+
+/* Attention read-out of ONE bag: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1]
+ * (`ret_with_attn=True`, model/deepmil.py:206-213).  ml [P,2] comes from vlsa_agg_fwd.  out_A is [P,N]. */
+int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
+                  float* out_A, void* stream);
+
+/* softmax -> w_ifmle * SurvIFMLE + w_emd * SurvEMD, value and gradient in one pass
+ * (runner/vlsa_handler.py:241-258; loss/loss_surv.py:144-169 with alpha/eps; loss/loss_surv_ext.py:70-109
+ * with p=2, raw distance, exp(logit_scale) detached).  t, e: int64 [B] (time bin, event indicator).
+ * inv_norm = 1 / (number of samples the mean runs over; the GLOBAL batch when bags are sharded).
+ * out_loss [3] = (total, ifmle, emd); out_if [B,R] and out_dlogits [B,R] may be NULL;
+ * out_per_sample [B,2] (ifmle_i, emd_i) is required (it is also the reduction scratch). */
+int vlsa_surv_loss_fwd_bwd(const float* logits, const int64_t* t, const int64_t* e, int B, int R,
+                           const float* logit_scale, float w_ifmle, float w_emd, float alpha, float eps,
+                           float inv_norm, float* out_loss, float* out_if, float* out_dlogits,
+                           float* out_per_sample, void* stream);
+
+/* Zero-shot arm (model/vlsa.py:189-196 with FeatMIL identity, model/deepmil.py:16-37) for ONE bag:
+ * per-patch logits exp(logit_scale) * cos(x_n, T_r), pooled over N per class (mean, or mean of the
+ * top-min(k,N) values, k <= 64), preds = argmax_r (first maximal index).  out_logits [R], out_pred [1]. */
+size_t vlsa_logit_pool_workspace_bytes(int64_t N, int R, int k);
+int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, int R, const float* logit_scale,
+                        int mode, int k, void* workspace, size_t workspace_bytes, float* out_logits,
+                        int64_t* out_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

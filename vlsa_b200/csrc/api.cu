@@ -7,6 +7,8 @@
 
 #include "agg_simt.cuh"
 #include "head_kernels.cuh"
+#include "loss_kernels.cuh"
+#include "aux_kernels.cuh"
 
 using namespace vlsa;
 
@@ -54,7 +56,9 @@ struct AggWorkspace {
     float* part_l;
     float* part_O;
     float* delta;      // [B, P]   backward
-    float* dgf;        // [2, B, D] backward: dg then df
+    float* df;         // [B, D]   backward
+    float* dv;         // [B, D]   backward
+    float* dls_part;   // [B]      backward
     size_t bytes;
 };
 
@@ -70,7 +74,9 @@ static AggWorkspace carve(void* base, int total_chunks, int B, int P) {
     w.part_l = take(size_t(total_chunks) * P);
     w.part_O = take(size_t(total_chunks) * P * VLSA_D);
     w.delta = take(size_t(B) * P);
-    w.dgf = take(size_t(2) * B * VLSA_D);
+    w.df = take(size_t(B) * VLSA_D);
+    w.dv = take(size_t(B) * VLSA_D);
+    w.dls_part = take(size_t(B));
     w.bytes = off;
     return w;
 }
@@ -169,6 +175,128 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     adapter_fwd_kernel<<<VLSA_D / 4, 128, 0, st>>>(W, bias, out_v, B, out_f);
     VLSA_CUDA(cudaGetLastError());
     head_fwd_kernel<<<B, 256, 0, st>>>(out_f, T, R, logit_scale, out_g, out_logits, out_if, out_Tn);
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
+                 const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
+                 void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db, float* dT,
+                 float* dlogit_scale, void* stream) {
+    if (!cu_rows || !chunk_start || !Q || !W || !T || !logit_scale || !v || !f || !g || !logits || !ml || !O ||
+        !d_logits || !dQ || !dW || !db || !dT || !dlogit_scale || !workspace)
+        return VLSA_EINVAL;
+    if (B < 1 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R || chunk_rows <= 0 || chunk_rows % kRowTile ||
+        total_chunks < 0)
+        return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (total_chunks > 0 && !X) return VLSA_EINVAL;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    head_bwd_kernel<<<B, 256, 0, st>>>(f, g, T, R, logit_scale, logits, d_logits, d_g, ws.df, ws.dls_part);
+    VLSA_CUDA(cudaGetLastError());
+    text_bwd_kernel<<<R, 256, 0, st>>>(T, R, g, d_logits, B, logit_scale, ws.dls_part, dT, dlogit_scale);
+    VLSA_CUDA(cudaGetLastError());
+    adapter_bwd_dw_kernel<<<VLSA_D / 8, 512, 0, st>>>(ws.df, v, B, dW, db);
+    VLSA_CUDA(cudaGetLastError());
+    adapter_bwd_dv_kernel<<<dim3((B + 7) / 8, VLSA_D / 128), 128, 0, st>>>(ws.df, W, B, ws.dv);
+    VLSA_CUDA(cudaGetLastError());
+    delta_kernel<<<B, 256, 0, st>>>(ws.dv, O, P, ws.delta);
+    VLSA_CUDA(cudaGetLastError());
+
+    AggParams prm{};
+    prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
+    prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
+    prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta;
+    int rc = 0;
+    VLSA_DISPATCH_P(P, {
+        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, true, float>(prm, st);
+        else rc = launch_agg<kP, true, __nv_bfloat16>(prm, st);
+        if (rc) return rc;
+    });
+    merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ);
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
+                  float* out_A, void* stream) {
+    if (N == 0) return 0;
+    if (!X || !Q || !ml || !out_A || N < 0 || P < 1 || P > VLSA_MAX_P) return VLSA_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t(P) * VLSA_D + 32 * (P + 1)) * sizeof(float);
+    const unsigned grid = unsigned((N + 31) / 32);
+    if (x_dtype == VLSA_DTYPE_F32) {
+        row_cosine_kernel<float, 0><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale,
+                                                              nullptr, ml, out_A);
+    } else if (x_dtype == VLSA_DTYPE_BF16) {
+        row_cosine_kernel<__nv_bfloat16, 0><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P,
+                                                                      coattn_scale, nullptr, ml, out_A);
+    } else {
+        return VLSA_EUNSUPPORTED;
+    }
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_surv_loss_fwd_bwd(const float* logits, const int64_t* t, const int64_t* e, int B, int R,
+                           const float* logit_scale, float w_ifmle, float w_emd, float alpha, float eps,
+                           float inv_norm, float* out_loss, float* out_if, float* out_dlogits,
+                           float* out_per_sample, void* stream) {
+    if (!logits || !t || !e || !logit_scale || !out_loss || !out_per_sample) return VLSA_EINVAL;
+    if (B < 1 || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    surv_loss_kernel<<<(B + 3) / 4, 128, 0, st>>>(logits, reinterpret_cast<const long long*>(t),
+                                                  reinterpret_cast<const long long*>(e), B, R, logit_scale, w_ifmle,
+                                                  w_emd, alpha, eps, inv_norm, out_if, out_dlogits, out_per_sample);
+    VLSA_CUDA(cudaGetLastError());
+    surv_loss_reduce_kernel<<<1, 256, 0, st>>>(out_per_sample, B, w_ifmle, w_emd, inv_norm, out_loss);
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t vlsa_logit_pool_workspace_bytes(int64_t N, int R, int k) {
+    if (N < 0 || R < 1 || R > VLSA_MAX_R || k < 0) return 0;
+    return align_up(size_t(N) * R * sizeof(float), 256) + 512;
+}
+
+int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, int R, const float* logit_scale,
+                        int mode, int k, void* workspace, size_t workspace_bytes, float* out_logits,
+                        int64_t* out_pred, void* stream) {
+    if (!X || !T || !logit_scale || !workspace || !out_logits || !out_pred) return VLSA_EINVAL;
+    if (N < 1 || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
+    if (mode != VLSA_POOL_MEAN && mode != VLSA_POOL_TOPK) return VLSA_EINVAL;
+    if (mode == VLSA_POOL_TOPK && (k < 1 || k > 64)) return VLSA_EUNSUPPORTED;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    const size_t logits_bytes = align_up(size_t(N) * R * sizeof(float), 256);
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + logits_bytes + 4 > workspace_bytes) return VLSA_EWORKSPACE;
+    float* patch_logits = reinterpret_cast<float*>(base);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(base + logits_bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VLSA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const size_t smem = (size_t(R) * VLSA_D + 32 * (R + 1)) * sizeof(float);
+    const unsigned grid = unsigned((N + 31) / 32);
+    if (x_dtype == VLSA_DTYPE_F32) {
+        auto kern = row_cosine_kernel<float, 1>;
+        VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, T, R, 0.f, logit_scale, nullptr, patch_logits);
+    } else if (x_dtype == VLSA_DTYPE_BF16) {
+        auto kern = row_cosine_kernel<__nv_bfloat16, 1>;
+        VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, T, R, 0.f, logit_scale, nullptr,
+                                      patch_logits);
+    } else {
+        return VLSA_EUNSUPPORTED;
+    }
+    VLSA_CUDA(cudaGetLastError());
+    logit_pool_kernel<<<R, 1024, 0, st>>>(patch_logits, N, R, mode, k, out_logits,
+                                          reinterpret_cast<long long*>(out_pred), counter);
     VLSA_CUDA(cudaGetLastError());
     return 0;
 }

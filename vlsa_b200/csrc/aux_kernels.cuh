@@ -1,0 +1,170 @@
+// Secondary consumers of the path:
+//  * attention read-out A[P,N] (ret_with_attn=True, model/deepmil.py:206-213; used by
+//    utils/model_inference.py:118-131),
+//  * the zero-shot arm: per-patch logits + logit pooling (model/vlsa.py:189-196, model/deepmil.py:16-37).
+#pragma once
+#include "common.cuh"
+
+namespace vlsa {
+
+template <typename XT>
+__device__ __forceinline__ void load_row16(const XT* __restrict__ row, int lane, float (&x)[16]);
+
+// lane holds x[j*128 + lane*4 + k], j=0..3, k=0..3  (fp32)
+template <>
+__device__ __forceinline__ void load_row16<float>(const float* __restrict__ row, int lane, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row + j * 128 + lane * 4));
+        x[4 * j + 0] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+    }
+}
+// lane holds x[j*256 + lane*8 + k], j=0..1, k=0..7  (bf16)
+template <>
+__device__ __forceinline__ void load_row16<__nv_bfloat16>(const __nv_bfloat16* __restrict__ row, int lane, float (&x)[16]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + j * 256 + lane * 8));
+        x[8 * j + 0] = bf16_lo(u.x); x[8 * j + 1] = bf16_hi(u.x); x[8 * j + 2] = bf16_lo(u.y); x[8 * j + 3] = bf16_hi(u.y);
+        x[8 * j + 4] = bf16_lo(u.z); x[8 * j + 5] = bf16_hi(u.z); x[8 * j + 6] = bf16_lo(u.w); x[8 * j + 7] = bf16_hi(u.w);
+    }
+}
+// feature index of register slot i for the two layouts above
+template <typename XT>
+__device__ __forceinline__ int slot_col(int lane, int i) {
+    return sizeof(XT) == 4 ? (i >> 2) * 128 + lane * 4 + (i & 3) : (i >> 3) * 256 + lane * 8 + (i & 7);
+}
+
+// Normalise `nq` rows of `src` [nq, D] into shared memory `dst` (row-major), whole block cooperates.
+__device__ __forceinline__ void load_normalized_rows(const float* __restrict__ src, int nq, float* dst) {
+    constexpr int D = VLSA_D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = warp; r < nq; r += nw) {
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) { const float v = __ldg(src + size_t(r) * D + d); ss += v * v; }
+        ss = warp_sum(ss);
+        const float inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+        for (int d = lane; d < D; d += 32) dst[r * D + d] = __ldg(src + size_t(r) * D + d) * inv;
+    }
+}
+
+// cos[n][q] * mult for one bag; block = 256 threads = 8 warps x 4 rows = 32 rows per block.
+// MODE 0: A[q][n] = exp(scale*cos - m_q) / l_q          (attention read-out, out is [nq, N])
+// MODE 1: out[n][q] = mult * cos                        (per-patch logits, out is [N, nq])
+template <typename XT, int MODE>
+__global__ void __launch_bounds__(256) row_cosine_kernel(const XT* __restrict__ X, long long N, const float* __restrict__ Qsrc,
+                                                         int nq, float mult, const float* __restrict__ mult_log,
+                                                         const float* __restrict__ ml, float* __restrict__ out) {
+    constexpr int D = VLSA_D;
+    extern __shared__ __align__(16) float s_q[];            // [nq][D] + [32][nq+1] staging
+    float* s_out = s_q + size_t(nq) * D;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_normalized_rows(Qsrc, nq, s_q);
+    __syncthreads();
+    if (mult_log) mult = expf(*mult_log);
+    const long long row0 = (long long)blockIdx.x * 32;
+    for (int rr = 0; rr < 4; ++rr) {
+        const long long n = row0 + warp * 4 + rr;
+        if (n >= N) break;                                   // warp-uniform
+        float x[16];
+        load_row16<XT>(X + n * D, lane, x);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ss += x[i] * x[i];
+        ss = warp_sum(ss);
+        const float inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+        for (int q = 0; q < nq; ++q) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a += x[i] * s_q[q * D + slot_col<XT>(lane, i)];
+            a = warp_sum(a);
+            if (lane == 0) s_out[(warp * 4 + rr) * (nq + 1) + q] = a * inv;
+        }
+    }
+    __syncthreads();
+    const int nrows = (N - row0) < 32 ? int(N - row0) : 32;
+    if (MODE == 0) {
+        for (int i = tid; i < nq * 32; i += 256) {
+            const int q = i >> 5, r = i & 31;
+            if (r < nrows)
+                out[size_t(q) * N + row0 + r] = expf(mult * s_out[r * (nq + 1) + q] - ml[q * 2]) / ml[q * 2 + 1];
+        }
+    } else {
+        for (int i = tid; i < nrows * nq; i += 256) {
+            const int r = i / nq, q = i % nq;
+            out[size_t(row0 + r) * nq + q] = (mult * s_out[r * (nq + 1) + q]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// logit pooling over N per class (deepmil.py:16-37).  grid R, 1024 threads.
+//   mode 0: mean over N;  mode 1: mean of the top-min(k,N) values (values only: ties are harmless).
+// Then (last block done) preds = argmax_r pooled (first maximal index, torch.argmax semantics).
+__global__ void __launch_bounds__(1024) logit_pool_kernel(const float* __restrict__ logits, long long N, int R, int mode,
+                                                          int k, float* __restrict__ pooled, long long* __restrict__ pred,
+                                                          unsigned int* __restrict__ done_counter) {
+    __shared__ float s_val[32];
+    __shared__ long long s_idx[32];
+    __shared__ float s_top[64];
+    __shared__ long long s_sel[64];
+    __shared__ bool s_last;
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float result;
+    if (mode == 0) {
+        float a = 0.f;
+        for (long long n = tid; n < N; n += 1024) a += logits[n * R + r];
+        a = block_sum(a, s_val);
+        result = a / float(N);
+    } else {
+        const int kk = (long long)k < N ? k : int(N);
+        for (int j = 0; j < kk; ++j) {
+            float best = -INFINITY; long long bi = -1;
+            for (long long n = tid; n < N; n += 1024) {
+                bool taken = false;
+                for (int q = 0; q < j; ++q) taken |= (s_sel[q] == n);
+                const float v = logits[n * R + r];
+                if (!taken && (v > best || bi < 0)) { best = v; bi = n; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+            }
+            __syncthreads();
+            if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+            __syncthreads();
+            if (warp == 0) {
+                best = s_val[lane]; bi = s_idx[lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (oi >= 0 && (bi < 0 || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+                }
+                if (lane == 0) { s_top[j] = best; s_sel[j] = bi; }
+            }
+            __syncthreads();
+        }
+        float a = 0.f;
+        for (int j = 0; j < kk; ++j) a += s_top[j];        // descending order, like values.mean(dim=0)
+        result = a / float(kk);
+    }
+    if (tid == 0) {
+        pooled[r] = result;
+        __threadfence();
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        s_last = (prev == unsigned(R - 1));
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        int best = 0; float bv = *((volatile float*)pooled);
+        for (int q = 1; q < R; ++q) { const float v = ((volatile float*)pooled)[q]; if (v > bv) { bv = v; best = q; } }
+        *pred = best;
+        *done_counter = 0;          // re-arm for the next call on this workspace
+    }
+}
+
+}  // namespace vlsa

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict_
     if (blockIdx.y == 0 && tid < P) {
         out_ml[(size_t(b) * P + tid) * 2 + 0] = s_mx[tid];
         float lt = 0.f;
+#pragma unroll
         for (int p = 0; p < P; ++p) if (p == tid) lt = l[p];
         out_ml[(size_t(b) * P + tid) * 2 + 1] = lt;
     }
@@ -154,6 +155,177 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
         const float sum = warp_sum(e);
         if (lane < R) out_if[size_t(b) * R + lane] = e / sum;
     }
+}
+
+}  // namespace vlsa
+
+// ================================================================================================
+// Backward of the head (autograd of model/vlsa.py:185-192 + deepmil.py:117,136,204).
+// ================================================================================================
+namespace vlsa {
+
+// per bag: dg = ls * dlogits @ Tn (+ external dg); df = (dg - g (g.dg)) / |f|; dls_part = sum_r dlogits_r logits_r
+// grid B, 256 threads.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ f, const float* __restrict__ g,
+                                                       const float* __restrict__ T, int R,
+                                                       const float* __restrict__ logit_scale,
+                                                       const float* __restrict__ logits,
+                                                       const float* __restrict__ d_logits,
+                                                       const float* __restrict__ d_g_ext, float* __restrict__ df,
+                                                       float* __restrict__ dls_part) {
+    constexpr int D = VLSA_D;
+    __shared__ float s_tinv[VLSA_MAX_R];
+    __shared__ float s_dl[VLSA_MAX_R];
+    __shared__ float s_red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float ls = expf(*logit_scale);
+    for (int r = warp; r < R; r += 8) {
+        float tt = 0.f;
+        for (int k = lane; k < D; k += 32) { const float t = T[size_t(r) * D + k]; tt += t * t; }
+        tt = warp_sum(tt);
+        if (lane == 0) s_tinv[r] = 1.f / fmaxf(sqrtf(tt), VLSA_NORM_EPS);
+    }
+    if (tid < R) s_dl[tid] = d_logits[size_t(b) * R + tid];
+    __syncthreads();
+    float dg[2], gv[2], fv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int d = tid + h * 256;
+        float a = 0.f;
+        for (int r = 0; r < R; ++r) a += s_dl[r] * (T[size_t(r) * D + d] * s_tinv[r]);
+        dg[h] = ls * a + (d_g_ext ? d_g_ext[size_t(b) * D + d] : 0.f);
+        gv[h] = g[size_t(b) * D + d];
+        fv[h] = f[size_t(b) * D + d];
+    }
+    const float gdg = block_sum(gv[0] * dg[0] + gv[1] * dg[1], s_red);
+    const float ff = block_sum(fv[0] * fv[0] + fv[1] * fv[1], s_red);
+    const float inv = 1.f / fmaxf(sqrtf(ff), VLSA_NORM_EPS);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) df[size_t(b) * D + tid + h * 256] = (dg[h] - gv[h] * gdg) * inv;
+    if (warp == 0) {
+        float a = lane < R ? s_dl[lane] * logits[size_t(b) * R + lane] : 0.f;
+        a = warp_sum(a);
+        if (lane == 0) dls_part[b] = a;
+    }
+}
+
+// dW[o][i] = sum_b df[b][o] v[b][i] ; db[o] = sum_b df[b][o].  grid D/8, 512 threads (thread = column i).
+__global__ void __launch_bounds__(512) adapter_bwd_dw_kernel(const float* __restrict__ df, const float* __restrict__ v,
+                                                             int B, float* __restrict__ dW, float* __restrict__ db) {
+    constexpr int D = VLSA_D, OT = 8, BT = 32;
+    __shared__ float s_df[BT][OT];
+    const int i = threadIdx.x, o0 = blockIdx.x * OT;
+    float acc[OT], accb = 0.f;
+#pragma unroll
+    for (int k = 0; k < OT; ++k) acc[k] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += BT) {
+        const int nb = (B - b0) < BT ? (B - b0) : BT;
+        __syncthreads();
+        if (i < nb * OT) s_df[i / OT][i % OT] = df[size_t(b0 + i / OT) * D + o0 + i % OT];
+        __syncthreads();
+        for (int bb = 0; bb < nb; ++bb) {
+            const float vv = v[size_t(b0 + bb) * D + i];
+#pragma unroll
+            for (int k = 0; k < OT; ++k) acc[k] += s_df[bb][k] * vv;
+            if (i < OT) accb += s_df[bb][i];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < OT; ++k) dW[size_t(o0 + k) * D + i] = acc[k];
+    if (i < OT) db[o0 + i] = accb;
+}
+
+// dv[b][i] = sum_o df[b][o] W[o][i].  grid (ceil(B/8), D/128), 128 threads (thread = column i, 8 bags).
+__global__ void __launch_bounds__(128) adapter_bwd_dv_kernel(const float* __restrict__ df, const float* __restrict__ W,
+                                                             int B, float* __restrict__ dv) {
+    constexpr int D = VLSA_D, BT = 8;
+    __shared__ float s_df[BT][D];
+    const int tid = threadIdx.x, b0 = blockIdx.x * BT, i = blockIdx.y * 128 + tid;
+    const int nb = (B - b0) < BT ? (B - b0) : BT;
+    for (int k = tid; k < BT * D; k += 128) s_df[k / D][k % D] = (k / D < nb) ? df[size_t(b0 + k / D) * D + k % D] : 0.f;
+    __syncthreads();
+    float acc[BT];
+#pragma unroll
+    for (int k = 0; k < BT; ++k) acc[k] = 0.f;
+#pragma unroll 4
+    for (int o = 0; o < D; ++o) {
+        const float w = W[size_t(o) * D + i];
+#pragma unroll
+        for (int k = 0; k < BT; ++k) acc[k] += s_df[k][o] * w;
+    }
+#pragma unroll
+    for (int k = 0; k < BT; ++k) if (k < nb) dv[size_t(b0 + k) * D + i] = acc[k];
+}
+
+// delta[b][p] = (dv_b . O_b,p) / P  (= dO_p . O_p with dO_p = dv / P).  grid B, 256 threads.
+__global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ dv, const float* __restrict__ O, int P,
+                                                    float* __restrict__ delta) {
+    constexpr int D = VLSA_D;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = warp; p < P; p += 8) {
+        float a = 0.f;
+        for (int k = lane; k < D; k += 32) a += dv[size_t(b) * D + k] * O[(size_t(b) * P + p) * D + k];
+        a = warp_sum(a);
+        if (lane == 0) delta[size_t(b) * P + p] = a / float(P);
+    }
+}
+
+// dTn[r] = ls * sum_b dlogits[b][r] g[b] ; dT[r] = (dTn - Tn (Tn.dTn)) / |T_r| ; block 0 also reduces dls.
+// grid R, 256 threads.
+__global__ void __launch_bounds__(256) text_bwd_kernel(const float* __restrict__ T, int R, const float* __restrict__ g,
+                                                       const float* __restrict__ d_logits, int B,
+                                                       const float* __restrict__ logit_scale,
+                                                       const float* __restrict__ dls_part, float* __restrict__ dT,
+                                                       float* __restrict__ dls) {
+    constexpr int D = VLSA_D;
+    __shared__ float s_red[32];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const float ls = expf(*logit_scale);
+    float acc[2] = {0.f, 0.f};
+    for (int b = 0; b < B; ++b) {
+        const float dl = d_logits[size_t(b) * R + r];
+        acc[0] += dl * g[size_t(b) * D + tid];
+        acc[1] += dl * g[size_t(b) * D + 256 + tid];
+    }
+    acc[0] *= ls; acc[1] *= ls;
+    const float t0 = T[size_t(r) * D + tid], t1 = T[size_t(r) * D + 256 + tid];
+    const float tt = block_sum(t0 * t0 + t1 * t1, s_red);
+    const float inv = 1.f / fmaxf(sqrtf(tt), VLSA_NORM_EPS);
+    const float tn0 = t0 * inv, tn1 = t1 * inv;
+    const float proj = block_sum(tn0 * acc[0] + tn1 * acc[1], s_red);
+    dT[size_t(r) * D + tid] = (acc[0] - tn0 * proj) * inv;
+    dT[size_t(r) * D + 256 + tid] = (acc[1] - tn1 * proj) * inv;
+    if (r == 0) {
+        float a = 0.f;
+        for (int b = tid; b < B; b += 256) a += dls_part[b];
+        a = block_sum(a, s_red);
+        if (tid == 0) *dls = a;
+    }
+}
+
+// dQn[p] = sum over all chunks of the partials (fixed order); dQ[p] = (dQn - Qn (Qn.dQn)) / |Q_p|.
+// grid P, 512 threads.
+__global__ void __launch_bounds__(512) merge_bwd_kernel(const float* __restrict__ part, int total_chunks, int P,
+                                                        const float* __restrict__ Q, float* __restrict__ dQ) {
+    constexpr int D = VLSA_D;
+    __shared__ float s_red[32];
+    const int p = blockIdx.x, d = threadIdx.x;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= total_chunks; c += 4) {
+        a0 += part[(size_t(c + 0) * P + p) * D + d];
+        a1 += part[(size_t(c + 1) * P + p) * D + d];
+        a2 += part[(size_t(c + 2) * P + p) * D + d];
+        a3 += part[(size_t(c + 3) * P + p) * D + d];
+    }
+    for (; c < total_chunks; ++c) a0 += part[(size_t(c) * P + p) * D + d];
+    const float dqn = (a0 + a1) + (a2 + a3);
+    const float q = Q[size_t(p) * D + d];
+    const float qq = block_sum(q * q, s_red);
+    const float inv = 1.f / fmaxf(sqrtf(qq), VLSA_NORM_EPS);
+    const float qn = q * inv;
+    const float proj = block_sum(qn * dqn, s_red);
+    dQ[size_t(p) * D + d] = (dqn - qn * proj) * inv;
 }
 
 }  // namespace vlsa

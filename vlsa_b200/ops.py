@@ -156,6 +156,7 @@ class _AggregateFn(torch.autograd.Function):
         need_bwd = any(t.requires_grad for t in (Q, W, bias, T, logit_scale))
         out = aggregate_forward_raw(X, plan, Qc, Wc, bc, Tc, lsc, need_bwd=need_bwd, scale=scale)
         ctx.plan, ctx.scale, ctx.need_bwd = plan, scale, need_bwd
+        ctx.set_materialize_grads(False)
         ctx.ws = out["_workspace"]
         if need_bwd:
             ctx.save_for_backward(X, Qc, Wc, Tc, lsc, out["v"], out["f"], out["g"], out["logits"], out["ml"], out["O"])
@@ -164,8 +165,9 @@ class _AggregateFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_logits, d_g, d_Tn, _d_if, _d_ml):
-        if d_Tn is not None and bool((d_Tn != 0).any()):
-            raise NotImplementedError("gradient through the returned normalised text features is not supported")
+        if d_Tn is not None:
+            raise NotImplementedError("gradient through the returned normalised text features is not supported; "
+                                      "differentiate through the logits")
         X, Q, W, T, ls, v, f, g, logits, ml, O = ctx.saved_tensors
         plan = ctx.plan
         L = _lib.lib()
@@ -222,14 +224,17 @@ class _SurvLossFn(torch.autograd.Function):
                                       loss.data_ptr(), inc.data_ptr(), dlog.data_ptr(), per.data_ptr(), _stream())
         _lib.check(rc, "vlsa_surv_loss_fwd_bwd")
         ctx.save_for_backward(dlog)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(inc, per)
         return loss[0], loss[1], loss[2], inc, per
 
     @staticmethod
     def backward(ctx, d_total, d_ifmle, d_emd, _a, _b):
         (dlog,) = ctx.saved_tensors
-        if (d_ifmle is not None and bool((d_ifmle != 0).any())) or (d_emd is not None and bool((d_emd != 0).any())):
+        if d_ifmle is not None or d_emd is not None:
             raise NotImplementedError("differentiate the total loss, not its components")
+        if d_total is None:
+            return (None,) * 9
         return dlog * d_total, None, None, None, None, None, None, None, None
 
 
