@@ -65,26 +65,37 @@ size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P);
  *   g = f/|f|; Tn = T/|T|; logits = (exp(logit_scale) g) @ Tn^T        (vlsa.py:185-192)
  *   IF = softmax(logits)                                               (utils/func.py:44)
  * X is read exactly once.  out_ml / out_O / out_v / out_f are what vlsa_agg_bwd needs later
- * (out_O may be NULL when no backward follows).  out_if and out_Tn may be NULL. */
+ * (out_O may be NULL when no backward follows).  out_if and out_Tn may be NULL.
+ * Encoder-only use (VLFAN.forward alone, deepmil.py:170-215): T = NULL stops after f; out_g, out_logits,
+ * out_if, out_Tn are then ignored. */
 int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
                  const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
                  float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream);
 
+/* Only the streaming kernel of vlsa_agg_fwd (the one launch that reads X): writes the per-chunk
+ * online-softmax partials into `workspace` and nothing else.  Exists so that the dominant kernel can be
+ * timed in isolation (bench.py roofline) and so that callers can overlap the epilogue themselves. */
+int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                         int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Backward of vlsa_agg_fwd w.r.t. (Q, W, bias, T, logit_scale) — what torch autograd computes for
  * model/vlsa.py:181-198 when `pred_loss.backward()` runs (runner/vlsa_handler.py:281).  X is data: no dX.
  * Second (and last) read of X: dQn_p = sum_n scale * A_pn (u_n - delta_p) x_n / |x_n| with
  * u_n = dv.x_n / P, delta_p = dv.O_p / P, A recomputed from the saved (max, sum) in `ml`.
  * v, f, g, logits, ml, O are the tensors vlsa_agg_fwd wrote; d_logits [B,R] is the incoming
- * gradient; d_g [B,D] (gradient w.r.t. the returned image features) may be NULL.
+ * gradient; d_g [B,D] (gradient w.r.t. the returned image features) and d_f [B,D] (gradient w.r.t. the
+ * adapter output) may be NULL.  Encoder-only use (VLFAN.forward alone): T = NULL, then d_f is required and
+ * f, g, logits, d_logits, dT, dlogit_scale are ignored.
  * Outputs are overwritten (not accumulated): dQ [P,D], dW [D,D], db [D], dT [R,D], dlogit_scale [1]. */
 int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
-                 void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db, float* dT,
-                 float* dlogit_scale, void* stream);
+                 const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
+                 float* dT, float* dlogit_scale, void* stream);
 
 /* Attention read-out of ONE bag: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1]
  * (`ret_with_attn=True`, model/deepmil.py:206-213).  ml [P,2] comes from vlsa_agg_fwd.  out_A is [P,N]. */
@@ -95,11 +106,13 @@ int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, 
  * (runner/vlsa_handler.py:241-258; loss/loss_surv.py:144-169 with alpha/eps; loss/loss_surv_ext.py:70-109
  * with p=2, raw distance, exp(logit_scale) detached).  t, e: int64 [B] (time bin, event indicator).
  * inv_norm = 1 / (number of samples the mean runs over; the GLOBAL batch when bags are sharded).
+ * input_is_prob = 1: `logits` already holds the incidence (the reference loss modules' own signature,
+ * loss_surv.py:144); the softmax is skipped and out_dlogits is the gradient w.r.t. that incidence.
  * out_loss [3] = (total, ifmle, emd); out_if [B,R] and out_dlogits [B,R] may be NULL;
  * out_per_sample [B,2] (ifmle_i, emd_i) is required (it is also the reduction scratch). */
 int vlsa_surv_loss_fwd_bwd(const float* logits, const int64_t* t, const int64_t* e, int B, int R,
                            const float* logit_scale, float w_ifmle, float w_emd, float alpha, float eps,
-                           float inv_norm, float* out_loss, float* out_if, float* out_dlogits,
+                           float inv_norm, int input_is_prob, float* out_loss, float* out_if, float* out_dlogits,
                            float* out_per_sample, void* stream);
 
 /* Zero-shot arm (model/vlsa.py:189-196 with FeatMIL identity, model/deepmil.py:16-37) for ONE bag:

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvlsa_b200.so")
+LIB_PATH = os.environ.get("VLSA_B200_LIB") or os.path.join(_HERE, "lib", "libvlsa_b200.so")
 
 _lib = None
 
@@ -25,16 +25,18 @@ _SIGNATURES = {
     "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "vlsa_agg_partial_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+                                       C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vlsa_agg_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                C.c_float, c_f32p, c_f32p, C.c_int, c_f32p,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
-                               c_f32p, c_f32p,
+                               c_f32p, c_f32p, c_f32p,
                                C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "vlsa_attn_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_float, c_f32p, c_f32p,
                                 C.c_void_p]),
     "vlsa_surv_loss_fwd_bwd": (C.c_int, [c_f32p, c_i64p, c_i64p, C.c_int, C.c_int, c_f32p, C.c_float, C.c_float,
-                                         C.c_float, C.c_float, C.c_float, c_f32p, c_f32p, c_f32p, c_f32p,
+                                         C.c_float, C.c_float, C.c_float, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p,
                                          C.c_void_p]),
     "vlsa_logit_pool_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "vlsa_logit_pool_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int,

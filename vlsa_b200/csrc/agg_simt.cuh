@@ -30,12 +30,21 @@ struct AggParams {
     const float* delta;         // [B, P]   dO_p . O_p
 };
 
+#ifndef VLSA_AGG_WARPS
+#define VLSA_AGG_WARPS 4
+#endif
+#ifndef VLSA_AGG_STAGES
+#define VLSA_AGG_STAGES 2
+#endif
+
 template <int P, bool BWD, typename XT>
 struct AggCfg {
     static constexpr int D = VLSA_D;
-    static constexpr int THREADS = 256;
-    static constexpr int TN = 32;                      // rows per tile (8 warps x 4 rows)
-    static constexpr int STAGES = 2;
+    static constexpr int NW = VLSA_AGG_WARPS;          // warps per CTA (several CTAs share an SM)
+    static constexpr int THREADS = 32 * NW;
+    static constexpr int TN = 4 * NW;                  // rows per tile (4 rows per warp in phase A)
+    static constexpr int CPT = D / THREADS;            // feature columns per thread in phase B
+    static constexpr int STAGES = VLSA_AGG_STAGES;
     static constexpr int NQ = BWD ? P + 1 : P;         // query rows resident in smem
     static constexpr int NRED = NQ + 1;                // + sum of squares
     static constexpr int PP = (P + 3) & ~3;            // weights per row, float4-padded
@@ -62,9 +71,11 @@ __device__ __forceinline__ void chunk_info(const AggParams& p, int c, int& bag, 
 }
 
 template <int P, bool BWD, typename XT>
-__global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
+__global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(const AggParams prm) {
     using C = AggCfg<P, BWD, XT>;
     constexpr int D = C::D, TN = C::TN, STAGES = C::STAGES, NQ = C::NQ, NRED = C::NRED, PP = C::PP, NV = C::NV;
+    constexpr int NW = C::NW, CPT = C::CPT;
+    static_assert(TN <= 32 && (CPT == 2 || CPT == 4), "phase S maps rows to lanes; phase B loads 8 or 16 bytes");
     constexpr bool BF16 = sizeof(XT) == 2;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -86,8 +97,8 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
         for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
         mbar_fence_init();
     }
-    // Qn = Q / max(||Q||, eps)  (deepmil.py:187): warp w normalises rows w, w+8
-    for (int p = warp; p < P; p += 8) {
+    // Qn = Q / max(||Q||, eps)  (deepmil.py:187): warp w normalises rows w, w+NW, ...
+    for (int p = warp; p < P; p += NW) {
         const float* q = prm.Q + size_t(p) * D;
         float ss = 0.f;
         for (int d = lane; d < D; d += 32) { const float v = __ldg(q + d); ss += v * v; }
@@ -124,9 +135,11 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
     };
     if (tid == 0) for (int s = 0; s < STAGES - 1; ++s) produce();
 
-    float acc2[P][2];
+    float acc2[P][CPT];
 #pragma unroll
-    for (int p = 0; p < P; ++p) { acc2[p][0] = 0.f; acc2[p][1] = 0.f; }
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) acc2[p][k] = 0.f;
 
     int it = 0;
     for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
@@ -216,9 +229,10 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
             }
             __syncthreads();
 
-            // ---------------- phase S: per-(row, p) weights; lane = row, warp handles p = warp, warp+8 ----
-            for (int p = warp; p < P; p += 8) {
-                const float dot = red[lane * NRED + p], ss = red[lane * NRED + NQ];
+            // ---------------- phase S: per-(row, p) weights; lane = row, warp handles p = warp, warp+NW ----
+            for (int p = warp; p < P; p += NW) {
+                const int rl = lane < TN ? lane : 0;
+                const float dot = red[rl * NRED + p], ss = red[rl * NRED + NQ];
                 const float nrm = fmaxf(sqrtf(ss), VLSA_NORM_EPS);
                 const bool live = lane < nvalid;
                 const float s = live ? prm.scale * (dot / nrm) : -INFINITY;
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
                     const float mn = fmaxf(mo, tmax);
                     const float w = expf(s - mn);
                     const float wsum = warp_sum(w);
-                    wt[lane * PP + p] = w;
+                    if (lane < TN) wt[lane * PP + p] = w;
                     if (lane == 0) {
                         const float a = expf(mo - mn);
                         s_alpha[p] = a;
@@ -237,34 +251,54 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
                     }
                 } else {
                     const float a = expf(s - s_m[p]) * s_l[p];                 // A_pn (deepmil.py:198)
-                    const float u = red[lane * NRED + P];                       // (dv . x_n) / P
-                    wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
+                    const float u = red[rl * NRED + P];                         // (dv . x_n) / P
+                    if (lane < TN) wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
                 }
             }
             __syncthreads();
 
-            // ---------------- phase B: acc2[p][:] (+)= sum_r w[r][p] * x[r][2*tid .. 2*tid+1] -------------
+            // ---------------- phase B: acc2[p][:] (+)= sum_r w[r][p] * x[r][CPT*tid .. CPT*tid+CPT-1] ---------
             if (!BWD) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) { const float a = s_alpha[p]; acc2[p][0] *= a; acc2[p][1] *= a; }
+                for (int p = 0; p < P; ++p) {
+                    const float a = s_alpha[p];
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) acc2[p][k] *= a;
+                }
             }
 #pragma unroll 4
             for (int r = 0; r < nvalid; ++r) {
-                float x0, x1;
+                float xv[CPT];
                 if (!BF16) {
-                    const float2 xv = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(xt) + size_t(r) * D + 2 * tid);
-                    x0 = xv.x; x1 = xv.y;
+                    const float* src = reinterpret_cast<const float*>(xt) + size_t(r) * D + CPT * tid;
+                    if (CPT == 4) {
+                        const float4 v4 = *reinterpret_cast<const float4*>(src);
+                        xv[0] = v4.x; xv[1] = v4.y; xv[CPT - 2] = v4.z; xv[CPT - 1] = v4.w;
+                    } else {
+                        const float2 v2 = *reinterpret_cast<const float2*>(src);
+                        xv[0] = v2.x; xv[1] = v2.y;
+                    }
                 } else {
-                    const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const __nv_bfloat16*>(xt) + size_t(r) * D + 2 * tid);
-                    x0 = bf16_lo(u); x1 = bf16_hi(u);
+                    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(xt) + size_t(r) * D + CPT * tid;
+                    if (CPT == 4) {
+                        const uint2 u = *reinterpret_cast<const uint2*>(src);
+                        xv[0] = bf16_lo(u.x); xv[1] = bf16_hi(u.x); xv[CPT - 2] = bf16_lo(u.y); xv[CPT - 1] = bf16_hi(u.y);
+                    } else {
+                        const uint32_t u = *reinterpret_cast<const uint32_t*>(src);
+                        xv[0] = bf16_lo(u); xv[1] = bf16_hi(u);
+                    }
                 }
 #pragma unroll
-                for (int k = 0; k < PP / 4; ++k) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wt + r * PP + 4 * k);
-                    if (4 * k + 0 < P) { acc2[4 * k + 0 < P ? 4 * k + 0 : 0][0] += w4.x * x0; acc2[4 * k + 0 < P ? 4 * k + 0 : 0][1] += w4.x * x1; }
-                    if (4 * k + 1 < P) { acc2[4 * k + 1 < P ? 4 * k + 1 : 0][0] += w4.y * x0; acc2[4 * k + 1 < P ? 4 * k + 1 : 0][1] += w4.y * x1; }
-                    if (4 * k + 2 < P) { acc2[4 * k + 2 < P ? 4 * k + 2 : 0][0] += w4.z * x0; acc2[4 * k + 2 < P ? 4 * k + 2 : 0][1] += w4.z * x1; }
-                    if (4 * k + 3 < P) { acc2[4 * k + 3 < P ? 4 * k + 3 : 0][0] += w4.w * x0; acc2[4 * k + 3 < P ? 4 * k + 3 : 0][1] += w4.w * x1; }
+                for (int k4 = 0; k4 < PP / 4; ++k4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(wt + r * PP + 4 * k4);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (4 * k4 + j < P) {
+#pragma unroll
+                            for (int k = 0; k < CPT; ++k) acc2[(4 * k4 + j < P) ? 4 * k4 + j : 0][k] += wv[j] * xv[k];
+                        }
+                    }
                 }
             }
 
@@ -273,8 +307,13 @@ __global__ void __launch_bounds__(256, 1) agg_simt_kernel(const AggParams prm) {
                 float* o = prm.part_O + size_t(c) * P * D;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    *reinterpret_cast<float2*>(o + size_t(p) * D + 2 * tid) = make_float2(acc2[p][0], acc2[p][1]);
-                    acc2[p][0] = 0.f; acc2[p][1] = 0.f;
+                    if (CPT == 4)
+                        *reinterpret_cast<float4*>(o + size_t(p) * D + CPT * tid) =
+                            make_float4(acc2[p][0], acc2[p][1], acc2[p][CPT - 2], acc2[p][CPT - 1]);
+                    else
+                        *reinterpret_cast<float2*>(o + size_t(p) * D + CPT * tid) = make_float2(acc2[p][0], acc2[p][1]);
+#pragma unroll
+                    for (int k = 0; k < CPT; ++k) acc2[p][k] = 0.f;
                 }
                 if (!BWD) {
                     __syncthreads();           // phase-B readers of s_alpha are done before the reset below

@@ -40,7 +40,7 @@ using namespace vlsa;
         default: return VLSA_EINVAL;                               \
     }
 
-static constexpr int kRowTile = 32;   // AggCfg::TN
+static constexpr int kRowTile = 4 * VLSA_AGG_WARPS;   // AggCfg::TN
 
 static int device_sm_count() {
     int dev = 0, sms = 0;
@@ -86,8 +86,11 @@ static int launch_agg(const AggParams& prm, cudaStream_t st) {
     using C = AggCfg<P, BWD, XT>;
     auto kern = agg_simt_kernel<P, BWD, XT>;
     VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
-    const int sms = device_sm_count();
-    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    int occ = 1;
+    VLSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM));
+    if (occ < 1) occ = 1;
+    const int slots = device_sm_count() * occ;          // persistent CTAs: every resident slot, no second wave
+    const int grid = prm.total_chunks < slots ? prm.total_chunks : slots;
     if (grid <= 0) return 0;
     kern<<<grid, C::THREADS, C::SMEM, st>>>(prm);
     return static_cast<int>(cudaGetLastError());
@@ -115,11 +118,15 @@ int vlsa_agg_plan(const int64_t* cu_rows_host, int B, int sm_count, int* chunk_r
         if (n < 0) return VLSA_EINVAL;
         total_tiles += (n + kRowTile - 1) / kRowTile;
     }
-    // aim at ~4 chunks per persistent CTA (tail balance) while keeping a partial (P*2 KB) small next
-    // to the chunk it summarises (>= 8 tiles = 512 KB of fp32 rows once the batch is large enough)
-    long long tiles_per_chunk = (total_tiles + 4LL * sm_count - 1) / (4LL * sm_count);
-    if (tiles_per_chunk < 1) tiles_per_chunk = 1;
-    if (tiles_per_chunk > 64) tiles_per_chunk = 64;
+    // ~12 chunks per SM (several persistent CTAs share an SM; a few chunks each for tail balance), but keep
+    // a chunk >= 8 row tiles so that its partial (P x 2 KB) stays small next to the rows it summarises;
+    // tiny problems fall back to one chunk per SM.
+    long long tiles_per_chunk = (total_tiles + 12LL * sm_count - 1) / (12LL * sm_count);
+    if (tiles_per_chunk < 8) {
+        const long long per_sm = total_tiles / sm_count;
+        tiles_per_chunk = per_sm < 8 ? (per_sm < 1 ? 1 : per_sm) : 8;
+    }
+    if (tiles_per_chunk > 128) tiles_per_chunk = 128;
     const int chunk_rows = int(tiles_per_chunk) * kRowTile;
     long long c = 0;
     for (int b = 0; b < B; ++b) {
@@ -144,11 +151,9 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
                  float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream) {
     if (B == 0) return 0;
-    if (!cu_rows || !chunk_start || !Q || !W || !bias || !T || !logit_scale || !out_v || !out_f || !out_g ||
-        !out_logits || !out_ml)
-        return VLSA_EINVAL;
-    if (B < 0 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R || chunk_rows <= 0 || chunk_rows % kRowTile ||
-        total_chunks < 0)
+    if (!cu_rows || !chunk_start || !Q || !W || !bias || !out_v || !out_f || !out_ml) return VLSA_EINVAL;
+    if (T && (!logit_scale || !out_g || !out_logits || R < 1 || R > VLSA_MAX_R)) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
     if (total_chunks > 0 && (!X || !workspace)) return VLSA_EINVAL;
@@ -174,22 +179,48 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     VLSA_CUDA(cudaGetLastError());
     adapter_fwd_kernel<<<VLSA_D / 4, 128, 0, st>>>(W, bias, out_v, B, out_f);
     VLSA_CUDA(cudaGetLastError());
-    head_fwd_kernel<<<B, 256, 0, st>>>(out_f, T, R, logit_scale, out_g, out_logits, out_if, out_Tn);
-    VLSA_CUDA(cudaGetLastError());
+    if (T) {
+        head_fwd_kernel<<<B, 256, 0, st>>>(out_f, T, R, logit_scale, out_g, out_logits, out_if, out_Tn);
+        VLSA_CUDA(cudaGetLastError());
+    }
     return 0;
+}
+
+int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                         int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (B == 0 || total_chunks == 0) return 0;
+    if (!X || !cu_rows || !chunk_start || !Q || !workspace) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
+        return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
+    AggParams prm{};
+    prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
+    prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = 0;
+    VLSA_DISPATCH_P(P, {
+        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
+        else rc = launch_agg<kP, false, __nv_bfloat16>(prm, st);
+    });
+    return rc;
 }
 
 int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
-                 void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db, float* dT,
-                 float* dlogit_scale, void* stream) {
-    if (!cu_rows || !chunk_start || !Q || !W || !T || !logit_scale || !v || !f || !g || !logits || !ml || !O ||
-        !d_logits || !dQ || !dW || !db || !dT || !dlogit_scale || !workspace)
+                 const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
+                 float* dT, float* dlogit_scale, void* stream) {
+    if (!cu_rows || !chunk_start || !Q || !W || !v || !ml || !O || !dQ || !dW || !db || !workspace) return VLSA_EINVAL;
+    if (T && (!logit_scale || !f || !g || !logits || !d_logits || !dT || !dlogit_scale || R < 1 || R > VLSA_MAX_R))
         return VLSA_EINVAL;
-    if (B < 1 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R || chunk_rows <= 0 || chunk_rows % kRowTile ||
-        total_chunks < 0)
+    if (!T && !d_f) return VLSA_EINVAL;
+    if (B < 1 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
     if (total_chunks > 0 && !X) return VLSA_EINVAL;
@@ -198,13 +229,17 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    head_bwd_kernel<<<B, 256, 0, st>>>(f, g, T, R, logit_scale, logits, d_logits, d_g, ws.df, ws.dls_part);
+    const float* df = d_f;
+    if (T) {
+        head_bwd_kernel<<<B, 256, 0, st>>>(f, g, T, R, logit_scale, logits, d_logits, d_g, d_f, ws.df, ws.dls_part);
+        VLSA_CUDA(cudaGetLastError());
+        text_bwd_kernel<<<R, 256, 0, st>>>(T, R, g, d_logits, B, logit_scale, ws.dls_part, dT, dlogit_scale);
+        VLSA_CUDA(cudaGetLastError());
+        df = ws.df;
+    }
+    adapter_bwd_dw_kernel<<<VLSA_D / 8, 512, 0, st>>>(df, v, B, dW, db);
     VLSA_CUDA(cudaGetLastError());
-    text_bwd_kernel<<<R, 256, 0, st>>>(T, R, g, d_logits, B, logit_scale, ws.dls_part, dT, dlogit_scale);
-    VLSA_CUDA(cudaGetLastError());
-    adapter_bwd_dw_kernel<<<VLSA_D / 8, 512, 0, st>>>(ws.df, v, B, dW, db);
-    VLSA_CUDA(cudaGetLastError());
-    adapter_bwd_dv_kernel<<<dim3((B + 7) / 8, VLSA_D / 128), 128, 0, st>>>(ws.df, W, B, ws.dv);
+    adapter_bwd_dv_kernel<<<dim3((B + 7) / 8, VLSA_D / 128), 128, 0, st>>>(df, W, B, ws.dv);
     VLSA_CUDA(cudaGetLastError());
     delta_kernel<<<B, 256, 0, st>>>(ws.dv, O, P, ws.delta);
     VLSA_CUDA(cudaGetLastError());
@@ -247,14 +282,15 @@ int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, 
 
 int vlsa_surv_loss_fwd_bwd(const float* logits, const int64_t* t, const int64_t* e, int B, int R,
                            const float* logit_scale, float w_ifmle, float w_emd, float alpha, float eps,
-                           float inv_norm, float* out_loss, float* out_if, float* out_dlogits,
+                           float inv_norm, int input_is_prob, float* out_loss, float* out_if, float* out_dlogits,
                            float* out_per_sample, void* stream) {
     if (!logits || !t || !e || !logit_scale || !out_loss || !out_per_sample) return VLSA_EINVAL;
     if (B < 1 || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     surv_loss_kernel<<<(B + 3) / 4, 128, 0, st>>>(logits, reinterpret_cast<const long long*>(t),
                                                   reinterpret_cast<const long long*>(e), B, R, logit_scale, w_ifmle,
-                                                  w_emd, alpha, eps, inv_norm, out_if, out_dlogits, out_per_sample);
+                                                  w_emd, alpha, eps, inv_norm, input_is_prob, out_if, out_dlogits,
+                                                  out_per_sample);
     VLSA_CUDA(cudaGetLastError());
     surv_loss_reduce_kernel<<<1, 256, 0, st>>>(out_per_sample, B, w_ifmle, w_emd, inv_norm, out_loss);
     VLSA_CUDA(cudaGetLastError());

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ logit_scale,
                                                        const float* __restrict__ logits,
                                                        const float* __restrict__ d_logits,
-                                                       const float* __restrict__ d_g_ext, float* __restrict__ df,
+                                                       const float* __restrict__ d_g_ext,
+                                                       const float* __restrict__ d_f_ext, float* __restrict__ df,
                                                        float* __restrict__ dls_part) {
     constexpr int D = VLSA_D;
     __shared__ float s_tinv[VLSA_MAX_R];
@@ -201,7 +202,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const float ff = block_sum(fv[0] * fv[0] + fv[1] * fv[1], s_red);
     const float inv = 1.f / fmaxf(sqrtf(ff), VLSA_NORM_EPS);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) df[size_t(b) * D + tid + h * 256] = (dg[h] - gv[h] * gdg) * inv;
+    for (int h = 0; h < 2; ++h) {
+        const size_t at = size_t(b) * D + tid + h * 256;
+        df[at] = (dg[h] - gv[h] * gdg) * inv + (d_f_ext ? d_f_ext[at] : 0.f);
+    }
     if (warp == 0) {
         float a = lane < R ? s_dl[lane] * logits[size_t(b) * R + lane] : 0.f;
         a = warp_sum(a);

@@ -27,7 +27,7 @@ __device__ __forceinline__ float warp_suffix_sum(float v, int lane) {
 __global__ void __launch_bounds__(128) surv_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ t_,
                                                         const long long* __restrict__ e_, int B, int R,
                                                         const float* __restrict__ logit_scale, float w_ifmle, float w_emd,
-                                                        float alpha, float eps, float inv_norm,
+                                                        float alpha, float eps, float inv_norm, int input_is_prob,
                                                         float* __restrict__ out_if, float* __restrict__ out_dlogits,
                                                         float* __restrict__ per_sample) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -43,13 +43,18 @@ __global__ void __launch_bounds__(128) surv_loss_kernel(const float* __restrict_
     const float x = live ? logits[size_t(i) * R + lane] : -INFINITY;
     const float mx = warp_max(x);
     const float ex = live ? expf(x - mx) : 0.f;
-    const float p = ex / warp_sum(ex);
+    const float sm = ex / warp_sum(ex);
+    // input_is_prob: the caller already applied the output converter (reference loss-module signature)
+    const float p = input_is_prob ? (live ? x : 0.f) : sm;
     if (out_if && live) out_if[size_t(i) * R + lane] = p;
 
     // ---- SurvIFMLE (loss_surv.py:153-160)
     const float cif = warp_incl_scan(p, lane);
     const float pt = __shfl_sync(0xffffffffu, p, t);
-    const float surv_t = 1.f - __shfl_sync(0xffffffffu, cif, t);
+    // 1 - CIF(t): with a softmax input sum(p) = 1, so the tail sum over r > t is the same number without the
+    // cancellation of 1 - cumsum (closer to the fp64 run of the reference when CIF(t) -> 1)
+    const float tail = warp_sum((live && lane > t) ? p : 0.f);
+    const float surv_t = input_is_prob ? 1.f - __shfl_sync(0xffffffffu, cif, t) : tail;
     const float unc = -(1.f - c) * logf(fmaxf(pt, eps));
     const float cen = -c * logf(fmaxf(surv_t, eps));
     const float l1 = (1.f - alpha) * (cen + unc) + alpha * unc;
@@ -81,7 +86,8 @@ __global__ void __launch_bounds__(128) surv_loss_kernel(const float* __restrict_
     // ---- back through the incidence softmax, mean reduction folded in (inv_norm)
     const float dp = w_ifmle * dp1 + w_emd * dp2;
     const float pd = warp_sum(p * dp);
-    if (out_dlogits && live) out_dlogits[size_t(i) * R + lane] = p * (dp - pd) * inv_norm;
+    if (out_dlogits && live)
+        out_dlogits[size_t(i) * R + lane] = (input_is_prob ? dp : p * (dp - pd)) * inv_norm;
     if (lane == 0) { per_sample[size_t(i) * 2] = l1; per_sample[size_t(i) * 2 + 1] = l2; }
 }
 

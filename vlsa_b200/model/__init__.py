@@ -1,0 +1,6 @@
+from .deepmil import VLFAN, FeatMIL, logit_pooling
+from .prompt_adapter import PromptAdapter
+from .utils import load_model
+from .vlsa import VLSA
+
+__all__ = ["VLSA", "VLFAN", "FeatMIL", "logit_pooling", "PromptAdapter", "load_model"]

@@ -1,0 +1,115 @@
+"""``VLSA`` on B200 — drop-in for model/vlsa.py:21-198 of liupei101/VLSA (hot path only).
+
+``forward(X)`` keeps the reference contract: ``X [1, N, 512]`` on the GPU ->
+``(logits [1, R], image_features [1, 512], text_features [R, 512])``, differentiable w.r.t.
+``logit_scale``, the visual adapter, the query residuals and whatever produced the text features.
+``forward_packed`` is the batched entry: one launch for a whole optimizer step of
+ragged bags, text features evaluated once.
+
+The language end (CoOp prompt learner + frozen CONCH text tower, model/prompt_encoder.py) is outside
+the accelerated path: its output enters as a tensor / callable (``text_features=``), exactly like the
+reference's own ``pretrained_text_features`` shortcut (model/vlsa.py:58-61,160-161).
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import deepmil
+from .prompt_adapter import PromptAdapter
+
+
+class VLSA(nn.Module):
+    def __init__(self, text_encoder_cfg=None, image_encoder_cfg=None, prompt_learner_cfg=None,
+                 pretrained_prompt_learner_cfg=None, info_prefix="VLSA-B200", *,
+                 text_features: torch.Tensor | Callable[[], torch.Tensor] | nn.Module | None = None,
+                 query_prompt_features: torch.Tensor | None = None, logit_scale_init: float = 4.6052,
+                 **kwargs) -> None:
+        super().__init__()
+        self.kwargs = kwargs
+        image_encoder_cfg = dict(image_encoder_cfg or {})
+        self.text_encoder_cfg = text_encoder_cfg
+        self.image_encoder_cfg = image_encoder_cfg
+        self.prompt_learner_cfg = prompt_learner_cfg
+        self.pmt_learner_name = (prompt_learner_cfg or {}).get("name", "CoOp")
+
+        # Vision end: same selection rule as model/utils_vl.py:129-137 (class looked up by cfg['name'])
+        enc_name = image_encoder_cfg.get("name", "VLFAN")
+        enc_cls = getattr(deepmil, enc_name, None)
+        if enc_cls is None:
+            raise NotImplementedError(f"image encoder {enc_name!r} is not part of the accelerated path")
+        self.mil_encoder = enc_cls(**{k: v for k, v in image_encoder_cfg.items() if k != "name"})
+
+        if enc_name == "VLFAN" and image_encoder_cfg.get("query", "Parameter") == "Text":
+            query_text_cfg = {k.split("query_text_")[-1]: v for k, v in image_encoder_cfg.items()
+                              if k.startswith("query_text")}                         # model/vlsa.py:82-87
+            query_text_cfg.update(num_prompts=image_encoder_cfg["num_query"],
+                                  load_negative_prompts=image_encoder_cfg.get("gated_query", False),
+                                  pretrained_prompt_features=query_prompt_features)
+            for drop in ("load_path", "load_idx"):
+                query_text_cfg.pop(drop, None)               # prototype sentences are encoded outside
+            self.mil_encoder.reset_query(PromptAdapter(None, **query_text_cfg))
+
+        # Language end: a tensor (frozen), a Parameter / module / callable (trainable elsewhere)
+        self._text_fn = None
+        if isinstance(text_features, nn.Module):
+            self.prompt_learner = text_features               # keeps reference attribute name for ckpt keys
+        elif callable(text_features) and not isinstance(text_features, torch.Tensor):
+            self._text_fn = text_features
+        elif text_features is not None:
+            self.register_buffer("pretrained_text_features", text_features.detach().clone().float(), persistent=False)
+
+        # CLIP-style learnable temperature (model/vlsa.py:102; CONCH initialises it at log(1/0.07)-ish;
+        # the shipped BLCA checkpoint holds 4.0309)
+        self.logit_scale = nn.Parameter(torch.tensor(float(logit_scale_init)))
+
+    # ---- reference API -------------------------------------------------------------------------
+    def forward_text_only(self):
+        if hasattr(self, "pretrained_text_features"):
+            return self.pretrained_text_features.clone()          # model/vlsa.py:160-161
+        if hasattr(self, "prompt_learner"):
+            return self.prompt_learner()
+        if self._text_fn is not None:
+            return self._text_fn()
+        raise RuntimeError("no source of ordinal prompt embeddings: pass text_features= to VLSA(...)")
+
+    def encode_instances(self, X):
+        return self.mil_encoder(X)
+
+    def get_logit_scale(self):
+        return self.logit_scale.exp()
+
+    def forward(self, X):
+        """X: one bag, [1, N, feat_dim] (model/vlsa.py:181-198)."""
+        if X.dim() != 3 or X.shape[0] != 1:
+            raise AssertionError("X must be [1, N, feat_dim]")       # deepmil.py:175
+        Xp = X[0].contiguous()
+        text_features = self.forward_text_only()
+        if isinstance(self.mil_encoder, deepmil.FeatMIL):
+            if Xp.shape[0] > 1 and self.mil_encoder.pooling not in ("mean", "max"):
+                _, pooled = ops.logit_pool(Xp, text_features.detach().contiguous(), self.logit_scale,
+                                           self.image_encoder_cfg["pooling"])
+                Tn = torch.nn.functional.normalize(text_features, dim=-1)
+                # image_features of the zero-shot arm are the N normalised patches; callers discard them
+                return pooled, None, Tn
+            raise NotImplementedError("FeatMIL with mean/max feature pooling is not on the accelerated path")
+        plan = ops.make_plan([Xp.shape[0]], Xp.device)
+        logits, g, Tn, _, _ = self._fused(Xp, plan, text_features)
+        return logits, g, Tn
+
+    # ---- batched entry -------------------------------------------------------------
+    def _fused(self, Xp, plan, text_features):
+        enc = self.mil_encoder
+        return ops.aggregate(Xp, plan, enc.get_query(), enc.visual_adapter.weight, enc.visual_adapter.bias,
+                             text_features, self.logit_scale, float(enc.get_coattn_logit_scale()))
+
+    def forward_packed(self, X_packed: torch.Tensor, plan: "ops.BagPlan", text_features: torch.Tensor | None = None):
+        """All bags of one step in one launch: X_packed [sum N_i, 512] + plan -> (logits [B,R], g [B,512], Tn,
+        incidence [B,R]).  Numerically identical to looping ``forward`` over the bags."""
+        if text_features is None:
+            text_features = self.forward_text_only()
+        logits, g, Tn, inc, _ = self._fused(X_packed, plan, text_features)
+        return logits, g, Tn, inc

@@ -147,6 +147,16 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
     return out
 
 
+def aggregate_partial_only(X, plan: BagPlan, Q, workspace: torch.Tensor, scale: float | None = None) -> None:
+    """Launch only the streaming kernel (vlsa_agg_partial_fwd); used to time the dominant kernel alone."""
+    rc = _lib.lib().vlsa_agg_partial_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+                                         plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
+                                         plan.total_chunks, Q.data_ptr(), Q.shape[0],
+                                         coattn_scale() if scale is None else float(scale), workspace.data_ptr(),
+                                         workspace.numel(), _stream())
+    _lib.check(rc, "vlsa_agg_partial_fwd")
+
+
 class _AggregateFn(torch.autograd.Function):
     """Differentiable w.r.t. (Q, W, bias, T, logit_scale).  X is data (the reference never asks for dX)."""
 
@@ -182,10 +192,65 @@ class _AggregateFn(torch.autograd.Function):
                             plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P,
                             coattn_scale() if ctx.scale is None else float(ctx.scale), W.data_ptr(), T.data_ptr(), R,
                             ls.data_ptr(), v.data_ptr(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), ml.data_ptr(),
-                            O.data_ptr(), d_logits.data_ptr(), _ptr(d_g), ctx.ws.data_ptr(), ctx.ws.numel(),
+                            O.data_ptr(), d_logits.data_ptr(), _ptr(d_g), None, ctx.ws.data_ptr(), ctx.ws.numel(),
                             dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), dT.data_ptr(), dls.data_ptr(), _stream())
         _lib.check(rc, "vlsa_agg_bwd")
         return None, None, dQ, dW, db, dT, dls, None
+
+
+class _EncodeFn(torch.autograd.Function):
+    """VLFAN.forward alone (deepmil.py:170-215): packed bags -> f [B, D]; differentiable w.r.t. (Q, W, bias)."""
+
+    @staticmethod
+    def forward(ctx, X, plan, Q, W, bias, scale):
+        L = _lib.lib()
+        Qc, Wc, bc = (t.detach().contiguous() for t in (Q, W, bias))
+        B, P = plan.num_bags, Qc.shape[0]
+        if X.dim() != 2 or X.shape[1] != D_FEAT or X.shape[0] != plan.total_rows:
+            raise ValueError(f"packed X must be [{plan.total_rows}, {D_FEAT}], got {tuple(X.shape)}")
+        if not (1 <= P <= MAX_P):
+            raise ValueError(f"num_query P={P} outside 1..{MAX_P}")
+        _check_cuda(X, "X", None)
+        for name, t in (("Q", Qc), ("W", Wc), ("bias", bc)):
+            _check_cuda(t, name)
+        f32 = dict(dtype=torch.float32, device=X.device)
+        v, f = torch.empty(B, D_FEAT, **f32), torch.empty(B, D_FEAT, **f32)
+        ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
+        ws = _workspace(plan, P, X.device)
+        sc = coattn_scale() if scale is None else float(scale)
+        rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+                            plan.chunk_rows, plan.total_chunks, Qc.data_ptr(), P, sc, Wc.data_ptr(), bc.data_ptr(),
+                            None, 0, None, ws.data_ptr(), ws.numel(), v.data_ptr(), f.data_ptr(), None, None, None,
+                            ml.data_ptr(), O.data_ptr(), None, _stream())
+        _lib.check(rc, "vlsa_agg_fwd")
+        ctx.plan, ctx.scale, ctx.ws = plan, sc, ws
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(X, Qc, Wc, v, ml, O)
+        ctx.mark_non_differentiable(ml)
+        return f, ml
+
+    @staticmethod
+    def backward(ctx, d_f, _d_ml):
+        if d_f is None:
+            return (None,) * 6
+        X, Q, W, v, ml, O = ctx.saved_tensors
+        plan = ctx.plan
+        P = Q.shape[0]
+        f32 = dict(dtype=torch.float32, device=X.device)
+        d_f = d_f.contiguous().float()
+        dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
+        rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+                                     plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows, plan.total_chunks,
+                                     Q.data_ptr(), P, ctx.scale, W.data_ptr(), None, 0, None, v.data_ptr(), None, None,
+                                     None, ml.data_ptr(), O.data_ptr(), None, None, d_f.data_ptr(), ctx.ws.data_ptr(),
+                                     ctx.ws.numel(), dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), None, None, _stream())
+        _lib.check(rc, "vlsa_agg_bwd")
+        return None, None, dQ, dW, db, None
+
+
+def encode(X, plan: BagPlan, Q, W, bias, scale: float | None = None):
+    """Fused VLFAN forward on a packed batch: returns (f [B,D], ml [B,P,2])."""
+    return _EncodeFn.apply(X, plan, Q, W, bias, scale)
 
 
 def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None):
@@ -210,7 +275,7 @@ def attention_scores(X, Q, ml, scale: float | None = None):
 
 class _SurvLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, t, e, logit_scale, w_ifmle, w_emd, alpha, eps, inv_norm):
+    def forward(ctx, logits, t, e, logit_scale, w_ifmle, w_emd, alpha, eps, inv_norm, input_is_prob):
         L = _lib.lib()
         B, R = logits.shape
         lg = logits.detach().contiguous().float()
@@ -221,7 +286,7 @@ class _SurvLossFn(torch.autograd.Function):
         per = torch.empty(B, 2, dtype=torch.float32, device=dev)
         rc = L.vlsa_surv_loss_fwd_bwd(lg.data_ptr(), t.data_ptr(), e.data_ptr(), B, R, logit_scale.data_ptr(),
                                       float(w_ifmle), float(w_emd), float(alpha), float(eps), float(inv_norm),
-                                      loss.data_ptr(), inc.data_ptr(), dlog.data_ptr(), per.data_ptr(), _stream())
+                                      int(bool(input_is_prob)), loss.data_ptr(), inc.data_ptr(), dlog.data_ptr(), per.data_ptr(), _stream())
         _lib.check(rc, "vlsa_surv_loss_fwd_bwd")
         ctx.save_for_backward(dlog)
         ctx.set_materialize_grads(False)
@@ -234,12 +299,12 @@ class _SurvLossFn(torch.autograd.Function):
         if d_ifmle is not None or d_emd is not None:
             raise NotImplementedError("differentiate the total loss, not its components")
         if d_total is None:
-            return (None,) * 9
-        return dlog * d_total, None, None, None, None, None, None, None, None
+            return (None,) * 10
+        return dlog * d_total, None, None, None, None, None, None, None, None, None
 
 
 def surv_loss(logits, t, e, logit_scale, w_ifmle: float = 1.0, w_emd: float = 1.0, alpha: float = 0.0,
-              eps: float = 1e-7, norm: int | None = None):
+              eps: float = 1e-7, norm: int | None = None, input_is_prob: bool = False):
     """softmax -> w_ifmle * SurvIFMLE + w_emd * SurvEMD with mean over ``norm`` samples (default: B), fused
     forward + gradient (runner/vlsa_handler.py:241-258, loss/loss_surv.py:144-169, loss/loss_surv_ext.py:70-109).
     ``logit_scale`` is the log-space parameter; SurvEMD uses exp(logit_scale).detach().
@@ -252,7 +317,7 @@ def surv_loss(logits, t, e, logit_scale, w_ifmle: float = 1.0, w_emd: float = 1.
         raise ValueError("t and e must have one entry per row of logits")
     ls = logit_scale.detach().reshape(()).float().contiguous()
     inv_norm = 1.0 / float(B if norm is None else norm)
-    return _SurvLossFn.apply(logits, t, e, ls, w_ifmle, w_emd, alpha, eps, inv_norm)
+    return _SurvLossFn.apply(logits, t, e, ls, w_ifmle, w_emd, alpha, eps, inv_norm, input_is_prob)
 
 
 def logit_pool(X, T, logit_scale, pooling: str):
