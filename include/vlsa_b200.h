@@ -123,6 +123,20 @@ int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, i
                         int mode, int k, void* workspace, size_t workspace_bytes, float* out_logits,
                         int64_t* out_pred, void* stream);
 
+/* Whole path with HOST buffers (what a caller holding CPU tensors — the reference's DataLoader output,
+ * dataset/PatchWSI.py:197-215 + runner/vlsa_handler.py:205,322-330 — would call): stage the packed bags
+ * X_host [total_rows, D] (pinned memory for a truly asynchronous copy) to the device on `stream_copy`,
+ * run vlsa_agg_fwd on `stream_compute` once the copy has landed, and copy the incidence [B,R] (and raw
+ * logits if out_logits_host != NULL) back to the host on `stream_compute`.  Parameters (Q, W, bias, T,
+ * logit_scale) are DEVICE pointers (they live on the GPU between calls).  Returns after enqueueing;
+ * synchronise `stream_compute` before reading the outputs.  `workspace` is device memory of at least
+ * vlsa_forward_host_workspace_bytes(total_rows, B, P, x_dtype) bytes. */
+size_t vlsa_forward_host_workspace_bytes(int64_t total_rows, int B, int P, int x_dtype);
+int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_host, int B, const float* Q, int P,
+                      float coattn_scale, const float* W, const float* bias, const float* T, int R,
+                      const float* logit_scale, void* workspace, size_t workspace_bytes, float* out_if_host,
+                      float* out_logits_host, void* stream_compute, void* stream_copy);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,6 +195,13 @@ def main():
     real = torch.load(os.path.join(args.ref, "assert/blca-test-WSI-TCGA-XF-A9ST.pt"), map_location="cpu").float()
     np.save(os.path.join(HERE, "blca_bag_A9ST.npy"), real.numpy())
 
+    # the shipped experiment config the host side must parse unchanged (a config file, not source)
+    import shutil
+    shutil.copyfile(os.path.join(args.ref, "config/IFMLE/tcga_blca/cfg_vlsa_conch.yaml"),
+                    os.path.join(HERE, "cfg_vlsa_conch.yaml"))
+    shutil.copyfile(os.path.join(args.ref, "assert/blca-train-VLSA/config.yaml"),
+                    os.path.join(HERE, "blca_train_config.yaml"))
+
     index = []
     # ---- case family 1: single bags, shapes x generators ----------------------------------
     cases = []

@@ -1,0 +1,211 @@
+"""GPU: the reference-facing Python API (VLSA / VLFAN / handler / loader / host-buffer entry) on top of the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_cases
+from golden_util import load_case, rebuild_inputs
+
+pytestmark = pytest.mark.gpu
+IF_TOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def build_net(pr, P, R, dev, encoder="VLFAN", pooling=None):
+    from vlsa_b200.model import VLSA
+    if encoder == "VLFAN":
+        img = dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, drop_rate=0.25, query="Text", num_query=P,
+                   gated_query=False, query_pooling="mean", pred_head="default", query_text_method="TaskRes",
+                   query_text_res_ratio=pr["res_ratio"])
+    else:
+        img = dict(name="FeatMIL", pooling=pooling)
+    net = VLSA({"name": "mahmoodlab/conch"}, img, {"name": "CoOp"}, text_features=pr["text_features"],
+               query_prompt_features=pr["prompt_features"], logit_scale_init=float(pr["logit_scale"]),
+               vlsa_api="CONCH", path_clip_model=None).to(dev)
+    if encoder == "VLFAN":
+        with torch.no_grad():
+            net.mil_encoder.Q.residual_features.copy_(pr["residual_features"])
+            net.mil_encoder.visual_adapter.weight.copy_(pr["W"])
+            net.mil_encoder.visual_adapter.bias.copy_(pr["b"])
+    return net
+
+
+@pytest.mark.parametrize("name", golden_cases("real_") + ["single_P12_R12_g1_N2798", "single_P7_R13_g0_N1000"])
+def test_vlsa_forward_module_matches_reference(name, dev):
+    """VLSA.forward(X[1,N,512]) -> (logits, image_features, text_features) and the handler's softmax (config 1)."""
+    case = load_case(name)
+    bags, pr, t, e = rebuild_inputs(name, case)
+    P, R = int(case["P"]), int(case["R"])
+    net = build_net(pr, P, R, dev)
+    X = bags[0].unsqueeze(0).to(dev)
+    logits, g, Tn = net(X)
+    assert logits.shape == (1, R) and g.shape == (1, 512) and Tn.shape == (R, 512)
+    inc = torch.softmax(logits, -1)
+    assert np.abs(inc.detach().cpu().numpy() - case["if_f64"]).max() <= IF_TOL
+    np.testing.assert_allclose(g.detach().cpu().numpy(), case["g_f64"], atol=2e-6)
+    np.testing.assert_allclose(Tn.detach().norm(dim=-1).cpu().numpy(), 1.0, atol=1e-6)
+    # encoder alone + attention (mil_encoder(X, ret_with_attn=True), utils/model_inference.py:118)
+    f, A = net.mil_encoder(X, ret_with_attn=True)
+    assert f.shape == (1, 512) and A.shape == (1, P, X.shape[1])
+    np.testing.assert_allclose(f.detach().cpu().numpy(), case["f_f64"], atol=5e-6, rtol=1e-5)
+    k = case["attn_head_f64"].shape[1]
+    np.testing.assert_allclose(A[0, :, :k].cpu().numpy(), case["attn_head_f64"], rtol=2e-4, atol=1e-9)
+    # gradients flow to the reference's trainable tensors
+    loss = logits.square().sum() + f.sum()
+    loss.backward()
+    for p in (net.logit_scale, net.mil_encoder.visual_adapter.weight, net.mil_encoder.visual_adapter.bias,
+              net.mil_encoder.Q.residual_features):
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+
+
+def test_encoder_only_backward_matches_autograd_of_oracle(dev):
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import synth
+    P = 8
+    pr = synth.make_params(P, P, 21)
+    X = synth.make_bag("g1", 3000, 77)
+    net = build_net(pr, P, P, dev)
+    f = net.mil_encoder(X.unsqueeze(0).to(dev))
+    wvec = torch.linspace(-1, 1, 512, device=dev)
+    (f * wvec).sum().backward()
+    res = pr["residual_features"].double().requires_grad_(True)
+    W = pr["W"].double().requires_grad_(True)
+    b = pr["b"].double().requires_grad_(True)
+    Q = O.task_res_query(pr["prompt_features"].double(), res, pr["res_ratio"])
+    f64 = O.vlfan_forward(X.double().unsqueeze(0), Q, W, b)
+    (f64 * wvec.cpu().double()).sum().backward()
+    for got, ref, what in ((net.mil_encoder.Q.residual_features.grad, res.grad, "dQ"),
+                           (net.mil_encoder.visual_adapter.weight.grad, W.grad, "dW"),
+                           (net.mil_encoder.visual_adapter.bias.grad, b.grad, "db")):
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= 2e-4 * ref.abs().max().item(), what
+
+
+@pytest.mark.parametrize("name", golden_cases("zeroshot_"))
+def test_zero_shot_module(name, dev):
+    case = load_case(name)
+    bags, pr, _, _ = rebuild_inputs(name, case)
+    n = bags[0].shape[0]
+    if n == 1:
+        pytest.skip("single-patch bags take the reference's non-pooled branch (logits.shape[0] == 1)")
+    net = build_net(pr, 1, int(case["R"]), dev, encoder="FeatMIL", pooling=str(case["pooling"]))
+    logits, _, Tn = net(bags[0].unsqueeze(0).to(dev))
+    np.testing.assert_allclose(logits.cpu().numpy(), case["logits_f32"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", golden_cases("batch_"))
+def test_handler_update_network_and_test_model(name, dev):
+    """`_update_network` (one optimizer step on ragged bags) and `test_model` against the reference golden."""
+    from vlsa_b200.runner import VLSAHandler
+    case = load_case(name)
+    bags, pr, t, e = rebuild_inputs(name, case)
+    P, R = int(case["P"]), int(case["R"])
+    net = build_net(pr, P, R, dev)
+    net.pretrained_text_features.requires_grad_(False)
+    cfg = dict(task="vlsa", arch="VLSA", net_output_converter="softmax", loss_type="SurvIFMLE-SurvEMD",
+               loss_survifmle_weight=1.0, loss_survemd_weight=1.0, opt_name="adam", opt_lr=2e-4, opt_weight_decay=1e-5,
+               bp_every_batch=32)
+    h = VLSAHandler(cfg, net, device=dev)
+    xs = [b.unsqueeze(0).to(dev) for b in bags]
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2).to(dev) for i in range(len(bags))]
+
+    # eval path first (parameters untouched): DataLoader-style iterable of (idx, (feats, coords), label)
+    loader = [(torch.tensor([[i]]), (xs[i], torch.zeros(1)), ys[i]) for i in range(len(bags))]
+    cltor = h.test_model(h.net, loader, "test", bags_per_launch=3)
+    assert np.abs(cltor["pred"]["y_hat"].numpy() - case["if_f64"]).max() <= IF_TOL
+    np.testing.assert_allclose(cltor["pred"]["raw_y_hat"].numpy(), case["logits_f64"], atol=2e-4, rtol=1e-5)
+    assert cltor["pred"]["uid"].tolist() == list(range(len(bags)))
+    h.net.train()
+
+    before = {k: v.detach().clone() for k, v in h.net.state_dict().items()}
+    loss, preds = h._update_network(xs, ys)
+    np.testing.assert_allclose(loss, case["loss_f64"], rtol=2e-5)
+    np.testing.assert_allclose(preds.numpy(), case["logits_f64"], atol=2e-4, rtol=1e-5)
+    # the reduced gradient bucket holds what the reference's autograd produced
+    named = [(n, p) for n, p in h.net.named_parameters() if p.requires_grad]
+    at = 0
+    got = {}
+    for (n, p), sz in zip(named, h.bucket.sizes):
+        got[n] = h.bucket.flat[at:at + sz].view_as(p).cpu().numpy()
+        at += sz
+    for key, ref in (("mil_encoder.Q.residual_features", case["d_residual_f64"]),
+                     ("mil_encoder.visual_adapter.bias", case["d_b_f64"]), ("logit_scale", case["d_logit_scale_f64"])):
+        assert np.abs(got[key] - ref).max() <= max(2e-4 * np.abs(ref).max(), 1e-7), key
+    assert np.abs(got["mil_encoder.visual_adapter.weight"][:8] - case["d_W_rows_f64"]).max() <= 2e-4 * np.abs(case["d_W_rows_f64"]).max()
+    # Adam moved every trainable tensor by at most lr per element
+    after = h.net.state_dict()
+    for k in ("logit_scale", "mil_encoder.visual_adapter.weight", "mil_encoder.Q.residual_features"):
+        delta = (after[k] - before[k]).abs().max().item()
+        assert 0 < delta <= 2e-4 * 1.01 + 1e-5 * 2e-4 * before[k].abs().max().item() + 1e-9, (k, delta)
+
+
+def test_forward_host_and_async_loader_match_device_path(dev):
+    """Host-buffer C-ABI entry and the pinned ring loader give bit-identical results to device-resident inputs."""
+    from vlsa_b200 import ops, synth
+    from vlsa_b200.dataset import AsyncBagLoader
+    P = R = 12
+    pr = synth.make_params(P, R, 4)
+    net = build_net(pr, P, R, dev).eval()
+    steps = []
+    for s in range(3):
+        sizes = [1000 + 37 * s, 1, 5000, 64 + s]
+        steps.append([synth.make_bag("g1", n, 300 + 10 * s + i) for i, n in enumerate(sizes)])
+    Q = net.mil_encoder.get_query().detach().contiguous()
+    W, b = net.mil_encoder.visual_adapter.weight.detach(), net.mil_encoder.visual_adapter.bias.detach()
+    T, ls = net.forward_text_only(), net.logit_scale.detach()
+    direct = []
+    for bags in steps:
+        X = torch.cat(bags, 0).to(dev)
+        plan = ops.make_plan([x.shape[0] for x in bags], dev)
+        direct.append(ops.aggregate_forward_raw(X, plan, Q, W, b, T, ls)["incidence"].cpu())
+    # (a) C-ABI host entry
+    copy_stream = torch.cuda.Stream()
+    for bags, ref in zip(steps, direct):
+        host = torch.cat(bags, 0).pin_memory()
+        out, _ = ops.forward_host(host, [x.shape[0] for x in bags], Q, W, b, T, ls, copy_stream=copy_stream)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    # (b) loader + module API
+    loader = AsyncBagLoader(((bags, None, None) for bags in steps), dev, depth=2)
+    got = []
+    with torch.no_grad():
+        for batch in loader:
+            batch.wait()
+            logits, g, Tn, inc = net.forward_packed(batch.X, batch.plan)
+            loader.release(batch)
+            got.append(inc.cpu())
+    assert len(got) == 3
+    for a, ref in zip(got, direct):
+        assert torch.equal(a, ref)
+    assert loader.h2d_bytes == sum(x.shape[0] for bags in steps for x in bags) * 512 * 4
+
+
+def test_loss_modules_keep_reference_signature(dev):
+    """SurvIFMLE / SurvEMD take the converted incidence (loss_surv.py:144, loss_surv_ext.py:70)."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200.loss import SurvEMD, SurvIFMLE, load_loss
+    case = load_case("loss_R12")
+    raw = torch.from_numpy(case["raw"])
+    t, e = torch.from_numpy(case["t"]), torch.from_numpy(case["e"])
+    p = torch.softmax(raw.to(dev), -1).requires_grad_(True)
+    ls = torch.tensor(float(case["logit_scale"]), device=dev)
+    fns = load_loss("vlsa", loss_type=["SurvIFMLE", "SurvEMD"], SurvIFMLE={}, SurvEMD={"p": 2})
+    l1 = fns["SurvIFMLE"](p, t.view(-1, 1).float().to(dev), e.view(-1, 1).float().to(dev))
+    l2 = fns["SurvEMD"](p, t.view(-1, 1).float().to(dev), e.view(-1, 1).float().to(dev), ls.exp())
+    (l1 + l2).backward()
+    p64 = torch.softmax(raw.double(), -1).requires_grad_(True)
+    r1 = O.surv_ifmle(p64, t, e)
+    r2 = O.surv_emd(p64, t, e, torch.tensor(float(case["logit_scale"]), dtype=torch.float64).exp())
+    (r1 + r2).backward()
+    np.testing.assert_allclose(l1.item(), r1.item(), rtol=1e-5)
+    np.testing.assert_allclose(l2.item(), r2.item(), rtol=1e-5)
+    ref = p64.grad.numpy()
+    assert np.abs(p.grad.cpu().numpy() - ref).max() <= 2e-4 * np.abs(ref).max()
+    assert isinstance(SurvIFMLE(reduction="sum"), torch.nn.Module) and isinstance(SurvEMD(), torch.nn.Module)
+    with pytest.raises(NotImplementedError):
+        SurvEMD(p=1)

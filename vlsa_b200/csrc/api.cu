@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "agg_simt.cuh"
 #include "head_kernels.cuh"
@@ -335,6 +336,83 @@ int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, i
                                           reinterpret_cast<long long*>(out_pred), counter);
     VLSA_CUDA(cudaGetLastError());
     return 0;
+}
+
+// ---- host-buffer entry ---------------------------------------------------------------------------
+struct HostWs {
+    void* X; long long* cu_rows; int* chunk_start; void* agg; size_t agg_bytes;
+    float *v, *f, *g, *logits, *inc, *ml; size_t bytes;
+};
+static int max_chunks_bound(int B) { return 16 * device_sm_count() + B + 8; }
+static HostWs carve_host(void* base, int64_t total_rows, int B, int P, int esize) {
+    HostWs w; size_t off = 0;
+    auto take = [&](size_t nbytes) {
+        void* p = base ? static_cast<void*>(static_cast<char*>(base) + off) : nullptr;
+        off += align_up(nbytes ? nbytes : 1, 256);
+        return p;
+    };
+    w.X = take(size_t(total_rows) * VLSA_D * esize);
+    w.cu_rows = static_cast<long long*>(take(size_t(B + 1) * sizeof(long long)));
+    w.chunk_start = static_cast<int*>(take(size_t(B + 1) * sizeof(int)));
+    w.agg_bytes = carve(nullptr, max_chunks_bound(B), B, P).bytes + 256;
+    w.agg = take(w.agg_bytes);
+    w.v = static_cast<float*>(take(size_t(B) * VLSA_D * 4));
+    w.f = static_cast<float*>(take(size_t(B) * VLSA_D * 4));
+    w.g = static_cast<float*>(take(size_t(B) * VLSA_D * 4));
+    w.logits = static_cast<float*>(take(size_t(B) * VLSA_MAX_R * 4));
+    w.inc = static_cast<float*>(take(size_t(B) * VLSA_MAX_R * 4));
+    w.ml = static_cast<float*>(take(size_t(B) * VLSA_MAX_P * 2 * 4));
+    w.bytes = off;
+    return w;
+}
+
+size_t vlsa_forward_host_workspace_bytes(int64_t total_rows, int B, int P, int x_dtype) {
+    if (total_rows < 0 || B < 0 || P < 1 || P > VLSA_MAX_P) return 0;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return 0;
+    return carve_host(nullptr, total_rows, B, P, x_dtype == VLSA_DTYPE_F32 ? 4 : 2).bytes + 256;
+}
+
+int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_host, int B, const float* Q, int P,
+                      float coattn_scale, const float* W, const float* bias, const float* T, int R,
+                      const float* logit_scale, void* workspace, size_t workspace_bytes, float* out_if_host,
+                      float* out_logits_host, void* stream_compute, void* stream_copy) {
+    if (B == 0) return 0;
+    if (!cu_rows_host || !Q || !W || !bias || !T || !logit_scale || !workspace || !out_if_host) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    const int esize = x_dtype == VLSA_DTYPE_F32 ? 4 : 2;
+    const int64_t total_rows = cu_rows_host[B];
+    if (total_rows < 0 || (total_rows > 0 && !X_host)) return VLSA_EINVAL;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    HostWs ws = carve_host(reinterpret_cast<void*>(base), total_rows, B, P, esize);
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
+
+    int chunk_rows = 0;
+    int32_t* cs_host = static_cast<int32_t*>(malloc(size_t(B + 1) * sizeof(int32_t)));
+    if (!cs_host) return VLSA_EINVAL;
+    int rc = vlsa_agg_plan(cu_rows_host, B, 0, &chunk_rows, cs_host);
+    const int total_chunks = rc == 0 ? cs_host[B] : 0;
+    if (rc == 0 && total_chunks > max_chunks_bound(B)) rc = VLSA_EWORKSPACE;
+    cudaStream_t sc = static_cast<cudaStream_t>(stream_compute), sx = static_cast<cudaStream_t>(stream_copy);
+    cudaEvent_t landed = nullptr;
+    if (rc == 0) rc = static_cast<int>(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+    if (rc == 0 && total_rows > 0)
+        rc = static_cast<int>(cudaMemcpyAsync(ws.X, X_host, size_t(total_rows) * VLSA_D * esize, cudaMemcpyHostToDevice, sx));
+    // small pageable arrays: the runtime stages them before returning, so cs_host can be freed below
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(ws.cu_rows, cu_rows_host, size_t(B + 1) * 8, cudaMemcpyHostToDevice, sx));
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(ws.chunk_start, cs_host, size_t(B + 1) * 4, cudaMemcpyHostToDevice, sx));
+    if (rc == 0) rc = static_cast<int>(cudaEventRecord(landed, sx));
+    if (rc == 0) rc = static_cast<int>(cudaStreamWaitEvent(sc, landed, 0));
+    if (rc == 0)
+        rc = vlsa_agg_fwd(ws.X, x_dtype, reinterpret_cast<const int64_t*>(ws.cu_rows), ws.chunk_start, B, chunk_rows,
+                          total_chunks, Q, P, coattn_scale, W, bias, T, R, logit_scale, ws.agg, ws.agg_bytes, ws.v,
+                          ws.f, ws.g, ws.logits, ws.inc, ws.ml, nullptr, nullptr, sc);
+    if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(out_if_host, ws.inc, size_t(B) * R * 4, cudaMemcpyDeviceToHost, sc));
+    if (rc == 0 && out_logits_host)
+        rc = static_cast<int>(cudaMemcpyAsync(out_logits_host, ws.logits, size_t(B) * R * 4, cudaMemcpyDeviceToHost, sc));
+    if (landed) cudaEventDestroy(landed);      // deferred until the event has completed
+    free(cs_host);
+    return rc;
 }
 
 }  // extern "C"

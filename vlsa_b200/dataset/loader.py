@@ -40,7 +40,9 @@ def pack_bags(bags: Sequence[torch.Tensor], out: torch.Tensor | None = None) -> 
     D = flat[0].shape[1] if flat else ops.D_FEAT
     dtype = flat[0].dtype if flat else torch.float32
     if out is None or out.shape[0] < total or out.dtype != dtype:
-        out = torch.empty(max(total, 1), D, dtype=dtype).pin_memory()
+        out = torch.empty(max(total, 1), D, dtype=dtype)
+        if torch.cuda.is_available():
+            out = out.pin_memory()
     at = 0
     for b, n in zip(flat, sizes):
         out[at:at + n].copy_(b)

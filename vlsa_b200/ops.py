@@ -46,6 +46,8 @@ _SM_COUNT: dict[int, int] = {}
 
 
 def sm_count(device=None) -> int:
+    if device is not None and torch.device(device).type != "cuda":
+        return 148                      # planning only (host logic / CPU tests); kernels never run there
     idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
     if idx not in _SM_COUNT:
         _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
@@ -89,7 +91,9 @@ def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
                                   cs.ctypes.data_as(C.POINTER(C.c_int32)))
     _lib.check(rc, "vlsa_agg_plan")
     # one small pinned staging buffer -> async H2D on the current stream
-    stage = torch.empty(len(cu) * 2, dtype=torch.int64).pin_memory()
+    stage = torch.empty(len(cu) * 2, dtype=torch.int64)
+    if torch.device(device).type == "cuda":
+        stage = stage.pin_memory()
     stage[: len(cu)] = torch.from_numpy(cu)
     stage[len(cu):].view(torch.int32)[: len(cs)] = torch.from_numpy(cs)
     dev = stage.to(device, non_blocking=True)
@@ -343,3 +347,32 @@ def logit_pool(X, T, logit_scale, pooling: str):
                                ws.data_ptr(), ws.numel(), pooled.data_ptr(), pred.data_ptr(), _stream())
     _lib.check(rc, "vlsa_logit_pool_fwd")
     return pred, pooled
+
+
+def forward_host(X_host: torch.Tensor, bag_sizes, Q, W, bias, T, logit_scale, out_if_host: torch.Tensor | None = None,
+                 workspace: torch.Tensor | None = None, copy_stream: torch.cuda.Stream | None = None,
+                 scale: float | None = None, device=None):
+    """vlsa_forward_host: packed HOST bags (pinned for async copies) -> incidence on the HOST.  Enqueues the
+    H2D copy on `copy_stream`, the kernels and the D2H copy on the current stream; returns
+    (out_if_host [B,R], workspace) without synchronising."""
+    L = _lib.lib()
+    device = Q.device if device is None else torch.device(device)
+    sizes = np.asarray(list(bag_sizes), dtype=np.int64)
+    cu = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum(sizes, out=cu[1:])
+    B, P, R = len(sizes), Q.shape[0], T.shape[0]
+    if X_host.is_cuda or X_host.dim() != 2 or X_host.shape[1] != D_FEAT or X_host.shape[0] < int(cu[-1]):
+        raise ValueError("X_host must be a CPU tensor [>= total_rows, 512]")
+    code = _x_dtype_code(X_host)
+    need = L.vlsa_forward_host_workspace_bytes(int(cu[-1]), B, P, code)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(int(need), dtype=torch.uint8, device=device)
+    if out_if_host is None:
+        out_if_host = torch.empty(B, R, dtype=torch.float32).pin_memory()
+    cs = copy_stream.cuda_stream if copy_stream is not None else _stream()
+    rc = L.vlsa_forward_host(X_host.data_ptr(), code, cu.ctypes.data_as(C.POINTER(C.c_int64)), B, Q.data_ptr(), P,
+                             coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
+                             T.data_ptr(), R, logit_scale.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                             out_if_host.data_ptr(), None, _stream(), cs)
+    _lib.check(rc, "vlsa_forward_host")
+    return out_if_host, workspace

@@ -1,0 +1,99 @@
+"""Host-side pieces of the multi-GPU path: bags are independent, so they shard across
+ranks with NO data-path collective; per optimizer step there is exactly one exchange — an all-reduce
+(SUM) of one flat gradient bucket (+ the scalar loss riding in the same bucket).
+
+Everything here is device-agnostic torch.distributed code so that it is covered on CPU with gloo
+(tests/test_dist_gloo.py) and runs unchanged over NCCL / NVLink on the B200 box.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(sizes: Sequence[int], rank: int, world_size: int, balance: bool = True) -> list[int]:
+    """Indices of the bags rank `rank` processes out of one step's bags.
+
+    balance=False: round robin, bag i -> rank i mod world.
+    balance=True : longest-processing-time greedy on the row counts (deterministic: ties broken by index),
+                   so ragged bags (1k..100k rows) give every GPU about the same number of rows to stream.
+    Every rank computes the same assignment from the same `sizes`; no communication."""
+    n = len(sizes)
+    if world_size <= 1:
+        return list(range(n))
+    if not balance:
+        return [i for i in range(n) if i % world_size == rank]
+    order = sorted(range(n), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world_size
+    owner = [0] * n
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += int(sizes[i])
+    return [i for i in range(n) if owner[i] == rank]
+
+
+class FlatBucket:
+    """One contiguous fp32 buffer holding every trainable gradient (+ `extra` scalars at the tail).
+
+    `pack()` copies the .grad tensors in (zeros where a parameter got no gradient), `all_reduce()` sums
+    it over the ranks in ONE collective, `unpack()` writes the reduced gradients back.  For the BLCA model
+    this is 284 161 floats = 1.14 MB: latency-bound, so one bucket and one launch."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 1):
+        self.params = [p for p in params if p.requires_grad]
+        self.sizes = [p.numel() for p in self.params]
+        self.extra = extra
+        total = sum(self.sizes) + extra
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+
+    @property
+    def tail(self) -> torch.Tensor:
+        return self.flat[len(self.flat) - self.extra:]
+
+    def pack(self, extra_values: torch.Tensor | None = None) -> None:
+        at = 0
+        for p, n in zip(self.params, self.sizes):
+            if p.grad is None:
+                self.flat[at:at + n].zero_()
+            else:
+                self.flat[at:at + n].copy_(p.grad.reshape(-1))
+            at += n
+        if self.extra:
+            if extra_values is None:
+                self.tail.zero_()
+            else:
+                self.tail.copy_(extra_values.reshape(-1).to(self.flat.dtype))
+
+    def all_reduce(self) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+
+    def unpack(self) -> None:
+        at = 0
+        for p, n in zip(self.params, self.sizes):
+            g = self.flat[at:at + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            at += n
+
+
+def all_reduce_rows(local_rows: torch.Tensor, local_idx: Sequence[int], n_total: int) -> torch.Tensor:
+    """Assemble the [n_total, R] prediction matrix from every rank's rows (each row owned by one rank)."""
+    out = torch.zeros(n_total, local_rows.shape[-1], dtype=local_rows.dtype, device=local_rows.device)
+    if len(local_idx):
+        out[torch.as_tensor(list(local_idx), device=local_rows.device)] = local_rows
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)
+    return out

@@ -1,0 +1,205 @@
+"""``VLSAHandler`` on B200 — the call sites of the hot path (runner/vlsa_handler.py:87-151,189-345 and the
+bits of runner/base_handler.py they need), re-designed around one packed launch per optimizer step.
+
+Kept from the reference: the flat config keys (``cfg_vlsa_conch.yaml`` parses unchanged; prefixes routed
+like ``utils/func.py:136-147``), ``_update_network(xs, ys) -> (loss, preds)``, ``calc_objective_loss``,
+``test_model`` returning ``{'pred': {'y','raw_y_hat','y_hat','uid'}}``, Adam with decay / no-decay groups
+(optim/optim_factory.py:25-37), checkpoint = ``{'epoch','model','optimizer'}`` with the reference's
+state-dict key names.  Changed on purpose: the 32 bags of a step are ONE varlen launch, the
+text features are evaluated once per step instead of once per bag, and with torch.distributed initialised
+the bags shard across ranks with a single flat-bucket all-reduce per step.
+
+Out of scope here (use the reference's own code): wandb, csv split loading, SurvivalEVAL metrics.
+"""
+from __future__ import annotations
+
+import os
+from typing import Sequence
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from ..dataset.loader import pack_bags
+from ..loss import SurvObjective
+from ..model import VLSA
+from . import dist as vdist
+
+
+def fetch_kws(d: dict, prefix: str = "") -> dict:
+    """utils/func.py:136-147: strip `prefix_` from matching keys."""
+    if not prefix:
+        return dict(d)
+    pre = prefix + "_"
+    return {k[len(pre):]: v for k, v in d.items() if k.startswith(pre)}
+
+
+def create_output_converter(converter=None):
+    """utils/func.py:40-48."""
+    if converter == "sigmoid":
+        return torch.sigmoid
+    if converter == "softmax":
+        return lambda x: F.softmax(x, dim=-1)
+    return lambda x: x
+
+
+def param_groups_weight_decay(model: torch.nn.Module, weight_decay: float):
+    """optim/optim_factory.py:25-37: no weight decay on 1-D parameters and biases."""
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        if p.dim() <= 1 or name.endswith(".bias"):
+            no_decay.append(p)
+        else:
+            decay.append(p)
+    return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]
+
+
+class VLSAHandler:
+    def __init__(self, cfg: dict, net: VLSA | None = None, *, text_features=None, query_prompt_features=None,
+                 device=None, balance_shards: bool = True):
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        assert cfg.get("task", "vlsa") == "vlsa" and cfg.get("arch", "VLSA") == "VLSA"      # vlsa_handler.py:33-41
+        assert cfg.get("net_output_converter", "softmax") == "softmax", "VLSA needs the softmax converter"
+        if net is None:
+            img_cfg = fetch_kws(cfg, "vlsa_img_encoder")
+            txt_cfg = fetch_kws(cfg, "vlsa_txt_encoder")
+            pmt_name = cfg.get("vlsa_pmt_learner_name", "CoOp")
+            pmt_cfg = fetch_kws(cfg, "vlsa_pmt_learner_" + pmt_name.lower())
+            pmt_cfg["name"] = pmt_name
+            net = VLSA(txt_cfg, img_cfg, pmt_cfg, text_features=text_features,
+                       query_prompt_features=query_prompt_features, vlsa_api=cfg.get("vlsa_api", "CONCH"),
+                       path_clip_model=cfg.get("path_clip_model"))
+        self.net = net.to(self.device)
+        if cfg.get("vlsa_frozen_logit_scale", False):
+            self.net.logit_scale.requires_grad_(False)
+        if cfg.get("vlsa_img_encoder_frozen", False):
+            for p in self.net.mil_encoder.parameters():
+                p.requires_grad_(False)
+        # losses: 'SurvIFMLE-SurvEMD' with per-loss weights (cfg_vlsa_conch.yaml:102-105)
+        names = [n for n in str(cfg.get("loss_type", "SurvIFMLE-SurvEMD")).split("-") if n]
+        for n in names:
+            if n not in ("SurvIFMLE", "SurvEMD"):
+                raise NotImplementedError(f"loss {n} is not part of the accelerated VLSA path")
+        self.loss_weight = {n: float(cfg.get(f"loss_{n.lower()}_weight", 1.0)) for n in names}
+        self.objective = SurvObjective(self.loss_weight.get("SurvIFMLE", 0.0), self.loss_weight.get("SurvEMD", 0.0),
+                                       alpha=float(cfg.get("loss_survifmle_alpha", 0.0)))
+        self.output_converter = create_output_converter(cfg.get("net_output_converter", "softmax"))
+        assert cfg.get("opt_name", "adam") == "adam", "only Adam is wired (cfg_vlsa_conch.yaml:111)"
+        self.optimizer = torch.optim.Adam(param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5))),
+                                          lr=float(cfg.get("opt_lr", 2e-4)))
+        self.rank, self.world_size = vdist.world()
+        self.balance_shards = balance_shards
+        self.bucket = vdist.FlatBucket(self.net.parameters(), extra=1)
+
+    # ------------------------------------------------------------------------------------------------
+    def calc_objective_loss(self, raw_pred, label, norm: int | None = None):
+        """runner/vlsa_handler.py:241-258, fused: softmax + weighted SurvIFMLE + SurvEMD (+ gradient)."""
+        t, e = label[:, 0], label[:, 1]
+        total, _, _, _ = self.objective(raw_pred, t, e, self.net.logit_scale, norm=norm)
+        return total
+
+    def _pack_local(self, xs: Sequence[torch.Tensor], idx: Sequence[int]):
+        bags = [xs[i][0] if xs[i].dim() == 3 else xs[i] for i in idx]
+        sizes = [int(b.shape[0]) for b in bags]
+        if bags and not bags[0].is_cuda:
+            host, _ = pack_bags(bags)
+            X = host[: sum(sizes)].to(self.device, non_blocking=True)
+        elif bags:
+            X = torch.cat(bags, 0) if len(bags) > 1 else bags[0].contiguous()
+        else:
+            X = torch.empty(0, ops.D_FEAT, device=self.device)
+        return X, ops.make_plan(sizes, self.device)
+
+    def _update_network(self, xs, ys):
+        """One optimizer step on the bags `xs` (list of [1,N_i,512]) with labels `ys` (list of [1,2])."""
+        n_sample = len(xs)
+        sizes = [int(x.shape[-2]) for x in xs]
+        mine = vdist.shard_indices(sizes, self.rank, self.world_size, self.balance_shards)
+        self.optimizer.zero_grad(set_to_none=True)
+        bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
+        if mine:
+            X, plan = self._pack_local(xs, mine)
+            logits, _, _, _ = self.net.forward_packed(X, plan)                       # [B_local, R]
+            sel = torch.as_tensor(mine, device=self.device)
+            pred_loss = self.calc_objective_loss(logits, bag_label[sel], norm=n_sample)   # sum_local / n_sample
+            pred_loss.backward()
+            local_loss, local_pred = pred_loss.detach(), logits.detach()
+        else:
+            local_loss = torch.zeros((), device=self.device)
+            local_pred = torch.zeros(0, self.net.forward_text_only().shape[0], device=self.device)
+        # the one exchange of the step: gradients + loss in one flat bucket
+        self.bucket.pack(local_loss.reshape(1))
+        self.bucket.all_reduce()
+        self.bucket.unpack()
+        self.optimizer.step()
+        val_loss = float(self.bucket.tail[0])
+        val_preds = vdist.all_reduce_rows(local_pred, mine, n_sample).cpu()
+        return val_loss, val_preds
+
+    def _train_each_epoch(self, epoch, train_loader, name_loader="train"):
+        self.net.train()
+        bp_every_batch = int(self.cfg.get("bp_every_batch", 32))
+        all_raw_pred, all_gt, all_idx, losses = [], [], [], []
+        idx_c, x_c, y_c = [], [], []
+        num_samples = len(train_loader)
+        for i_batch, (data_idx, data_x, data_y) in enumerate(train_loader, start=1):
+            x_c.append(data_x[0])
+            y_c.append(data_y)
+            idx_c.append(data_idx)
+            if i_batch % bp_every_batch == 0 or i_batch == num_samples:
+                batch_loss, batch_pred = self._update_network(x_c, y_c)
+                losses.append(batch_loss)
+                all_raw_pred.append(batch_pred)
+                all_gt.append(torch.cat([y.reshape(1, 2) for y in y_c], dim=0).cpu())
+                all_idx.append(torch.cat([i.reshape(-1) for i in idx_c], dim=0).cpu())
+                idx_c, x_c, y_c = [], [], []
+        raw = torch.cat(all_raw_pred, 0)
+        return {"pred": {"y": torch.cat(all_gt, 0), "raw_y_hat": raw, "y_hat": self.output_converter(raw),
+                         "uid": torch.cat(all_idx, 0)}, "loss": losses}
+
+    @torch.no_grad()
+    def test_model(self, model, loader, loader_name="test", ckpt_path=None, bags_per_launch: int = 32):
+        """runner/vlsa_handler.py:315-345: every bag -> raw prediction + incidence; here `bags_per_launch` bags
+        share one launch and one evaluation of the text features."""
+        if ckpt_path is not None:
+            net_ckpt = torch.load(ckpt_path, map_location=self.device)
+            model.load_state_dict(net_ckpt["model"], strict=False)
+        model.eval()
+        all_idx, all_raw, all_pred, all_gt = [], [], [], []
+        T = model.forward_text_only()
+        buf_x, buf_y, buf_i = [], [], []
+
+        def flush():
+            if not buf_x:
+                return
+            X, plan = self._pack_local(buf_x, range(len(buf_x)))
+            logits, _, _, inc = model.forward_packed(X, plan, T)
+            all_raw.append(logits.cpu())
+            all_pred.append(inc.cpu())
+            all_gt.extend(buf_y)
+            all_idx.extend(buf_i)
+            buf_x.clear(); buf_y.clear(); buf_i.clear()
+
+        for data_idx, data_x, data_y in loader:
+            buf_x.append(data_x[0])
+            buf_y.append(data_y.reshape(1, 2).cpu())
+            buf_i.append(data_idx.reshape(-1).cpu())
+            if len(buf_x) == bags_per_launch:
+                flush()
+        flush()
+        return {"pred": {"y": torch.cat(all_gt, 0), "raw_y_hat": torch.cat(all_raw, 0),
+                         "y_hat": torch.cat(all_pred, 0), "uid": torch.cat(all_idx, 0)}}
+
+    # ---- checkpoint (runner/base_handler.py:641-682) ---------------------------------------------------
+    def save_model(self, path: str, epoch: int, module_filter: str | None = "prompt_encoder") -> None:
+        state = {k: v for k, v in self.net.state_dict().items() if not (module_filter and module_filter in k)}
+        if self.rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+            torch.save({"epoch": epoch, "model": state, "optimizer": self.optimizer.state_dict()}, path)
+
+    def load_model(self, path: str):
+        ckpt = torch.load(path, map_location=self.device)
+        return self.net.load_state_dict(ckpt["model"], strict=False)
