@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "agg_simt.cuh"
+#include "agg_tc.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
@@ -97,6 +98,43 @@ static int launch_agg(const AggParams& prm, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
+template <int NP>
+static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
+    using C = TcCfg<NP>;
+    auto kern = agg_tc_kernel<NP>;
+    VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+    const int sms = device_sm_count();
+    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    if (grid <= 0) return 0;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// Which streaming kernel serves the fp32 forward: the tcgen05 variant or the CUDA-core one.
+// VLSA_AGG_VARIANT=simt|tc overrides (development / cross-checking); default: see agg_use_tc().
+static bool agg_use_tc(int P, int x_dtype) {
+    static const int forced = [] {
+        const char* e = getenv("VLSA_AGG_VARIANT");
+        if (!e) return -1;
+        if (e[0] == 't') return 1;
+        if (e[0] == 's') return 0;
+        return -1;
+    }();
+    if (x_dtype != VLSA_DTYPE_F32) return false;
+    if (forced >= 0) return forced == 1;
+    return P > 4;
+}
+
+static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {
+    if (agg_use_tc(P, x_dtype)) return P <= 8 ? launch_agg_tc<8>(prm, P, st) : launch_agg_tc<16>(prm, P, st);
+    int rc = 0;
+    VLSA_DISPATCH_P(P, {
+        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
+        else rc = launch_agg<kP, false, __nv_bfloat16>(prm, st);
+    });
+    return rc;
+}
+
 extern "C" {
 
 int vlsa_version(void) { return 100; }
@@ -169,11 +207,9 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
 
-    int rc = 0;
+    int rc = launch_agg_fwd(prm, P, x_dtype, st);
+    if (rc) return rc;
     VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
-        else rc = launch_agg<kP, false, __nv_bfloat16>(prm, st);
-        if (rc) return rc;
         merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(ws.part_m, ws.part_l, ws.part_O, chunk_start,
                                                                      out_ml, out_O, out_v);
     });
@@ -203,12 +239,7 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, con
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = 0;
-    VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
-        else rc = launch_agg<kP, false, __nv_bfloat16>(prm, st);
-    });
-    return rc;
+    return launch_agg_fwd(prm, P, x_dtype, st);
 }
 
 int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
