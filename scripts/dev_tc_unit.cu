@@ -1,0 +1,226 @@
+// Dev harness (GPU box): unit checks of the tcgen05 forms used by agg_tc_kernel, one test per process
+// (an illegal descriptor kills the context).   usage: dev_tc_unit <test>
+//   ts    : D[128 x 32] = A[128 x 64] (fp16, in TMEM, written with tcgen05.st) . B[32 x 64]^T (fp16, K-major SW128)
+//   mix48 : D[128 x 48] = A^T, A = two [32(K) x 64(M)] planes fp16 MN-major SW128 (LBO 8192) . B[48 x 32]^T bf16 K-major SW128
+//   mix32 : same with N = 32          bf48: same as mix48 with bf16 A          f48: fp16 A and fp16 B
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include "../vlsa_b200/csrc/tc_common.cuh"
+using namespace vlsa;
+
+// ---------------------------------------------------------------------------------- TS test
+__global__ void __launch_bounds__(128) ts_test(const uint32_t* Apacked /*[128][32] packed fp16 pairs*/,
+                                               const __half* B /*[32][64]*/, float* Dout /*[128][32]*/) {
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    unsigned char* sB = raw + (base - smem_u32(raw));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base, 128);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tmem_base;
+    {   // A row = TMEM lane tid: 32 columns (64 fp16)
+        uint32_t v[32];
+        for (int i = 0; i < 32; ++i) v[i] = Apacked[tid * 32 + i];
+        tmem_st32(tm + (uint32_t(32 * warp) << 16), v);
+        tmem_wait_st();
+    }
+    for (int i = tid; i < 32 * 64; i += 128) {
+        const int r = i / 64, k = i % 64;
+        *reinterpret_cast<__half*>(sB + sw128_offset(r, k >> 3, (k & 7) * 2)) = B[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    if (tid == 0) {
+        constexpr uint32_t idesc = umma_idesc(UMMA_F16, UMMA_F16, 128, 32, false, false);
+        for (int ks = 0; ks < 4; ++ks)
+            tc_mma_ts(tm + 64, tm + ks * 8, umma_desc_sw128(smem_u32(sB) + ks * 32, 16, 1024), idesc, ks > 0);
+        tc_commit(&bar);
+    }
+    mbar_wait_wd(&bar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[8];
+        tmem_ld8(tm + 64 + 8 * cb + (uint32_t(32 * warp) << 16), r);
+        tmem_wait_ld();
+        for (int c = 0; c < 8; ++c) Dout[tid * 32 + 8 * cb + c] = __uint_as_float(r[c]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 128);
+}
+
+// ---------------------------------------------------------------------------------- mixed-format MN-major test
+__global__ void __launch_bounds__(128) mix_test(const uint16_t* X /*[2 planes][32 k][64 m]*/, const uint16_t* W /*[N][32]*/,
+                                                float* Dout /*[128][64]*/, int N, uint32_t idesc) {
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    unsigned char* sA = raw + (base - smem_u32(raw));      // two slots of 8192 B (plane 4096 used)
+    unsigned char* sB = sA + 16384;                          // N rows x 128 B
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tmem_base;
+    for (int i = tid; i < 2 * 32 * 64; i += 128) {
+        const int p = i / 2048, k = (i / 64) % 32, mm = i % 64;
+        *reinterpret_cast<uint16_t*>(sA + p * 8192 + sw128_offset(k, mm >> 3, (mm & 7) * 2)) = X[i];
+    }
+    for (int i = tid; i < N * 32; i += 128) {
+        const int r = i / 32, k = i % 32;
+        *reinterpret_cast<uint16_t*>(sB + sw128_offset(r, k >> 3, (k & 7) * 2)) = W[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    if (tid == 0) {
+        for (int ks = 0; ks < 2; ++ks)
+            tc_mma_ss(tm, umma_desc_sw128(smem_u32(sA) + ks * 2048, 8192, 1024),
+                      umma_desc_sw128(smem_u32(sB) + ks * 32, 16, 1024), idesc, ks > 0);
+        tc_commit(&bar);
+    }
+    mbar_wait_wd(&bar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < N / 16; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(tm + 16 * cb + (uint32_t(32 * warp) << 16), r);
+        tmem_wait_ld();
+        for (int c = 0; c < 16; ++c) Dout[tid * 64 + 16 * cb + c] = __uint_as_float(r[c]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 64);
+}
+
+
+// ---------------------------------------------------------------------------------- accumulator rounding probe
+// D preset to +-1.0; each step adds A[m][0] * B[n][0] = 2^-12 * (2^-12 (n+1)/4) = (n+1)/8 ulp(1.0)
+__global__ void __launch_bounds__(128) rz_test(float* Dout /*[2][128][32]*/, int steps) {
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    unsigned char* sB = raw + (base - smem_u32(raw));
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base, 128);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tmem_base;
+    for (int i = tid; i < 4096 / 4; i += 128) reinterpret_cast<uint32_t*>(sB)[i] = 0u;
+    __syncthreads();
+    if (tid < 32) *reinterpret_cast<__half*>(sB + sw128_offset(tid, 0, 0)) = __float2half(ldexpf(float(tid + 1) / 4.f, -12));
+    for (int sign = 0; sign < 2; ++sign) {
+        uint32_t v[32];
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        v[0] = __half_as_ushort(__float2half(ldexpf(1.f, -12)));     // A[m][0] = 2^-12, everything else 0
+        tmem_st32(tm + (uint32_t(32 * warp) << 16), v);
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(sign ? -1.f : 1.f);
+        tmem_st32(tm + 64 + (uint32_t(32 * warp) << 16), v);
+        tmem_wait_st();
+        fence_proxy_async_smem();
+        tc_fence_before(); __syncthreads(); tc_fence_after();
+        if (tid == 0) {
+            constexpr uint32_t idesc = umma_idesc(UMMA_F16, UMMA_F16, 128, 32, false, false);
+            for (int k = 0; k < steps; ++k)
+                tc_mma_ts(tm + 64, tm, umma_desc_sw128(smem_u32(sB), 16, 1024), idesc, 1u);
+            tc_commit(&bar);
+        }
+        mbar_wait_wd(&bar, sign);
+        tc_fence_after();
+        for (int cb = 0; cb < 4; ++cb) {
+            uint32_t r[8];
+            tmem_ld8(tm + 64 + 8 * cb + (uint32_t(32 * warp) << 16), r);
+            tmem_wait_ld();
+            for (int c = 0; c < 8; ++c) Dout[(sign * 128 + tid) * 32 + 8 * cb + c] = __uint_as_float(r[c]);
+        }
+        tc_fence_before(); __syncthreads(); tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tm, 128);
+}
+
+static float rnd() { return float(rand() % 2001 - 1000) / 500.f; }
+static uint16_t to16(float x, bool bf) {
+    if (bf) { __nv_bfloat16 b = __float2bfloat16(x); uint16_t u; memcpy(&u, &b, 2); return u; }
+    __half h = __float2half(x); uint16_t u; memcpy(&u, &h, 2); return u;
+}
+static float from16(uint16_t u, bool bf) {
+    if (bf) { __nv_bfloat16 b; memcpy(&b, &u, 2); return __bfloat162float(b); }
+    __half h; memcpy(&h, &u, 2); return __half2float(h);
+}
+
+int main(int argc, char** argv) {
+    const char* t = argc > 1 ? argv[1] : "ts";
+    srand(7);
+    if (!strcmp(t, "ts")) {
+        std::vector<uint32_t> A(128 * 32); std::vector<float> fA(128 * 64), fB(32 * 64); std::vector<__half> B(32 * 64);
+        for (int m = 0; m < 128; ++m) for (int c = 0; c < 32; ++c) {
+            const uint16_t lo = to16(rnd(), false), hi = to16(rnd(), false);
+            fA[m * 64 + 2 * c] = from16(lo, false); fA[m * 64 + 2 * c + 1] = from16(hi, false);
+            A[m * 32 + c] = uint32_t(lo) | (uint32_t(hi) << 16);
+        }
+        for (int i = 0; i < 32 * 64; ++i) { B[i] = __float2half(rnd()); fB[i] = __half2float(B[i]); }
+        uint32_t* dA; __half* dB; float* dD;
+        cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dD, 128 * 32 * 4);
+        cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
+        cudaMemset(dD, 0, 128 * 32 * 4);
+        ts_test<<<1, 128, 4096 + 1024>>>(dA, dB, dD);
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("[ts] kernel: %s\n", cudaGetErrorString(e));
+        if (e != cudaSuccess) return 1;
+        std::vector<float> Dh(128 * 32); cudaMemcpy(Dh.data(), dD, Dh.size() * 4, cudaMemcpyDeviceToHost);
+        double err = 0;
+        for (int m = 0; m < 128; ++m) for (int n = 0; n < 32; ++n) {
+            double ref = 0; for (int k = 0; k < 64; ++k) ref += double(fA[m * 64 + k]) * fB[n * 64 + k];
+            err = fmax(err, fabs(Dh[m * 32 + n] - ref));
+        }
+        printf("[ts] A in TMEM (lane = row, 2 fp16 per column, low half first): max err %.3e  (D[0][0..1] = %f %f)\n", err, Dh[0], Dh[1]);
+        return err < 1e-2 ? 0 : 2;
+    }
+    if (!strcmp(t, "rz")) {
+        float* dD; cudaMalloc(&dD, 2 * 128 * 32 * 4);
+        for (int steps : {1, 16}) {
+            rz_test<<<1, 128, 4096 + 1024>>>(dD, steps);
+            cudaError_t e = cudaDeviceSynchronize();
+            printf("[rz] steps=%d kernel: %s\n", steps, cudaGetErrorString(e));
+            if (e != cudaSuccess) return 1;
+            std::vector<float> Dh(2 * 128 * 32); cudaMemcpy(Dh.data(), dD, Dh.size() * 4, cudaMemcpyDeviceToHost);
+            for (int sign = 0; sign < 2; ++sign) {
+                printf("[rz]  D0=%+.0f, exact increment per step (n+1)/8 ulp; result - D0 in ulp(1)=2^-23, n=0..15:\n     ", sign ? -1.f : 1.f);
+                for (int n = 0; n < 16; ++n) printf("%.2f ", (double(Dh[(sign * 128) * 32 + n]) - (sign ? -1.0 : 1.0)) / ldexp(1.0, -23));
+                printf("\n");
+            }
+        }
+        return 0;
+    }
+    int N = 48; bool abf = false, bbf = true;
+    if (!strcmp(t, "mix32")) N = 32;
+    else if (!strcmp(t, "bf48")) abf = true;
+    else if (!strcmp(t, "f48")) bbf = false;
+    else if (strcmp(t, "mix48")) { printf("unknown test %s\n", t); return 3; }
+    std::vector<uint16_t> X(2 * 32 * 64), W(N * 32); std::vector<float> fX(X.size()), fW(W.size());
+    for (size_t i = 0; i < X.size(); ++i) { X[i] = to16(rnd(), abf); fX[i] = from16(X[i], abf); }
+    for (size_t i = 0; i < W.size(); ++i) { W[i] = to16(rnd(), bbf); fW[i] = from16(W[i], bbf); }
+    uint16_t *dX, *dW; float* dD;
+    cudaMalloc(&dX, X.size() * 2); cudaMalloc(&dW, W.size() * 2); cudaMalloc(&dD, 128 * 64 * 4);
+    cudaMemcpy(dX, X.data(), X.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dW, W.data(), W.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0, 128 * 64 * 4);
+    const uint32_t idesc = umma_idesc(abf ? UMMA_BF16 : UMMA_F16, bbf ? UMMA_BF16 : UMMA_F16, 128, N, true, false);
+    mix_test<<<1, 128, 16384 + 8192 + 1024>>>(dX, dW, dD, N, idesc);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("[%s] kernel: %s\n", t, cudaGetErrorString(e));
+    if (e != cudaSuccess) return 1;
+    std::vector<float> Dh(128 * 64); cudaMemcpy(Dh.data(), dD, Dh.size() * 4, cudaMemcpyDeviceToHost);
+    double err = 0;
+    for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+        double ref = 0; for (int k = 0; k < 32; ++k) ref += double(fX[(m / 64) * 2048 + k * 64 + (m % 64)]) * fW[n * 32 + k];
+        err = fmax(err, fabs(Dh[m * 64 + n] - ref));
+    }
+    printf("[%s] M=128 N=%d A %s MN-major (32-row planes), B %s: max err %.3e\n", t, N, abf ? "bf16" : "fp16", bbf ? "bf16" : "fp16", err);
+    return err < 1e-2 ? 0 : 2;
+}

@@ -42,7 +42,8 @@ using namespace vlsa;
         default: return VLSA_EINVAL;                               \
     }
 
-static constexpr int kRowTile = 4 * VLSA_AGG_WARPS;   // AggCfg::TN
+static constexpr int kRowTile = 32;   // TcCfg::TR; a multiple of the CUDA-core kernel's AggCfg::TN
+static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile == TcCfg::TR, "chunk_rows must suit both streaming kernels");
 
 static int device_sm_count() {
     int dev = 0, sms = 0;
@@ -98,10 +99,9 @@ static int launch_agg(const AggParams& prm, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
-template <int NP>
 static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
-    using C = TcCfg<NP>;
-    auto kern = agg_tc_kernel<NP>;
+    using C = TcCfg;
+    auto kern = agg_tc_kernel;
     VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
     const int sms = device_sm_count();
     const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
@@ -126,7 +126,7 @@ static bool agg_use_tc(int P, int x_dtype) {
 }
 
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {
-    if (agg_use_tc(P, x_dtype)) return P <= 8 ? launch_agg_tc<8>(prm, P, st) : launch_agg_tc<16>(prm, P, st);
+    if (agg_use_tc(P, x_dtype)) return launch_agg_tc(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
