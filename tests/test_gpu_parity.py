@@ -176,7 +176,7 @@ def test_properties_full_size(dev):
     Xd = X.to(dev)
     args = tuple(z.to(dev) for z in (_query(pr), pr["W"], pr["b"], pr["text_features"], pr["logit_scale"]))
     plan_a = ops.make_plan([100000], dev)
-    plan_b = ops.make_plan([100000], dev, sms=37)          # different chunking
+    plan_b = ops.make_plan([100000], dev, sms=8)           # different chunking
     a = ops.aggregate_forward_raw(Xd, plan_a, *args)
     b = ops.aggregate_forward_raw(Xd, plan_b, *args)
     assert plan_a.chunk_rows != plan_b.chunk_rows

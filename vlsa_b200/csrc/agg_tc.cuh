@@ -1,28 +1,34 @@
-// Fused language-guided aggregation on the 5th-generation tensor cores (tcgen05 + TMEM), forward pass.
-// Same contract as agg_simt_kernel<P,false,float>: ONE read of X, per-chunk online-softmax partials
-// (m, l, O[P,D]) — with both skinny contractions on tcgen05.mma (kind::f16, fp32 accumulators in TMEM):
+// Fused language-guided aggregation on the 5th-generation tensor cores (tcgen05 + TMEM), forward and backward.
+// Same contract as agg_simt_kernel<P,BWD,float>: ONE read of X, per-chunk partials — forward: online-softmax
+// (m, l, O[P,D]); backward: partial dQn[P,D] — with both skinny contractions on tcgen05.mma (kind::f16, fp32
+// accumulators in TMEM):
 //
 //   GEMM1  S^T[128, 64]  = Qn'[128, 512] (A, resident in TMEM) . [X_hi ; X_lo][64, 512]^T (B, K-major smem)
 //   GEMM2  O^T[512 d, 32 | 16] += X_hi^T | X_lo^T [512, 32] (A, MN-major, the SAME smem bytes) . W[32 | 16, 32]^T
 //
 // Precision design (the tensor core truncates its fp32 accumulator toward zero after every instruction —
 // measured with scripts/dev_tc_unit.cu — so the number of accumulation steps per accumulator is kept small):
-//   * every row of X is scaled by a power of two (largest |x| -> [1,2)) and split into fp16 (hi, lo) planes:
-//     22 significant bits at 4 bytes of shared memory per element; Qn is split the same way;
+//   * every row of X is split into fp16 (hi, lo) planes: 22 significant bits at 4 bytes of shared memory per
+//     element.  Rows whose norm lies in [4, 2^14] (every CONCH-like row) are split as they are; any other row
+//     is first scaled by a power of two (largest |x| -> [1,2)) that the softmax warps undo exactly;
+//     Qn is split the same way;
 //   * A-operand row (TMEM lane) 32 w + j holds prototype p = 4 w + (j & 3), part (j >> 2) & 1 (hi / lo) of Qn
 //     restricted to the feature range 128 (j >> 3) .. +127 (zeros elsewhere): every accumulator only sees
 //     8 non-zero steps, and the 16 partial sums of a score (2 parts x 4 ranges x 2 planes) are added in fp32
-//     registers.  Softmax warp w therefore owns prototypes 4 w .. 4 w + 3 completely (no cross-warp traffic);
-//   * the softmax weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); products with
+//     registers.  TMEM quadrant q therefore owns prototypes 4 q .. 4 q + 3 completely;
+//   * the per-row weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); products with
 //     the hi and the lo plane of X accumulate in separate TMEM columns; tcgen05.mma needs A and B in the same
 //     16-bit format (fp16 x bf16 traps), hence fp16 weights with the lazy-rescale range control below.
 //
-// Warp roles (14 warps, 1 persistent CTA / SM, static round-robin over chunks):
-//   warps 0-3   softmax : TMEM scores -> online softmax (lazy rescale) -> weights to smem; drain O per chunk
-//   warp  4     GEMM1 issuer (one thread) + TMEM allocation
-//   warp  5     GEMM2 issuer (one thread)
-//   warps 6-13  producers: L2 bulk prefetch ahead; LDG.128 of whole rows (one tile in flight in registers)
-//               -> power-of-two scale / fp16 split -> swizzled STS
+// Warp roles (20 warps, 1 persistent CTA / SM, static round-robin over chunks):
+//   warps 0-7   weights : warp w reads TMEM quadrant w & 3 (prototypes) for tile rows 16 (w >> 2) .. +15:
+//               scores -> online softmax with lazy rescale (forward) | A (u - delta) (backward) -> fp16 weight
+//               terms to smem; drain of the accumulators per chunk
+//   warp  8     GEMM1 issuer (one thread) + TMEM allocation
+//   warp  9     GEMM2 issuer (one thread)
+//   warp  10    L2 bulk prefetch, PF tiles ahead of the producers (warp 11 idles)
+//   warps 12-19 producers: LDG.128 of whole rows (one tile in flight in registers)
+//               -> row norm (packed f32x2 FMAs) -> fp16 split -> swizzled STS; backward: also u = dv . x / P
 // Ring: 3 tile buffers x 64 KB, a tile = 32 rows = 8 slots of 64 columns x (hi 4 KB | lo 4 KB), 128-byte swizzle.
 #pragma once
 #include <cuda_fp16.h>
@@ -47,14 +53,19 @@ struct TcCfg {
     static constexpr int WBUF = WROWS * 128;      // 4 KB per weight buffer (rows of 128 B, 64 B used)
     static constexpr int OFF_W = NBUF * TILE;
     static constexpr int OFF_F = OFF_W + 2 * WBUF;
-    // floats: rowinfo[NBUF][TR][2] | alpha[16]
-    static constexpr int NFLOAT = NBUF * TR * 2 + 16;
+    // floats: rowinfo[NBUF][TR][4] | alpha[16] | cand[2][16] | lsum[16]
+    static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 32 + 16;
     static constexpr int OFF_BAR = OFF_F + NFLOAT * 4;
     static constexpr int NBAR = 2 * NBUF + 8;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16 + 1024;
-    static constexpr int NWARPS = 14;
+    static constexpr int NSOFT = 8;               // weight ("softmax") warps
+    static constexpr int NPROD = 8;               // producer warps
+    static constexpr int W_G1 = NSOFT;            // GEMM1 issuer warp
+    static constexpr int W_G2 = NSOFT + 1;        // GEMM2 issuer warp
+    static constexpr int W_PF = NSOFT + 2;        // L2 prefetch warp (warp NSOFT + 3 idles: warps are allocated in fours)
+    static constexpr int W_PROD = NSOFT + 4;      // first producer warp
+    static constexpr int NWARPS = NSOFT + 4 + NPROD;
     static constexpr int THREADS = NWARPS * 32;
-    static constexpr int NPROD = 8;
     static constexpr int PF = 3;                  // L2 prefetch distance in tiles (3 x 64 KB x 148 SMs = 28 MB of L2)
     static constexpr int QPITCH = D + 1;          // prologue staging of Qn (aliases the ring)
     // TMEM columns: Qn operand | O^T accumulators: 4 blocks of 128 d x (hi.t0 16 | hi.t1 16 | lo.t0 16) | scores
@@ -63,20 +74,30 @@ struct TcCfg {
     static constexpr int TM_D2 = 256;
     static constexpr int TM_D1 = TM_D2 + 4 * D2W;   // 448: scores [hi plane rows 0..31 | lo plane rows 0..31]
     static constexpr int TMEM_COLS = 512;
-    // online softmax with lazy rescaling: on (re)set the reference is the running maximum + HEADROOM; the TMEM
-    // accumulators are rescaled only when a tile maximum exceeds the reference by more than MARGIN, so the
-    // fp16 weight terms stay within (0, e^MARGIN] (e^10 = 22026 < 65504) with an absolute floor of 2^-35.
+    // forward, online softmax with lazy rescaling: on (re)set the reference is the running maximum + HEADROOM;
+    // the TMEM accumulators are rescaled only when a tile maximum exceeds the reference by more than MARGIN, so
+    // the fp16 weight terms stay within (0, e^MARGIN] (e^10 = 22026 < 65504) with an absolute floor of 2^-35.
     static constexpr float HEADROOM = 6.f;
     static constexpr float MARGIN = 10.f;
+    // backward, the same idea on a power-of-two normaliser H_p: weights / H_p are kept <= 2^BWD_MAXE, (re)set
+    // so that the largest weight of the triggering tile becomes 2^BWD_SETE
+    static constexpr int BWD_MAXE = 14;
+    static constexpr int BWD_SETE = 6;
+    // rows with |x|^2 in [FAST_LO, FAST_HI] are split unscaled
+    static constexpr float FAST_LO = 16.f;
+    static constexpr float FAST_HI = 268435456.f;   // 2^28
 };
 
-// x = hi + lo with hi, lo fp16 (packed pairs, first element in the low half)
-__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(a, b);
+// x = hi + lo with hi, lo fp16 (packed pairs, first element in the low half); SASS: 2 F2FP + 2 HADD2.F32 + 1 FADD2
+__device__ __forceinline__ void split_f16x2(float2 a, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __float22half2_rn(a);
     const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    const __half2 l = __float22half2_rn(__fadd2_rn(a, make_float2(-hf.x, -hf.y)));
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    split_f16x2(make_float2(a, b), hi, lo);
 }
 
 // barrier among `nthreads` threads that also ORs a predicate across them (bar.red.or)
@@ -89,6 +110,7 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
     return out != 0;
 }
 
+template <bool BWD>
 __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggParams prm, const int P) {
     using C = TcCfg;
     constexpr int D = C::D, NP = C::NP, TR = C::TR;
@@ -98,29 +120,33 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
     unsigned char* ring = sm;
     unsigned char* wt = sm + C::OFF_W;
-    float* s_rowinfo = reinterpret_cast<float*>(sm + C::OFF_F);      // [NBUF][TR] x (score factor, 2^e)
-    float* s_alpha = s_rowinfo + C::NBUF * TR * 2;                   // [16] rescale factors (rare path)
+    float* s_rowinfo = reinterpret_cast<float*>(sm + C::OFF_F);      // [NBUF][TR] x (score factor, 2^e, u, -)
+    float* s_alpha = s_rowinfo + C::NBUF * TR * 4;                   // [16] rescale factors (rare path)
+    float* s_cand = s_alpha + 16;                                    // [2][16] per-half reference candidates
+    float* s_lsum = s_cand + 32;                                     // [16] softmax sums of the upper half
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
-    uint64_t* full = bars;                       // [NBUF] producers (8 warps)      -> GEMM1, softmax (row info)
+    uint64_t* full = bars;                       // [NBUF] producers (8 warps)      -> GEMM1, weight warps (row info)
     uint64_t* empty = bars + C::NBUF;            // [NBUF] GEMM2 commit             -> producers
-    uint64_t* s_ready = bars + 2 * C::NBUF;      //        GEMM1 commit             -> softmax
-    uint64_t* s_free = s_ready + 1;              //        softmax (4 warps)        -> GEMM1
-    uint64_t* w_ready = s_ready + 2;             // [2]    softmax (4 warps)        -> GEMM2
-    uint64_t* w_free = s_ready + 4;              // [2]    GEMM2 commit             -> softmax
-    uint64_t* d2_done = s_ready + 6;             //        last GEMM2 of a chunk    -> softmax (drain)
-    uint64_t* d2_free = s_ready + 7;             //        softmax (4 warps)        -> GEMM2 of the next chunk
+    uint64_t* s_ready = bars + 2 * C::NBUF;      //        GEMM1 commit             -> weight warps
+    uint64_t* s_free = s_ready + 1;              //        weight warps (8)         -> GEMM1
+    uint64_t* w_ready = s_ready + 2;             // [2]    weight warps (8)         -> GEMM2
+    uint64_t* w_free = s_ready + 4;              // [2]    GEMM2 commit             -> weight warps
+    uint64_t* d2_done = s_ready + 6;             //        last GEMM2 of a chunk    -> weight warps (drain)
+    uint64_t* d2_free = s_ready + 7;             //        weight warps (8)         -> GEMM2 of the next chunk
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    uint32_t* s_prog = tmem_ptr + 1;             // tiles filled so far (paces the L2 prefetcher)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int s = 0; s < C::NBUF; ++s) { mbar_init(full + s, C::NPROD); mbar_init(empty + s, 1); }
-        mbar_init(s_ready, 1); mbar_init(s_free, 4);
-        for (int s = 0; s < 2; ++s) { mbar_init(w_ready + s, 4); mbar_init(w_free + s, 1); }
-        mbar_init(d2_done, 1); mbar_init(d2_free, 4);
+        mbar_init(s_ready, 1); mbar_init(s_free, C::NSOFT);
+        for (int s = 0; s < 2; ++s) { mbar_init(w_ready + s, C::NSOFT); mbar_init(w_free + s, 1); }
+        mbar_init(d2_done, 1); mbar_init(d2_free, C::NSOFT);
+        *s_prog = 0u;
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    if (warp == C::W_G1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
     // ---- prologue: Qn = Q / max(|Q|, eps) staged as fp32 in the (still unused) ring, rows >= P are zero
     {
         float* qn = reinterpret_cast<float*>(ring);
@@ -163,122 +189,203 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     __syncthreads();                                       // Qn is in TMEM; the ring may be overwritten from here on
     tc_fence_after();
 
-    if (warp >= 6) {
+    // register budget: the launch bound gives every warp 96; the issuer warpgroup (8-11) hands most of its
+    // registers back and the two producer warpgroups (12-19) grow to 120 (the pool is per CTA: 8 x 96 + 4 x 40 + 8 x 120 <= 20 x 96)
+    if (warp >= C::W_PROD) {
         // =========================================================================== producers
-        const int pw = warp - 6;
-        const float* X = reinterpret_cast<const float*>(prm.X);
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        const int pw = warp - C::W_PROD;
         const uint64_t policy = make_evict_first_policy();
-        int cc = blockIdx.x; long long row = 0, r1 = 0; bool valid = cc < prm.total_chunks;
-        if (valid) { int bag; chunk_info(prm, cc, bag, row, r1); }
-        float4 buf[4][4];
-        auto issue_row = [&](int j) {
-            const long long r = row + 4 * pw + j;
-            if (valid && r < r1) {
-                const float* src = X + r * D + 4 * lane;
+        // cursor: tile = (pointer to its first row, already offset by this lane's 4 columns; rows left in the chunk)
+        int cc = blockIdx.x, bag = 0, rows_left = 0;
+        const float* tptr = nullptr;
+        bool valid = cc < prm.total_chunks;
+        if (valid) {
+            long long r0, r1;
+            chunk_info(prm, cc, bag, r0, r1);
+            tptr = reinterpret_cast<const float*>(prm.X) + r0 * D + 4 * lane;
+            rows_left = int(r1 - r0);
+        }
+        // two register sets of two rows each: set s = tile rows 4 pw + 2 s, + 1.  Rows past the end of the chunk
+        // re-read its last row (their weights are masked by the weight warps), so no load is predicated.
+        float4 buf[2][2][4];
+        auto issue_set = [&](int s, const float* tp, int rl) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) buf[j][i] = ldg_stream_f4(src + 128 * i, policy);
-            } else {
+            for (int k = 0; k < 2; ++k) {
+                const int lr = min(4 * pw + 2 * s + k, rl - 1);
+                const float* src = tp + lr * D;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) buf[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 4; ++i) buf[s][k][i] = ldg_stream_f4(src + 128 * i, policy);
             }
         };
+        if (valid) { issue_set(0, tptr, rows_left); issue_set(1, tptr, rows_left); }
+        // swizzled byte offset of this lane's 8-byte store inside a slot plane, per row j of the warp:
+        // columns 128 i + 4 lane .. +3 -> slot 2 i + (lane >> 4), 16-byte chunk (lane & 15) >> 1, half (lane & 1)
+        uint32_t soff[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) issue_row(j);
-        // L2 prefetch cursor, PF tiles ahead of the register loads: DRAM latency is absorbed by the 126 MB L2,
-        // so one tile of loads in flight per SM (64 KB of registers) is enough to stream at full rate
-        int fcc = blockIdx.x; long long frow = 0, fr1 = 0; bool fvalid = fcc < prm.total_chunks;
-        if (fvalid) { int bag; chunk_info(prm, fcc, bag, frow, fr1); }
-        auto prefetch_tile = [&]() {
-            if (!fvalid) return;
-            const long long r = frow + 4 * pw;
-            if (lane == 0 && r < fr1) {
-                const long long n = fr1 - r < 4 ? fr1 - r : 4;
-                l2_prefetch_bulk(X + r * D, uint32_t(n) * D * 4u);
-            }
-            frow += TR;
-            if (frow >= fr1) {
-                fcc += gridDim.x;
-                fvalid = fcc < prm.total_chunks;
-                if (fvalid) { int bag; chunk_info(prm, fcc, bag, frow, fr1); }
-            }
-        };
-#pragma unroll 1
-        for (int k = 0; k < C::PF; ++k) prefetch_tile();
+        for (int j = 0; j < 4; ++j)
+            soff[j] = (lane >> 4) * C::SLOT + sw128_offset(4 * pw + j, (lane & 15) >> 1, (lane & 1) * 8);
+        // backward: dv / P of the bag whose tile sits in the registers (16 columns per lane, as buf)
+        float4 dvr[BWD ? 4 : 1];
+        int dv_bag = -1;
         uint32_t tt = 0;
         while (valid) {
-            prefetch_tile();
-            // advance the load cursor to the next tile of this CTA
-            row += TR;
-            if (row >= r1) {
+            const int cur_bag = bag;
+            // the tile after this one
+            bool nvalid = true;
+            const float* nptr = tptr + TR * D;
+            int nrows = rows_left - TR;
+            if (nrows <= 0) {
                 cc += gridDim.x;
-                valid = cc < prm.total_chunks;
-                if (valid) { int bag; chunk_info(prm, cc, bag, row, r1); }
+                nvalid = cc < prm.total_chunks;
+                if (nvalid) {
+                    long long r0, r1;
+                    chunk_info(prm, cc, bag, r0, r1);
+                    nptr = reinterpret_cast<const float*>(prm.X) + r0 * D + 4 * lane;
+                    nrows = int(r1 - r0);
+                }
             }
-            const uint32_t b = tt % C::NBUF, u = tt / C::NBUF;
-            // per-row power-of-two scale: largest |x| -> [1, 2); the four rows reduce as independent shuffle chains
-            float mx[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                mx[j] = 0.f;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    mx[j] = fmaxf(fmaxf(mx[j], fmaxf(fabsf(buf[j][i].x), fabsf(buf[j][i].y))),
-                                  fmaxf(fabsf(buf[j][i].z), fabsf(buf[j][i].w)));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
-            }
-            mbar_wait_wd(empty + b, (u & 1u) ^ 1u);
-            unsigned char* tile = ring + b * C::TILE;
-            float ssq[4];
-            uint32_t exs[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = 4 * pw + j;
-                // zero / denormal / non-finite rows keep scale 1
-                uint32_t ex = __float_as_uint(mx[j]) >> 23;
-                if (ex == 0u || ex >= 255u) ex = 127u;
-                if (ex > 253u) ex = 253u;
-                exs[j] = ex;
-                const float sc = __uint_as_float((254u - ex) << 23);
-                float acc = 0.f;
+            if (BWD && cur_bag != dv_bag) {
+                dv_bag = cur_bag;
+                const float invP = 1.f / float(P);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float a0 = buf[j][i].x * sc, a1 = buf[j][i].y * sc, a2 = buf[j][i].z * sc, a3 = buf[j][i].w * sc;
-                    acc += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
-                    uint32_t h0, l0, h1, l1;
-                    split_f16x2(a0, a1, h0, l0);
-                    split_f16x2(a2, a3, h1, l1);
-                    // columns 128 i + 4 lane .. +3: slot 2 i + (lane >> 4), 16-byte chunk (lane & 15) >> 1, half (lane & 1)
-                    unsigned char* hi = tile + (2 * i + (lane >> 4)) * C::SLOT + sw128_offset(r, (lane & 15) >> 1, (lane & 1) * 8);
-                    *reinterpret_cast<uint2*>(hi) = make_uint2(h0, h1);
-                    *reinterpret_cast<uint2*>(hi + C::PLANE) = make_uint2(l0, l1);
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(prm.dv + size_t(cur_bag) * D + 128 * i + 4 * lane));
+                    dvr[i] = make_float4(t4.x * invP, t4.y * invP, t4.z * invP, t4.w * invP);
                 }
-                ssq[j] = acc;
-                issue_row(j);                               // same register slot, next tile
             }
+            const uint32_t b = tt % C::NBUF, u = tt / C::NBUF;
+            unsigned char* tile = ring + b * C::TILE;
+            // one register set: row norms (and u = dv . x / P) on the raw values -> row info -> fp16 split -> STS
+            auto process_set = [&](int s) {
+                float ssq[2], ud[2];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
+                for (int k = 0; k < 2; ++k) {
+                    float2 a2 = make_float2(0.f, 0.f), u2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], o);
-            }
-            if (lane < 4) {
-                const float sq = lane == 0 ? ssq[0] : (lane == 1 ? ssq[1] : (lane == 2 ? ssq[2] : ssq[3]));
-                const uint32_t ex = lane == 0 ? exs[0] : (lane == 1 ? exs[1] : (lane == 2 ? exs[2] : exs[3]));
-                float2 info;
-                // score = info.x * (Qn . x~);  x = 2^e x~ with 2^e = info.y
-                info.x = prm.scale / fmaxf(sqrtf(sq), VLSA_NORM_EPS * __uint_as_float((254u - ex) << 23));
-                info.y = __uint_as_float(ex << 23);
-                *reinterpret_cast<float2*>(s_rowinfo + (b * TR + 4 * pw + lane) * 2) = info;
-            }
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x4 = buf[s][k][i];
+                        const float2 xy = make_float2(x4.x, x4.y), zw = make_float2(x4.z, x4.w);
+                        a2 = __ffma2_rn(xy, xy, a2);
+                        a2 = __ffma2_rn(zw, zw, a2);
+                        if (BWD) {
+                            u2 = __ffma2_rn(xy, make_float2(dvr[BWD ? i : 0].x, dvr[BWD ? i : 0].y), u2);
+                            u2 = __ffma2_rn(zw, make_float2(dvr[BWD ? i : 0].z, dvr[BWD ? i : 0].w), u2);
+                        }
+                    }
+                    ssq[k] = a2.x + a2.y;
+                    ud[k] = u2.x + u2.y;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
+                        if (BWD) ud[k] += __shfl_xor_sync(0xffffffffu, ud[k], o);
+                    }
+                }
+                uint32_t exs[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    exs[k] = 127u;
+                    if (!(ssq[k] >= C::FAST_LO && ssq[k] <= C::FAST_HI)) {
+                        // general path (warp-uniform): power-of-two scale, largest |x| -> [1, 2); zero / denormal /
+                        // non-finite rows keep scale 1
+                        float mx = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(buf[s][k][i].x), fabsf(buf[s][k][i].y))),
+                                       fmaxf(fabsf(buf[s][k][i].z), fabsf(buf[s][k][i].w)));
+                        mx = warp_max(mx);
+                        uint32_t ex = __float_as_uint(mx) >> 23;
+                        if (ex == 0u || ex >= 255u) ex = 127u;
+                        if (ex > 253u) ex = 253u;
+                        exs[k] = ex;
+                        const float sc = __uint_as_float((254u - ex) << 23);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4& x4 = buf[s][k][i];
+                            x4.x *= sc; x4.y *= sc; x4.z *= sc; x4.w *= sc;
+                            acc += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w;
+                        }
+                        ssq[k] = warp_sum(acc);
+                    }
+                }
+                if (s == 0) mbar_wait_wd(empty + b, (u & 1u) ^ 1u);
+                if (lane < 2) {
+                    const float sq = lane == 0 ? ssq[0] : ssq[1];
+                    const uint32_t ex = lane == 0 ? exs[0] : exs[1];
+                    // score = info.x * (Qn . x~), info.x = scale / max(|x~|, eps 2^-e);  x = 2^e x~ with 2^e = info.y;
+                    // info.z = dv . x / P (backward).  1 / |x~| = rsqrt + one Newton step (<= 2 ulp).
+                    float4 info;
+                    info.y = __uint_as_float(ex << 23);
+                    float y = rsqrtf(sq);
+                    y = y * fmaf(-0.5f * sq * y, y, 1.5f);
+                    y = fminf(y, info.y * (1.f / VLSA_NORM_EPS));          // also catches sq == 0 (NaN -> cap)
+                    info.x = prm.scale * y;
+                    info.z = BWD ? (lane == 0 ? ud[0] : ud[1]) : 0.f;
+                    info.w = 0.f;
+                    *reinterpret_cast<float4*>(s_rowinfo + (b * TR + 4 * pw + 2 * s + lane) * 4) = info;
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    unsigned char* dst = tile + soff[2 * s + k];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x4 = buf[s][k][i];
+                        uint32_t h0, l0, h1, l1;
+                        split_f16x2(make_float2(x4.x, x4.y), h0, l0);
+                        split_f16x2(make_float2(x4.z, x4.w), h1, l1);
+                        *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT + C::PLANE) = make_uint2(l0, l1);
+                    }
+                }
+            };
+            // schedule: the proxy fence below waits for every outstanding load of the thread, so at the fence only
+            // set 0 of the next tile is in flight (issued half a tile earlier); set 1 is issued right after it
+            process_set(0);
+            if (nvalid) issue_set(0, nptr, nrows);
+            process_set(1);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + b);
+            if (nvalid) issue_set(1, nptr, nrows);
             ++tt;
+            if (pw == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(s_prog) = tt;
+            valid = nvalid; tptr = nptr; rows_left = nrows;
         }
-    } else if (warp == 4) {
+    } else if (warp >= C::NSOFT) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == C::W_PF) {
+        // =========================================================================== L2 prefetcher
+        // one bulk prefetch per tile, PF tiles ahead of the tile the producers are filling: DRAM latency is absorbed
+        // by the 126 MB L2, so one tile of loads in flight per SM (64 KB of registers) streams at full rate
+        if (lane == 0) {
+            const float* X = reinterpret_cast<const float*>(prm.X);
+            int fcc = blockIdx.x; long long frow = 0, fr1 = 0; bool fvalid = fcc < prm.total_chunks;
+            if (fvalid) { int fb; chunk_info(prm, fcc, fb, frow, fr1); }
+            auto prefetch_tile = [&]() {
+                if (!fvalid) return;
+                const long long n = fr1 - frow < TR ? fr1 - frow : TR;
+                l2_prefetch_bulk(X + frow * D, uint32_t(n) * D * 4u);
+                frow += TR;
+                if (frow >= fr1) {
+                    fcc += gridDim.x;
+                    fvalid = fcc < prm.total_chunks;
+                    if (fvalid) { int fb; chunk_info(prm, fcc, fb, frow, fr1); }
+                }
+            };
+            // paced by the producers' progress counter (monotonic: no parity aliasing if this warp lags)
+            volatile uint32_t* prog = s_prog;
+            uint32_t done = 0;
+            while (fvalid) {
+                if (done < *prog + uint32_t(C::PF + 1)) { prefetch_tile(); ++done; }
+                else __nanosleep(128);
+            }
+        }
+        __syncwarp();
+    } else if (warp == C::W_G1) {
         // =========================================================================== GEMM1 issuer
         if (lane == 0) {
             constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * TR, false, false);
@@ -307,7 +414,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == C::W_G2) {
         // =========================================================================== GEMM2 issuer
         if (lane == 0) {
             constexpr uint32_t idesc_hi = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * NP, true, false);
@@ -342,155 +449,235 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             }
         }
         __syncwarp();
+      }
     } else {
-        // =========================================================================== softmax / drain
-        const int pl = lane & 3, p = 4 * warp + pl, grp = lane >> 2;       // this thread: prototype p, tile rows 4 grp .. +3
+        // =========================================================================== weights / drain
+        // this thread: TMEM quadrant q (prototype p = 4 q + (lane & 3)), tile rows n0, n0 + 1
+        const int q = warp & 3, half = warp >> 2;
+        const int pl = lane & 3, p = 4 * q + pl, grp = lane >> 2;
+        const int n0 = 16 * half + 2 * grp;
         const bool pvalid = p < P;
-        const uint32_t tq = tmem + (uint32_t(32 * warp) << 16);
+        const uint32_t tq = tmem + (uint32_t(32 * q) << 16);
+        constexpr int NT = C::NSOFT * 32;
         uint32_t tt = 0, cc = 0;
         for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x, ++cc) {
             int bag; long long r0, r1;
             chunk_info(prm, c, bag, r0, r1);
-            const int ntiles = int((r1 - r0 + TR - 1) / TR);
+            const int chunk_nrows = int(r1 - r0);
+            const int ntiles = (chunk_nrows + TR - 1) / TR;
+            // forward: m_ref = softmax reference, lsum = running sum, exE = chunk reference exponent E
+            //          (accumulators hold 2^-E O)
+            // backward: m_ref = log2 of the normaliser H_p (accumulators hold dQn_p / H_p)
             float m_ref = -INFINITY, lsum = 0.f;
-            int exE = 127;                       // chunk reference exponent E: accumulators hold 2^-E O
+            int exE = 127;
+            float bw_m = 0.f, bw_il = 0.f, bw_delta = 0.f;
+            if (BWD && pvalid) {
+                bw_m = __ldg(prm.ml + (size_t(bag) * P + p) * 2);
+                bw_il = 1.f / __ldg(prm.ml + (size_t(bag) * P + p) * 2 + 1);
+                bw_delta = __ldg(prm.delta + size_t(bag) * P + p);
+            }
             for (int t = 0; t < ntiles; ++t, ++tt) {
                 const uint32_t i = tt & 1u, v = tt >> 1, b = tt % C::NBUF, u = tt / C::NBUF;
-                const long long left = r1 - (r0 + (long long)t * TR);
-                const int nvalid = left < TR ? int(left) : TR;
+                const int nvalid = min(TR, chunk_nrows - t * TR);
                 mbar_wait_wd(s_ready, tt & 1u);
                 tc_fence_after();
-                float sc4[4];
+                float sc2[2];
                 {
-                    // 64 partial scores of this lane's (prototype, part, range): rows 0..31 x (hi | lo plane)
-                    uint32_t sv[64];
-                    tmem_ld32(tq + C::TM_D1, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-                    tmem_ld32(tq + C::TM_D1 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
+                    // 32 partial scores of this lane's (prototype, part, range): rows 16 half .. +15 x (hi | lo plane)
+                    uint32_t sa[16], sb[16];
+                    tmem_ld16(tq + C::TM_D1 + 16 * half, sa);
+                    tmem_ld16(tq + C::TM_D1 + 32 + 16 * half, sb);
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(s_free);
                     // add the planes, then a transposed butterfly over the 8 lanes (part, range) of this prototype:
-                    // lane bits 4, 3, 2 select which half of the rows a lane keeps -> rows 4 grp .. 4 grp + 3
-                    float a16[16], a8[8];
-#pragma unroll
-                    for (int n = 0; n < 16; ++n) {
-                        const float lo_half = __uint_as_float(sv[n]) + __uint_as_float(sv[32 + n]);
-                        const float hi_half = __uint_as_float(sv[16 + n]) + __uint_as_float(sv[48 + n]);
-                        const bool up = lane & 16;
-                        const float keep = up ? hi_half : lo_half, send = up ? lo_half : hi_half;
-                        a16[n] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                    }
+                    // lane bits 4, 3, 2 select which half of the rows a lane keeps -> rows n0, n0 + 1
+                    float a8[8], a4[4];
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
-                        const bool up = lane & 8;
-                        const float keep = up ? a16[8 + n] : a16[n], send = up ? a16[n] : a16[8 + n];
-                        a8[n] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                        const float lo_half = __uint_as_float(sa[n]) + __uint_as_float(sb[n]);
+                        const float hi_half = __uint_as_float(sa[8 + n]) + __uint_as_float(sb[8 + n]);
+                        const bool up = lane & 16;
+                        const float keep = up ? hi_half : lo_half, send = up ? lo_half : hi_half;
+                        a8[n] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                     }
 #pragma unroll
                     for (int n = 0; n < 4; ++n) {
-                        const bool up = lane & 4;
+                        const bool up = lane & 8;
                         const float keep = up ? a8[4 + n] : a8[n], send = up ? a8[n] : a8[4 + n];
-                        sc4[n] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        a4[n] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+#pragma unroll
+                    for (int n = 0; n < 2; ++n) {
+                        const bool up = lane & 4;
+                        const float keep = up ? a4[2 + n] : a4[n], send = up ? a4[n] : a4[2 + n];
+                        sc2[n] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                     }
                 }
                 mbar_wait_wd(full + b, u & 1u);                        // acquire the producers' row info
-                if (t == 0) exE = int(__float_as_uint(s_rowinfo[(b * TR) * 2 + 1]) >> 23);
-                // ts = score + (e_row - E) ln 2: the weight fed to GEMM2 is exp(ts - m_ref) = A-weight x 2^(e_row - E)
-                const int n0 = 4 * grp;
-                float ts[4], unscale[4];
+                float4 info[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 info = *reinterpret_cast<const float2*>(s_rowinfo + (b * TR + n0 + k) * 2);
-                    int de = int(__float_as_uint(info.y) >> 23) - exE;
-                    de = de < -100 ? -100 : (de > 100 ? 100 : de);
-                    ts[k] = (n0 + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc4[k] * info.x) : -INFINITY;
-                    unscale[k] = __uint_as_float(uint32_t(127 - de) << 23);       // 2^-(e_row - E)
-                }
-                float mt = fmaxf(fmaxf(ts[0], ts[1]), fmaxf(ts[2], ts[3]));
-                mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
-                mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
-                mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
-                const bool grow = pvalid && (mt > m_ref + C::MARGIN);             // always true on the first tile
-                const bool any_grow = named_bar_or(1, 128, grow);
-                if (any_grow) {
-                    const float m_new = grow ? mt + C::HEADROOM : m_ref;
-                    if (t > 0) {
-                        // a later tile beats the reference by more than the margin: rescale the TMEM accumulators
-                        // once GEMM2 of the previous tile has completed (every warp owns its 32 TMEM lanes)
-                        const float alpha = grow ? expf(m_ref - m_new) : 1.f;
-                        if (lane < 4) s_alpha[p] = alpha;
-                        mbar_wait_wd(w_free + ((tt - 1) & 1u), ((tt - 1) >> 1) & 1u);
-                        tc_fence_after();
-                        named_bar_sync(2, 128);
-                        float al[16];
+                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + n0 + k) * 4);
+                float w[2];                                            // weights fed to GEMM2 (before the fp16 split)
+                if (!BWD) {
+                    if (t == 0) exE = int(__float_as_uint(s_rowinfo[(b * TR) * 4 + 1]) >> 23);
+                    // ts = score + (e_row - E) ln 2: the weight is exp(ts - m_ref) = A-weight x 2^(e_row - E)
+                    float ts[2], unscale[2];
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) al[q] = s_alpha[q];
-#pragma unroll 1
-                        for (int k = 0; k < 4 * C::D2W / 16; ++k) {
-                            uint32_t o[16];
-                            tmem_ld16(tq + C::TM_D2 + 16 * k, o);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * al[q]);
-                            tmem_st16(tq + C::TM_D2 + 16 * k, o);
-                        }
-                        tmem_wait_st();
-                        tc_fence_before();
-                        lsum *= alpha;
+                    for (int k = 0; k < 2; ++k) {
+                        int de = int(__float_as_uint(info[k].y) >> 23) - exE;
+                        de = de < -100 ? -100 : (de > 100 ? 100 : de);
+                        ts[k] = (n0 + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
+                        unscale[k] = __uint_as_float(uint32_t(127 - de) << 23);       // 2^-(e_row - E)
                     }
-                    m_ref = m_new;
+                    float mt = fmaxf(ts[0], ts[1]);
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+                    const bool grow = pvalid && (mt > m_ref + C::MARGIN);             // true on the first tile
+                    if (named_bar_or(1, NT, grow)) {
+                        // rare: both halves agree on the new reference of every prototype; from the second tile
+                        // on the TMEM accumulators are rescaled once GEMM2 of the previous tile has completed
+                        if (lane < 4) s_cand[16 * half + p] = grow ? mt + C::HEADROOM : m_ref;
+                        named_bar_sync(2, NT);
+                        const float m_new = fmaxf(s_cand[p], s_cand[16 + p]);
+                        if (t > 0) {
+                            const float alpha = (pvalid && m_new > m_ref) ? expf(m_ref - m_new) : 1.f;
+                            if (half == 0 && lane < 4) s_alpha[p] = alpha;
+                            mbar_wait_wd(w_free + ((tt - 1) & 1u), ((tt - 1) >> 1) & 1u);
+                            tc_fence_after();
+                            named_bar_sync(3, NT);
+                            float al[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) al[j] = s_alpha[j];
+#pragma unroll 1
+                            for (int k = 6 * half; k < 6 * half + 6; ++k) {
+                                uint32_t o[16];
+                                tmem_ld16(tq + C::TM_D2 + 16 * k, o);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * al[j]);
+                                tmem_st16(tq + C::TM_D2 + 16 * k, o);
+                            }
+                            tmem_wait_st();
+                            tc_fence_before();
+                            lsum *= alpha;
+                        }
+                        m_ref = m_new;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        w[k] = (pvalid && n0 + k < nvalid) ? expf(ts[k] - m_ref) : 0.f;
+                        lsum = fmaf(w[k], unscale[k], lsum);
+                    }
+                } else {
+                    // c = scale A (u - delta) / |x| = A (u - delta) info.x 2^-e; the weight on x~ = 2^-e x is c 2^e
+                    float cw[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const float a = expf(sc2[k] * info[k].x - bw_m) * bw_il;        // A_pn (deepmil.py:198)
+                        cw[k] = (pvalid && n0 + k < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
+                    }
+                    float mt = fmaxf(fabsf(cw[0]), fabsf(cw[1]));
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
+                    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
+                    // binary exponent of the tile maximum (zero / denormal -> very small, non-finite -> very large)
+                    int et = int((__float_as_uint(mt) >> 23) & 0xffu) - 127;
+                    et = et < -100 ? -100 : (et > 100 ? 100 : et);
+                    const bool grow = pvalid && (t == 0 || float(et) > m_ref + float(C::BWD_MAXE));
+                    if (named_bar_or(1, NT, grow)) {
+                        if (lane < 4) s_cand[16 * half + p] = grow ? float(et - C::BWD_SETE) : m_ref;
+                        named_bar_sync(2, NT);
+                        const float m_new = fmaxf(s_cand[p], s_cand[16 + p]);
+                        if (t > 0) {
+                            // exact: power-of-two ratio H_old / H_new
+                            const float alpha = (pvalid && m_new > m_ref) ? exp2f(m_ref - m_new) : 1.f;
+                            if (half == 0 && lane < 4) s_alpha[p] = alpha;
+                            mbar_wait_wd(w_free + ((tt - 1) & 1u), ((tt - 1) >> 1) & 1u);
+                            tc_fence_after();
+                            named_bar_sync(3, NT);
+                            float al[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) al[j] = s_alpha[j];
+#pragma unroll 1
+                            for (int k = 6 * half; k < 6 * half + 6; ++k) {
+                                uint32_t o[16];
+                                tmem_ld16(tq + C::TM_D2 + 16 * k, o);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * al[j]);
+                                tmem_st16(tq + C::TM_D2 + 16 * k, o);
+                            }
+                            tmem_wait_st();
+                            tc_fence_before();
+                        }
+                        m_ref = m_new;
+                    }
+                    const float inv_h = pvalid ? __uint_as_float(uint32_t(127 - int(m_ref)) << 23) : 0.f;   // 1 / H_p
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) w[k] = cw[k] * inv_h;
                 }
                 // weights of this tile as two fp16 terms (w = t0 + 2^-11 t1); B operand row (term * 16 + p), K = tile row
-                uint32_t b0[4], b1[4];
+                uint32_t b0[2], b1[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float w = (pvalid && n0 + k < nvalid) ? expf(ts[k] - m_ref) : 0.f;
-                    lsum = fmaf(w, unscale[k], lsum);
-                    const __half h0 = __float2half_rn(w);
-                    const __half h1 = __float2half_rn((w - __half2float(h0)) * 2048.f);
+                for (int k = 0; k < 2; ++k) {
+                    const __half h0 = __float2half_rn(w[k]);
+                    const __half h1 = __float2half_rn((w[k] - __half2float(h0)) * 2048.f);
                     b0[k] = __half_as_ushort(h0); b1[k] = __half_as_ushort(h1);
                 }
                 mbar_wait_wd(w_free + i, (v & 1u) ^ 1u);               // GEMM2 of tile tt-2 has read this buffer
                 unsigned char* wb = wt + i * C::WBUF;
-                *reinterpret_cast<uint2*>(wb + sw128_offset(p, grp >> 1, 8 * (grp & 1))) = make_uint2(b0[0] | (b0[1] << 16), b0[2] | (b0[3] << 16));
-                *reinterpret_cast<uint2*>(wb + sw128_offset(NP + p, grp >> 1, 8 * (grp & 1))) = make_uint2(b1[0] | (b1[1] << 16), b1[2] | (b1[3] << 16));
+                *reinterpret_cast<uint32_t*>(wb + sw128_offset(p, n0 >> 3, (2 * n0) & 15)) = b0[0] | (b0[1] << 16);
+                *reinterpret_cast<uint32_t*>(wb + sw128_offset(NP + p, n0 >> 3, (2 * n0) & 15)) = b1[0] | (b1[1] << 16);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(w_ready + i);
             }
             // ---- chunk end: drain O^T (lane = feature within a 128-block, columns = hi.t0 | hi.t1 | lo.t0 per prototype)
+            if (BWD) {
+                // per-prototype normalisers for the drain (every weight warp holds its own four)
+                if (half == 0 && lane < 4) s_alpha[p] = pvalid ? __uint_as_float(uint32_t(127 + int(m_ref)) << 23) : 0.f;
+                named_bar_sync(2, NT);
+            }
             mbar_wait_wd(d2_done, cc & 1u);
             tc_fence_after();
             float* po = prm.part_O + size_t(c) * P * D;
-            const float pwE = __uint_as_float(uint32_t(exE) << 23);
+            float mul[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) mul[j] = BWD ? s_alpha[j] : __uint_as_float(uint32_t(exE) << 23);
 #pragma unroll 1
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 2 * half; g < 2 * half + 2; ++g) {
                 uint32_t o0[16], o1[16], o2[16];
                 tmem_ld16(tq + C::TM_D2 + g * C::D2W, o0);
                 tmem_ld16(tq + C::TM_D2 + g * C::D2W + 16, o1);
                 tmem_ld16(tq + C::TM_D2 + g * C::D2W + 32, o2);
                 tmem_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    if (q < P) po[size_t(q) * D + 128 * g + 32 * warp + lane] =
-                        pwE * (fmaf(__uint_as_float(o1[q]), 0x1p-11f, __uint_as_float(o2[q])) + __uint_as_float(o0[q]));
+                for (int j = 0; j < 16; ++j)
+                    if (j < P) po[size_t(j) * D + 128 * g + 32 * q + lane] =
+                        mul[j] * (fmaf(__uint_as_float(o1[j]), 0x1p-11f, __uint_as_float(o2[j])) + __uint_as_float(o0[j]));
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d2_free);
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
-            if (lane < 4 && pvalid) {
-                prm.part_l[size_t(c) * P + p] = lsum;
-                prm.part_m[size_t(c) * P + p] = m_ref;
+            if (!BWD) {
+                lsum += __shfl_xor_sync(0xffffffffu, lsum, 4);
+                lsum += __shfl_xor_sync(0xffffffffu, lsum, 8);
+                lsum += __shfl_xor_sync(0xffffffffu, lsum, 16);
+                if (half == 1 && lane < 4) s_lsum[p] = lsum;
+                named_bar_sync(2, NT);
+                if (half == 0 && lane < 4 && pvalid) {
+                    prm.part_l[size_t(c) * P + p] = lsum + s_lsum[p];
+                    prm.part_m[size_t(c) * P + p] = m_ref;
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem, C::TMEM_COLS);
+    if (warp == C::W_G1) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 }  // namespace vlsa

@@ -99,9 +99,10 @@ static int launch_agg(const AggParams& prm, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
+template <bool BWD>
 static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
     using C = TcCfg;
-    auto kern = agg_tc_kernel;
+    auto kern = agg_tc_kernel<BWD>;
     VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
     const int sms = device_sm_count();
     const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
@@ -110,7 +111,7 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
-// Which streaming kernel serves the fp32 forward: the tcgen05 variant or the CUDA-core one.
+// Which streaming kernel serves an fp32 pass (forward or backward): the tcgen05 variant or the CUDA-core one.
 // VLSA_AGG_VARIANT=simt|tc overrides (development / cross-checking); default: see agg_use_tc().
 static bool agg_use_tc(int P, int x_dtype) {
     static const int forced = [] {
@@ -126,7 +127,7 @@ static bool agg_use_tc(int P, int x_dtype) {
 }
 
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {
-    if (agg_use_tc(P, x_dtype)) return launch_agg_tc(prm, P, st);
+    if (agg_use_tc(P, x_dtype)) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
@@ -282,11 +283,16 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta;
     int rc = 0;
-    VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, true, float>(prm, st);
-        else rc = launch_agg<kP, true, __nv_bfloat16>(prm, st);
+    if (agg_use_tc(P, x_dtype)) {
+        rc = launch_agg_tc<true>(prm, P, st);
         if (rc) return rc;
-    });
+    } else {
+        VLSA_DISPATCH_P(P, {
+            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, true, float>(prm, st);
+            else rc = launch_agg<kP, true, __nv_bfloat16>(prm, st);
+            if (rc) return rc;
+        });
+    }
     merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ);
     VLSA_CUDA(cudaGetLastError());
     return 0;

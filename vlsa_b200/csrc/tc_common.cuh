@@ -110,11 +110,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// mbarrier wait with a watchdog: a protocol bug traps instead of hanging the GPU
+// mbarrier wait with a watchdog: a protocol bug traps instead of hanging the GPU.  try_wait carries a
+// suspend-time hint, so a waiting warp sleeps in hardware instead of burning issue slots in a spin loop.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) { printf("vlsa: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    while (!mbar_try_wait_hint(bar, parity, 4000u)) {
+        if (++spins > (1u << 22)) { printf("vlsa: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
 
