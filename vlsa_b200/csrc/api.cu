@@ -62,8 +62,29 @@ struct AggWorkspace {
     float* df;         // [B, D]   backward
     float* dv;         // [B, D]   backward
     float* dls_part;   // [B]      backward
+    float* l2_m;       // level-2 merge partials: [B S, P] | backward: unused
+    float* l2_l;       // [B S, P]
+    float* l2_O;       // [B S, P, D]  | backward: [S, P, D]
     size_t bytes;
 };
+
+// Two-level merge of the per-chunk partials.  Level 1 folds runs of chunks with many small CTAs (about 8 per
+// SM), level 2 finishes per bag (forward) / per prototype (backward).  Splits depend only on the arguments below,
+// so the workspace size and the summation order are fixed by the plan.
+static int merge_fwd_splits(int total_chunks, int B, int P) {
+    if (B <= 0 || total_chunks < 8 * B) return 0;          // short bags: one level is enough
+    int S = 1184 / (B * P);
+    const int avg = total_chunks / B;
+    if (S > avg / 4) S = avg / 4;
+    if (S > 64) S = 64;
+    return S < 1 ? 1 : S;
+}
+static int merge_bwd_splits(int total_chunks, int P) {
+    if (total_chunks < 16) return 0;
+    int S = 1184 / P;
+    if (S > total_chunks / 4) S = total_chunks / 4;
+    return S < 1 ? 1 : S;
+}
 
 static AggWorkspace carve(void* base, int total_chunks, int B, int P) {
     AggWorkspace w;
@@ -80,6 +101,11 @@ static AggWorkspace carve(void* base, int total_chunks, int B, int P) {
     w.df = take(size_t(B) * VLSA_D);
     w.dv = take(size_t(B) * VLSA_D);
     w.dls_part = take(size_t(B));
+    const int sf = merge_fwd_splits(total_chunks, B, P), sb = merge_bwd_splits(total_chunks, P);
+    const size_t e = size_t(sf) * B > size_t(sb) ? size_t(sf) * B : size_t(sb);
+    w.l2_m = take(size_t(sf) * B * P);
+    w.l2_l = take(size_t(sf) * B * P);
+    w.l2_O = take(e * P * VLSA_D);
     w.bytes = off;
     return w;
 }
@@ -210,8 +236,15 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
 
     int rc = launch_agg_fwd(prm, P, x_dtype, st);
     if (rc) return rc;
+    const int S = merge_fwd_splits(total_chunks, B, P);
+    if (S > 0) {
+        merge_fwd_split_kernel<<<dim3(S, P, B), 128, 0, st>>>(ws.part_m, ws.part_l, ws.part_O, chunk_start, P, S,
+                                                                ws.l2_m, ws.l2_l, ws.l2_O);
+        VLSA_CUDA(cudaGetLastError());
+    }
     VLSA_DISPATCH_P(P, {
-        merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(ws.part_m, ws.part_l, ws.part_O, chunk_start,
+        merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
+                                                                     S > 0 ? ws.l2_O : ws.part_O, chunk_start, S,
                                                                      out_ml, out_O, out_v);
     });
     VLSA_CUDA(cudaGetLastError());
@@ -272,7 +305,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     }
     adapter_bwd_dw_kernel<<<VLSA_D / 8, 512, 0, st>>>(df, v, B, dW, db);
     VLSA_CUDA(cudaGetLastError());
-    adapter_bwd_dv_kernel<<<dim3((B + 7) / 8, VLSA_D / 128), 128, 0, st>>>(df, W, B, ws.dv);
+    adapter_bwd_dv_kernel<<<VLSA_D / 4, 128, 0, st>>>(df, W, B, ws.dv);
     VLSA_CUDA(cudaGetLastError());
     delta_kernel<<<B, 256, 0, st>>>(ws.dv, O, P, ws.delta);
     VLSA_CUDA(cudaGetLastError());
@@ -293,7 +326,14 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
             if (rc) return rc;
         });
     }
-    merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ);
+    const int Sb = merge_bwd_splits(total_chunks, P);
+    if (Sb > 0) {
+        merge_bwd_split_kernel<<<dim3(Sb, P), 128, 0, st>>>(ws.part_O, total_chunks, P, Sb, ws.l2_O);
+        VLSA_CUDA(cudaGetLastError());
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.l2_O, Sb, P, Q, dQ);
+    } else {
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ);
+    }
     VLSA_CUDA(cudaGetLastError());
     return 0;
 }

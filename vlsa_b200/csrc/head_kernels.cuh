@@ -10,10 +10,12 @@ namespace vlsa {
 // merge of the per-chunk online-softmax partials of one bag (flash-decoding style, fixed order):
 //   m = max_c m_c ; l = sum_c l_c e^{m_c-m} ; O_p = sum_c e^{m_c-m} O_c,p / l ; v = mean_p O_p
 // grid (B, D/128), 128 threads, thread = one feature column.
+// With S > 0 the inputs are the level-1 partials of merge_fwd_split_kernel: bag b owns entries [b S, b S + S)
+// (unused entries carry m = -inf, l = 0, O = 0); chunk_start then only tells whether the bag is empty.
 template <int P>
 __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
                                                         const float* __restrict__ part_O, const int* __restrict__ chunk_start,
-                                                        float* __restrict__ out_ml, float* __restrict__ out_O,
+                                                        int S, float* __restrict__ out_ml, float* __restrict__ out_O,
                                                         float* __restrict__ out_v) {
     constexpr int D = VLSA_D, CB = 32;                 // chunks per batch
     __shared__ float s_mx[P];
@@ -21,7 +23,8 @@ __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict_
     __shared__ float s_red[4][P];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = blockIdx.y * 128 + tid;
-    const int c0 = chunk_start[b], c1 = chunk_start[b + 1];
+    const bool bag_empty = chunk_start[b + 1] == chunk_start[b];
+    const int c0 = S > 0 ? b * S : chunk_start[b], c1 = S > 0 ? c0 + (bag_empty ? 0 : S) : chunk_start[b + 1];
 
     // pass 1: global max per p over the bag's chunks
     float mx[P];
@@ -47,7 +50,8 @@ __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict_
         __syncthreads();
         for (int i = tid; i < nb * P; i += 128) {
             const int c = i / P, p = i % P;
-            s_sf[c][p] = expf(part_m[size_t(cb + c) * P + p] - s_mx[p]);
+            const float mc = part_m[size_t(cb + c) * P + p];
+            s_sf[c][p] = mc == -INFINITY ? 0.f : expf(mc - s_mx[p]);
         }
         __syncthreads();
         for (int c = 0; c < nb; ++c) {
@@ -76,6 +80,61 @@ __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict_
         for (int p = 0; p < P; ++p) if (p == tid) lt = l[p];
         out_ml[(size_t(b) * P + tid) * 2 + 1] = lt;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// level 1 of the forward merge: CTA (split z, prototype p, bag b) folds chunks [c0 + z cps, c0 + (z + 1) cps) of its
+// bag into ONE partial of the same (m, l, O) format, entry (b S + z) of the level-2 arrays.  Fixed order.
+// grid (S, P, B), 128 threads (thread = 4 feature columns).
+__global__ void __launch_bounds__(128) merge_fwd_split_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                                              const float* __restrict__ part_O,
+                                                              const int* __restrict__ chunk_start, int P, int S,
+                                                              float* __restrict__ out_m, float* __restrict__ out_l,
+                                                              float* __restrict__ out_O) {
+    constexpr int D = VLSA_D;
+    const int z = blockIdx.x, p = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+    const int c0 = chunk_start[b], c1 = chunk_start[b + 1];
+    const int cps = (c1 - c0 + S - 1) / S;
+    const int lo = c0 + z * cps, hi = (lo + cps) < c1 ? (lo + cps) : c1;
+    float mx = -INFINITY;
+    for (int c = lo; c < hi; ++c) mx = fmaxf(mx, __ldg(part_m + size_t(c) * P + p));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float l = 0.f;
+#pragma unroll 4
+    for (int c = lo; c < hi; ++c) {
+        const float mc = __ldg(part_m + size_t(c) * P + p);
+        const float sf = mc == -INFINITY ? 0.f : expf(mc - mx);
+        const float4 o = *reinterpret_cast<const float4*>(part_O + (size_t(c) * P + p) * D + 4 * tid);
+        acc.x = fmaf(sf, o.x, acc.x); acc.y = fmaf(sf, o.y, acc.y); acc.z = fmaf(sf, o.z, acc.z); acc.w = fmaf(sf, o.w, acc.w);
+        l = fmaf(sf, __ldg(part_l + size_t(c) * P + p), l);
+    }
+    const size_t e = (size_t(b) * S + z) * P + p;
+    *reinterpret_cast<float4*>(out_O + e * D + 4 * tid) = acc;
+    if (tid == 0) { out_m[e] = mx; out_l[e] = l; }
+}
+
+// level 1 of the backward merge: out[z][p][:] = sum of part[c][p][:] over chunks c in split z (fixed order).
+// grid (S, P), 128 threads (thread = 4 feature columns).
+__global__ void __launch_bounds__(128) merge_bwd_split_kernel(const float* __restrict__ part, int total_chunks, int P, int S,
+                                                              float* __restrict__ out) {
+    constexpr int D = VLSA_D;
+    const int z = blockIdx.x, p = blockIdx.y, tid = threadIdx.x;
+    const int cps = (total_chunks + S - 1) / S;
+    const int lo = z * cps, hi = (lo + cps) < total_chunks ? (lo + cps) : total_chunks;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int c = lo;
+    for (; c + 2 <= hi; c += 2) {
+        const float4 o0 = *reinterpret_cast<const float4*>(part + (size_t(c) * P + p) * D + 4 * tid);
+        const float4 o1 = *reinterpret_cast<const float4*>(part + (size_t(c + 1) * P + p) * D + 4 * tid);
+        a0.x += o0.x; a0.y += o0.y; a0.z += o0.z; a0.w += o0.w;
+        a1.x += o1.x; a1.y += o1.y; a1.z += o1.z; a1.w += o1.w;
+    }
+    if (c < hi) {
+        const float4 o0 = *reinterpret_cast<const float4*>(part + (size_t(c) * P + p) * D + 4 * tid);
+        a0.x += o0.x; a0.y += o0.y; a0.z += o0.z; a0.w += o0.w;
+    }
+    *reinterpret_cast<float4*>(out + (size_t(z) * P + p) * D + 4 * tid) =
+        make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -239,26 +298,41 @@ __global__ void __launch_bounds__(512) adapter_bwd_dw_kernel(const float* __rest
     if (i < OT) db[o0 + i] = accb;
 }
 
-// dv[b][i] = sum_o df[b][o] W[o][i].  grid (ceil(B/8), D/128), 128 threads (thread = column i, 8 bags).
+// dv[b][i] = sum_o df[b][o] W[o][i].  grid D/4, 128 threads: a CTA owns 4 output columns i0 .. i0+3 for every
+// bag; thread t holds W[t + 128 k][i0 .. i0+3] (k < 4) in registers, bags go 8 at a time through a transposed
+// butterfly (32 values = 8 bags x 4 columns) and a 4-warp shared-memory sum.
 __global__ void __launch_bounds__(128) adapter_bwd_dv_kernel(const float* __restrict__ df, const float* __restrict__ W,
                                                              int B, float* __restrict__ dv) {
     constexpr int D = VLSA_D, BT = 8;
-    __shared__ float s_df[BT][D];
-    const int tid = threadIdx.x, b0 = blockIdx.x * BT, i = blockIdx.y * 128 + tid;
-    const int nb = (B - b0) < BT ? (B - b0) : BT;
-    for (int k = tid; k < BT * D; k += 128) s_df[k / D][k % D] = (k / D < nb) ? df[size_t(b0 + k / D) * D + k % D] : 0.f;
-    __syncthreads();
-    float acc[BT];
+    __shared__ float s_red[4][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i0 = blockIdx.x * 4;
+    float4 w[4];
 #pragma unroll
-    for (int k = 0; k < BT; ++k) acc[k] = 0.f;
-#pragma unroll 4
-    for (int o = 0; o < D; ++o) {
-        const float w = W[size_t(o) * D + i];
+    for (int k = 0; k < 4; ++k) w[k] = *reinterpret_cast<const float4*>(W + size_t(tid + 128 * k) * D + i0);
+    for (int b0 = 0; b0 < B; b0 += BT) {
+        float v[32];
 #pragma unroll
-        for (int k = 0; k < BT; ++k) acc[k] += s_df[k][o] * w;
+        for (int bb = 0; bb < BT; ++bb) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + bb < B) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = __ldg(df + size_t(b0 + bb) * D + tid + 128 * k);
+                    a.x = fmaf(d, w[k].x, a.x); a.y = fmaf(d, w[k].y, a.y); a.z = fmaf(d, w[k].z, a.z); a.w = fmaf(d, w[k].w, a.w);
+                }
+            }
+            v[4 * bb + 0] = a.x; v[4 * bb + 1] = a.y; v[4 * bb + 2] = a.z; v[4 * bb + 3] = a.w;
+        }
+        const float tot = warp_reduce_transpose<32>(v);       // lane L: sum over the warp of value L
+        __syncthreads();
+        s_red[warp][lane] = tot;
+        __syncthreads();
+        if (warp == 0) {
+            const float sum = (s_red[0][lane] + s_red[1][lane]) + (s_red[2][lane] + s_red[3][lane]);
+            const int bb = lane >> 2, c = lane & 3;
+            if (b0 + bb < B) dv[size_t(b0 + bb) * D + i0 + c] = sum;
+        }
     }
-#pragma unroll
-    for (int k = 0; k < BT; ++k) if (k < nb) dv[size_t(b0 + k) * D + i] = acc[k];
 }
 
 // delta[b][p] = (dv_b . O_b,p) / P  (= dO_p . O_p with dO_p = dv / P).  grid B, 256 threads.
