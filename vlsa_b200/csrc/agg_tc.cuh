@@ -9,7 +9,7 @@
 // Precision design (the tensor core truncates its fp32 accumulator toward zero after every instruction —
 // measured with scripts/dev_tc_unit.cu — so the number of accumulation steps per accumulator is kept small):
 //   * every row of X is split into fp16 (hi, lo) planes: 22 significant bits at 4 bytes of shared memory per
-//     element.  Rows whose norm lies in [4, 2^14] (every CONCH-like row) are split as they are; any other row
+//     element.  Rows whose norm surely lies in [2, 2^14] (every CONCH-like row) are split as they are; any other row
 //     is first scaled by a power of two (largest |x| -> [1,2)) that the softmax warps undo exactly;
 //     Qn is split the same way;
 //   * A-operand row (TMEM lane) 32 w + j holds prototype p = 4 w + (j & 3), part (j >> 2) & 1 (hi / lo) of Qn
@@ -66,7 +66,12 @@ struct TcCfg {
     static constexpr int W_PROD = NSOFT + 4;      // first producer warp
     static constexpr int NWARPS = NSOFT + 4 + NPROD;
     static constexpr int THREADS = NWARPS * 32;
-    static constexpr int PF = 3;                  // L2 prefetch distance in tiles (3 x 64 KB x 148 SMs = 28 MB of L2)
+#ifndef VLSA_TC_PF
+#define VLSA_TC_PF 0
+#endif
+    // L2 prefetch distance in tiles; 0 = off (default).  Measured (scripts/dev_readbw.cu): the register path alone
+    // streams at 7.3 TB/s, an L2 prefetch ahead of it only costs bandwidth (6.1 TB/s at 2 tiles, 4.8 at 8).
+    static constexpr int PF = VLSA_TC_PF;
     static constexpr int QPITCH = D + 1;          // prologue staging of Qn (aliases the ring)
     // TMEM columns: Qn operand | O^T accumulators: 4 blocks of 128 d x (hi.t0 16 | hi.t1 16 | lo.t0 16) | scores
     static constexpr int TM_Q = 0;
@@ -84,7 +89,7 @@ struct TcCfg {
     static constexpr int BWD_MAXE = 14;
     static constexpr int BWD_SETE = 6;
     // rows with |x|^2 in [FAST_LO, FAST_HI] are split unscaled
-    static constexpr float FAST_LO = 16.f;
+    static constexpr float FAST_LO = 4.f;
     static constexpr float FAST_HI = 268435456.f;   // 2^28
 };
 
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     tc_fence_after();
 
     // register budget: the launch bound gives every warp 96; the issuer warpgroup (8-11) hands most of its
-    // registers back and the two producer warpgroups (12-19) grow to 120 (the pool is per CTA: 8 x 96 + 4 x 40 + 8 x 120 <= 20 x 96)
+    // registers back and the two producer warpgroups (12-19) grow to 120 (the pool is per CTA: 8 x 96 + 4 x 48 + 8 x 120 = 20 x 96)
     if (warp >= C::W_PROD) {
         // =========================================================================== producers
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
@@ -206,19 +211,23 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             tptr = reinterpret_cast<const float*>(prm.X) + r0 * D + 4 * lane;
             rows_left = int(r1 - r0);
         }
-        // two register sets of two rows each: set s = tile rows 4 pw + 2 s, + 1.  Rows past the end of the chunk
-        // re-read its last row (their weights are masked by the weight warps), so no load is predicated.
-        float4 buf[2][2][4];
-        auto issue_set = [&](int s, const float* tp, int rl) {
+        // four register sets of one row each: set j = tile row 4 pw + j.  Rows past the end of the chunk re-read its
+        // last row (their weights are masked by the weight warps), so no load is predicated.
+        float4 buf[4][4];
+        auto issue_row = [&](int j, const float* tp, int rl) {
+            const int lr = min(4 * pw + j, rl - 1);
+            const float* src = tp + lr * D;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int lr = min(4 * pw + 2 * s + k, rl - 1);
-                const float* src = tp + lr * D;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) buf[s][k][i] = ldg_stream_f4(src + 128 * i, policy);
-            }
+#ifdef VLSA_TC_PLAINLDG
+            for (int i = 0; i < 4; ++i) buf[j][i] = __ldg(reinterpret_cast<const float4*>(src + 128 * i));
+#else
+            for (int i = 0; i < 4; ++i) buf[j][i] = ldg_stream_f4(src + 128 * i, policy);
+#endif
         };
-        if (valid) { issue_set(0, tptr, rows_left); issue_set(1, tptr, rows_left); }
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) issue_row(j, tptr, rows_left);
+        }
         // swizzled byte offset of this lane's 8-byte store inside a slot plane, per row j of the warp:
         // columns 128 i + 4 lane .. +3 -> slot 2 i + (lane >> 4), 16-byte chunk (lane & 15) >> 1, half (lane & 1)
         uint32_t soff[4];
@@ -256,119 +265,124 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             }
             const uint32_t b = tt % C::NBUF, u = tt / C::NBUF;
             unsigned char* tile = ring + b * C::TILE;
-            // one register set: row norms (and u = dv . x / P) on the raw values -> row info -> fp16 split -> STS
-            auto process_set = [&](int s) {
-                float ssq[2], ud[2];
+            // one row: per-lane partial norm (and u = dv . x / P) on the raw values; a warp vote on the partials decides
+            // whether the row is split AS IT IS (sufficient for FAST_LO <= |x|^2 <= FAST_HI: every CONCH-like row) or
+            // first scaled by a power of two; the five-level shuffle reduction of the norm is interleaved by hand
+            // with the quarters of the conversion (ptxas keeps the order), then lane 0 writes the row info.
+            auto convert_part = [&](int j, int i) {
+#ifdef VLSA_TC_NOCONV
+                return;
+#endif
+                unsigned char* dst = tile + soff[j];
+                const float4 x4 = buf[j][i];
+                uint32_t h0, l0, h1, l1;
+                split_f16x2(make_float2(x4.x, x4.y), h0, l0);
+                split_f16x2(make_float2(x4.z, x4.w), h1, l1);
+                *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT + C::PLANE) = make_uint2(l0, l1);
+            };
+            auto process_row = [&](int j) {
+                float2 a2 = make_float2(0.f, 0.f), u2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    float2 a2 = make_float2(0.f, 0.f), u2 = make_float2(0.f, 0.f);
+                for (int i = 0; i < 4; ++i) {
+                    const float4 x4 = buf[j][i];
+                    const float2 xy = make_float2(x4.x, x4.y), zw = make_float2(x4.z, x4.w);
+                    a2 = __ffma2_rn(xy, xy, a2);
+                    a2 = __ffma2_rn(zw, zw, a2);
+                    if (BWD) {
+                        u2 = __ffma2_rn(xy, make_float2(dvr[BWD ? i : 0].x, dvr[BWD ? i : 0].y), u2);
+                        u2 = __ffma2_rn(zw, make_float2(dvr[BWD ? i : 0].z, dvr[BWD ? i : 0].w), u2);
+                    }
+                }
+                float ssq = a2.x + a2.y, ud = u2.x + u2.y;
+                uint32_t ex = 127u;
+                const bool fast = __all_sync(0xffffffffu, ssq <= C::FAST_HI * (1.f / 32.f)) &&
+                                  __any_sync(0xffffffffu, ssq >= C::FAST_LO);
+                if (!fast) {
+                    // general path (warp-uniform, rare): power-of-two scale, largest |x| -> [1, 2); zero / denormal /
+                    // non-finite rows keep scale 1
+                    float mx = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(buf[j][i].x), fabsf(buf[j][i].y))),
+                                   fmaxf(fabsf(buf[j][i].z), fabsf(buf[j][i].w)));
+                    mx = warp_max(mx);
+                    ex = __float_as_uint(mx) >> 23;
+                    if (ex == 0u || ex >= 255u) ex = 127u;
+                    if (ex > 253u) ex = 253u;
+                    const float sc = __uint_as_float((254u - ex) << 23);
+                    ssq = 0.f;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 x4 = buf[s][k][i];
-                        const float2 xy = make_float2(x4.x, x4.y), zw = make_float2(x4.z, x4.w);
-                        a2 = __ffma2_rn(xy, xy, a2);
-                        a2 = __ffma2_rn(zw, zw, a2);
-                        if (BWD) {
-                            u2 = __ffma2_rn(xy, make_float2(dvr[BWD ? i : 0].x, dvr[BWD ? i : 0].y), u2);
-                            u2 = __ffma2_rn(zw, make_float2(dvr[BWD ? i : 0].z, dvr[BWD ? i : 0].w), u2);
-                        }
-                    }
-                    ssq[k] = a2.x + a2.y;
-                    ud[k] = u2.x + u2.y;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
-                        if (BWD) ud[k] += __shfl_xor_sync(0xffffffffu, ud[k], o);
+                        float4& x4 = buf[j][i];
+                        x4.x *= sc; x4.y *= sc; x4.z *= sc; x4.w *= sc;
+                        ssq += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w;
                     }
                 }
-                uint32_t exs[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    exs[k] = 127u;
-                    if (!(ssq[k] >= C::FAST_LO && ssq[k] <= C::FAST_HI)) {
-                        // general path (warp-uniform): power-of-two scale, largest |x| -> [1, 2); zero / denormal /
-                        // non-finite rows keep scale 1
-                        float mx = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(buf[s][k][i].x), fabsf(buf[s][k][i].y))),
-                                       fmaxf(fabsf(buf[s][k][i].z), fabsf(buf[s][k][i].w)));
-                        mx = warp_max(mx);
-                        uint32_t ex = __float_as_uint(mx) >> 23;
-                        if (ex == 0u || ex >= 255u) ex = 127u;
-                        if (ex > 253u) ex = 253u;
-                        exs[k] = ex;
-                        const float sc = __uint_as_float((254u - ex) << 23);
-                        float acc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float4& x4 = buf[s][k][i];
-                            x4.x *= sc; x4.y *= sc; x4.z *= sc; x4.w *= sc;
-                            acc += x4.x * x4.x + x4.y * x4.y + x4.z * x4.z + x4.w * x4.w;
-                        }
-                        ssq[k] = warp_sum(acc);
-                    }
-                }
-                if (s == 0) mbar_wait_wd(empty + b, (u & 1u) ^ 1u);
-                if (lane < 2) {
-                    const float sq = lane == 0 ? ssq[0] : ssq[1];
-                    const uint32_t ex = lane == 0 ? exs[0] : exs[1];
+                auto level = [&](int o) {
+                    ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+                    if (BWD) ud += __shfl_xor_sync(0xffffffffu, ud, o);
+                };
+                level(16);
+                convert_part(j, 0);
+                level(8);
+                convert_part(j, 1);
+                level(4);
+                convert_part(j, 2);
+                level(2);
+                convert_part(j, 3);
+                level(1);
+                if (lane == 0) {
                     // score = info.x * (Qn . x~), info.x = scale / max(|x~|, eps 2^-e);  x = 2^e x~ with 2^e = info.y;
                     // info.z = dv . x / P (backward).  1 / |x~| = rsqrt + one Newton step (<= 2 ulp).
                     float4 info;
                     info.y = __uint_as_float(ex << 23);
-                    float y = rsqrtf(sq);
-                    y = y * fmaf(-0.5f * sq * y, y, 1.5f);
-                    y = fminf(y, info.y * (1.f / VLSA_NORM_EPS));          // also catches sq == 0 (NaN -> cap)
+                    float y = rsqrtf(ssq);
+                    y = y * fmaf(-0.5f * ssq * y, y, 1.5f);
+                    y = fminf(y, info.y * (1.f / VLSA_NORM_EPS));          // also catches ssq == 0 (NaN -> cap)
                     info.x = prm.scale * y;
-                    info.z = BWD ? (lane == 0 ? ud[0] : ud[1]) : 0.f;
+                    info.z = BWD ? ud : 0.f;
                     info.w = 0.f;
-                    *reinterpret_cast<float4*>(s_rowinfo + (b * TR + 4 * pw + 2 * s + lane) * 4) = info;
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    unsigned char* dst = tile + soff[2 * s + k];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 x4 = buf[s][k][i];
-                        uint32_t h0, l0, h1, l1;
-                        split_f16x2(make_float2(x4.x, x4.y), h0, l0);
-                        split_f16x2(make_float2(x4.z, x4.w), h1, l1);
-                        *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2*>(dst + 2 * i * C::SLOT + C::PLANE) = make_uint2(l0, l1);
-                    }
+                    *reinterpret_cast<float4*>(s_rowinfo + (b * TR + 4 * pw + j) * 4) = info;
                 }
             };
-            // schedule: the proxy fence below waits for every outstanding load of the thread, so at the fence only
-            // set 0 of the next tile is in flight (issued half a tile earlier); set 1 is issued right after it
-            process_set(0);
-            if (nvalid) issue_set(0, nptr, nrows);
-            process_set(1);
+            // schedule: the proxy fence below waits for every outstanding load of the thread; with one row per
+            // register set only rows 0-2 of the next tile are in flight at the fence (the youngest a quarter of the
+            // conversion old), row 3 is issued right after it: tile period = load latency + a quarter conversion
+            mbar_wait_wd(empty + b, (u & 1u) ^ 1u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                process_row(j);
+                if (j < 3 && nvalid) issue_row(j, nptr, nrows);
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + b);
-            if (nvalid) issue_set(1, nptr, nrows);
+            if (nvalid) issue_row(3, nptr, nrows);
             ++tt;
             if (pw == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(s_prog) = tt;
             valid = nvalid; tptr = nptr; rows_left = nrows;
         }
     } else if (warp >= C::NSOFT) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
       if (warp == C::W_PF) {
         // =========================================================================== L2 prefetcher
         // one bulk prefetch per tile, PF tiles ahead of the tile the producers are filling: DRAM latency is absorbed
         // by the 126 MB L2, so one tile of loads in flight per SM (64 KB of registers) streams at full rate
-        if (lane == 0) {
+        if (C::PF > 0) {
             const float* X = reinterpret_cast<const float*>(prm.X);
             int fcc = blockIdx.x; long long frow = 0, fr1 = 0; bool fvalid = fcc < prm.total_chunks;
             if (fvalid) { int fb; chunk_info(prm, fcc, fb, frow, fr1); }
             auto prefetch_tile = [&]() {
                 if (!fvalid) return;
                 const long long n = fr1 - frow < TR ? fr1 - frow : TR;
-                l2_prefetch_bulk(X + frow * D, uint32_t(n) * D * 4u);
+#ifdef VLSA_TC_LANEPF
+                // one 128-byte line per lane and instruction: 16 lines per row
+                for (int l = lane; l < int(n) * 16; l += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(X + frow * D + l * 32));
+#else
+                if (lane == 0) l2_prefetch_bulk(X + frow * D, uint32_t(n) * D * 4u);
+#endif
                 frow += TR;
                 if (frow >= fr1) {
                     fcc += gridDim.x;
@@ -387,10 +401,10 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         __syncwarp();
     } else if (warp == C::W_G1) {
         // =========================================================================== GEMM1 issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * TR, false, false);
-            const uint32_t ring_a = smem_u32(ring);
-            const uint32_t d1 = tmem + C::TM_D1;
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(ring), 16, 1024);
+            const uint32_t d1 = tmem + C::TM_D1, tq0 = tmem + C::TM_Q;
             uint32_t tt = 0;
             for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
                 int bag; long long r0, r1;
@@ -401,25 +415,26 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     mbar_wait_wd(s_free, (tt & 1u) ^ 1u);           // scores of the previous tile have been read
                     mbar_wait_wd(full + b, u & 1u);
                     tc_fence_after();
-                    const uint32_t tb = ring_a + b * C::TILE;
-#pragma unroll 1
+                    const uint64_t tb = umma_desc_advance(desc0, b * C::TILE);
+#pragma unroll
                     for (int s = 0; s < C::NSLOT; ++s) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)              // B = 64 rows: hi plane | lo plane of the slot
-                            tc_mma_ts(d1, tmem + C::TM_Q + (s * 4 + ks) * 8,
-                                      umma_desc_sw128(tb + s * C::SLOT + ks * 32, 16, 1024), idesc1, (s | ks) != 0);
+                            tc_mma_ts(d1, tq0 + (s * 4 + ks) * 8, umma_desc_advance(tb, s * C::SLOT + ks * 32), idesc1,
+                                      (s | ks) != 0);
                     }
                     tc_commit(s_ready);
                 }
             }
         }
         __syncwarp();
-    } else if (warp == C::W_G2) {
+      } else if (warp == C::W_G2) {
         // =========================================================================== GEMM2 issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc_hi = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * NP, true, false);
             constexpr uint32_t idesc_lo = umma_idesc(UMMA_F16, UMMA_F16, 128, NP, true, false);
-            const uint32_t ring_a = smem_u32(ring), w_a = smem_u32(wt);
+            const uint64_t a0 = umma_desc_sw128(smem_u32(ring), C::SLOT, 1024);
+            const uint64_t w0 = umma_desc_sw128(smem_u32(wt), 16, 1024);
             uint32_t tt = 0, cc = 0;
             for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x, ++cc) {
                 int bag; long long r0, r1;
@@ -430,16 +445,17 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     mbar_wait_wd(w_ready + i, v & 1u);
                     if (t == 0) mbar_wait_wd(d2_free, (cc & 1u) ^ 1u);   // previous chunk's accumulators drained
                     tc_fence_after();
-                    const uint32_t tb = ring_a + b * C::TILE, wb = w_a + i * C::WBUF;
+                    const uint64_t tb = umma_desc_advance(a0, b * C::TILE), wb = umma_desc_advance(w0, i * C::WBUF);
+                    const uint32_t acc0 = t != 0;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const uint32_t d2 = tmem + C::TM_D2 + g * C::D2W;
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {              // 16 tile rows per step
-                            const uint32_t ah = tb + (2 * g) * C::SLOT + ks * 2048;
-                            const uint64_t bd = umma_desc_sw128(wb + ks * 32, 16, 1024);
-                            tc_mma_ss(d2, umma_desc_sw128(ah, C::SLOT, 1024), bd, idesc_hi, (t | ks) != 0);
-                            tc_mma_ss(d2 + 2 * NP, umma_desc_sw128(ah + C::PLANE, C::SLOT, 1024), bd, idesc_lo, (t | ks) != 0);
+                            const uint64_t ah = umma_desc_advance(tb, (2 * g) * C::SLOT + ks * 2048);
+                            const uint64_t bd = umma_desc_advance(wb, ks * 32);
+                            tc_mma_ss(d2, ah, bd, idesc_hi, ks ? 1u : acc0);
+                            tc_mma_ss(d2 + 2 * NP, umma_desc_advance(ah, C::PLANE), bd, idesc_lo, ks ? 1u : acc0);
                         }
                     }
                     tc_commit(empty + b);

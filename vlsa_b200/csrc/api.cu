@@ -20,7 +20,15 @@ using namespace vlsa;
         if (_e != cudaSuccess) return static_cast<int>(_e); \
     } while (0)
 
-// switch over the compile-time prototype count
+// switch over the compile-time prototype count (VLSA_DEV_FEWP: development builds with P in {4, 12} only)
+#ifdef VLSA_DEV_FEWP
+#define VLSA_DISPATCH_P(P_, ...)                                   \
+    switch (P_) {                                                  \
+        case 4: { constexpr int kP = 4; __VA_ARGS__; break; }      \
+        case 12: { constexpr int kP = 12; __VA_ARGS__; break; }    \
+        default: return VLSA_EINVAL;                               \
+    }
+#else
 #define VLSA_DISPATCH_P(P_, ...)                                   \
     switch (P_) {                                                  \
         case 1: { constexpr int kP = 1; __VA_ARGS__; break; }      \
@@ -41,6 +49,7 @@ using namespace vlsa;
         case 16: { constexpr int kP = 16; __VA_ARGS__; break; }    \
         default: return VLSA_EINVAL;                               \
     }
+#endif
 
 static constexpr int kRowTile = 32;   // TcCfg::TR; a multiple of the CUDA-core kernel's AggCfg::TN
 static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile == TcCfg::TR, "chunk_rows must suit both streaming kernels");

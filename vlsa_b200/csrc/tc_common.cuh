@@ -39,6 +39,18 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
     tc_mma_ss(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 
+// one lane of the (converged) warp: the compiler treats an elect.sync branch as uniform, so tcgen05.mma / commit
+// inside it compile to straight-line UTCHMMA (a `lane == 0` test makes it emit an ELECT loop around every MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // instruction descriptor, kind::f16 with f32 accumulator
 //   [4,6) c_format=1 (f32) | [7,10) a_format | [10,13) b_format (0 = f16, 1 = bf16) | 15 a_major (1 = MN) | 16 b_major |
 //   [17,23) N>>3 | [24,29) M>>4
@@ -56,6 +68,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
     return uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            (uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
+// the same descriptor with the start address advanced by `bytes` (no carry out of the 14-bit field: smem < 256 KB)
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 // byte offset of element (row, 16-byte chunk c, byte b) inside a [rows x 128 B] tile with 128-byte swizzle
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16, uint32_t byte_in_chunk) {
     return row * 128u + (((chunk16 ^ (row & 7u)) & 7u) << 4) + byte_in_chunk;
