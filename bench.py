@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--R", type=int, default=4, help="ordinal ranks")
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"], help="storage dtype of X")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
@@ -247,7 +248,12 @@ def main():
     W, b = net.mil_encoder.visual_adapter.weight.detach(), net.mil_encoder.visual_adapter.bias.detach()
     T, ls = net.forward_text_only().contiguous(), net.logit_scale.detach()
     ws = ops._workspace(plan, P, dev)
-    launches_per_step = 4                      # agg_simt, merge_fwd, adapter_fwd, head_fwd
+    use_tc = args.dtype == "fp32" and P > 4 and os.environ.get("VLSA_AGG_VARIANT", "")[:1] != "s" \
+        or os.environ.get("VLSA_AGG_VARIANT", "")[:1] == "t" and args.dtype == "fp32"
+    kernel_name = "agg_tc_kernel<false> (tcgen05)" if use_tc else "agg_simt_kernel<P,false,XT>"
+    two_level = plan.total_chunks >= 8 * nb
+    # streaming kernel, [merge level 1,] merge, adapter, head
+    launches_per_step = 4 + (1 if two_level else 0)
 
     def step(i):
         return ops.aggregate_forward_raw(batches[i % n_batches], plan, Q, W, b, T, ls, need_bwd=False, workspace=ws)
@@ -283,6 +289,48 @@ def main():
     torch.cuda.synchronize(dev)
     kernel_ms = k0.elapsed_time(k1) / args.steps
     clocks = sampler.stop()
+
+    # ---- one optimizer step (config 3): forward + fused loss + backward + ONE flat all-reduce + Adam ------
+    train = None
+    if not args.no_train:
+        from vlsa_b200.runner import VLSAHandler
+        cfg = {"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4}
+        net.train()
+        handler = VLSAHandler(cfg, net=net, device=dev)
+        t_lab, e_lab = synth.make_labels(nb, R, 77 + rank)
+        label = torch.stack([t_lab, e_lab], 1).to(dev)
+        n_global = nb * world
+
+        def train_step(i):
+            handler.optimizer.zero_grad(set_to_none=True)
+            logits, _, _, _ = handler.net.forward_packed(batches[i % n_batches], plan)
+            loss = handler.calc_objective_loss(logits, label, norm=n_global)
+            loss.backward()
+            handler.bucket.pack(loss.detach().reshape(1))
+            handler.bucket.all_reduce()
+            handler.bucket.unpack()
+            handler.optimizer.step()
+
+        n_train = max(3, min(args.steps, 10))
+        for i in range(3):
+            train_step(i)
+        sync_all()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(n_train):
+            train_step(i)
+        t1e.record()
+        sync_all()
+        train_ms = t0e.elapsed_time(t1e) / n_train
+        tt_ = torch.tensor([train_ms], device=dev)
+        if dist is not None:
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+        train_ms = float(tt_[0])
+        train = {"value": nb * world / (train_ms * 1e-3), "unit": "WSI/s", "ms_per_step": train_ms, "steps": n_train,
+                 "what": "VLSAHandler step on device-resident bags: forward_packed + SurvIFMLE/SurvEMD + backward "
+                         "(X read twice) + one flat-bucket all-reduce + Adam",
+                 "hbm_gbs_over_two_reads": 2 * nb * rows * 512 * esize / (train_ms * 1e-3) / 1e9}   # per GPU
+        net.eval()
 
     # ---- e2e: host buffers -> public API -> host result, copies inside the timed region --------------
     e2e = None
@@ -344,11 +392,16 @@ def main():
         "dtype": "f32" if args.dtype == "fp32" else "f32 accumulate, bf16 storage", "data": "synthetic",
         "config": workload_config(args, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "agg_simt_kernel<P,false,XT>", "kernel_ms": kernel_ms,
+                     "traffic": None, "kernel": kernel_name, "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                     "kernel_share_of_step": kernel_ms / (ms_total / args.steps)},
-        "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "e2e": e2e,
+                     "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
+                     "read_only_ceiling_gbs": 7300.0,
+                     "read_only_ceiling_source": "scripts/dev_readbw.cu on this pool: a pure cp.async.bulk read stream "
+                                                 "of the same 3.28 GB (profiles/readbw_r01.txt)"},
+        "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "e2e": e2e, "train_step": train,
     }
+    if train is not None:
+        train["frac_of_peak"] = train["hbm_gbs_over_two_reads"] / peak   # per GPU
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(traffic_file):
         try:

@@ -6,7 +6,10 @@ rep = sys.argv[1]
 tiles = int(sys.argv[2]) if len(sys.argv) > 2 else 50000
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = rows[1]; data = rows[2:]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # kernel index inside the report
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+rows = rows[starts[which]:starts[which + 1]]
+hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 ie = hdr.index("Instructions Executed"); sm = hdr.index("# Samples"); so = hdr.index("Source")
 stall = [i for i, c in enumerate(hdr) if c.startswith("stall_") and "Not Issued" not in c]
 print("kernel:", rows[0][1][:60])

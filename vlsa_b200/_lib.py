@@ -20,6 +20,7 @@ c_i32p = C.c_void_p
 _SIGNATURES = {
     "vlsa_version": (C.c_int, []),
     "vlsa_error_string": (C.c_char_p, [C.c_int]),
+    "vlsa_debug_set_agg_variant": (C.c_int, [C.c_int]),
     "vlsa_agg_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32)]),
     "vlsa_agg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,

@@ -147,16 +147,19 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
 }
 
 // Which streaming kernel serves an fp32 pass (forward or backward): the tcgen05 variant or the CUDA-core one.
-// VLSA_AGG_VARIANT=simt|tc overrides (development / cross-checking); default: see agg_use_tc().
+// Default: tensor cores for P > 4 (the CUDA-core kernel is faster at P <= 4).  Cross-checking hooks:
+// the environment variable VLSA_AGG_VARIANT=simt|tc and vlsa_debug_set_agg_variant() force one of them.
+#include <atomic>
+static std::atomic<int> g_agg_variant{[] {
+    const char* e = getenv("VLSA_AGG_VARIANT");
+    if (!e) return -1;
+    if (e[0] == 't') return 1;
+    if (e[0] == 's') return 0;
+    return -1;
+}()};
 static bool agg_use_tc(int P, int x_dtype) {
-    static const int forced = [] {
-        const char* e = getenv("VLSA_AGG_VARIANT");
-        if (!e) return -1;
-        if (e[0] == 't') return 1;
-        if (e[0] == 's') return 0;
-        return -1;
-    }();
     if (x_dtype != VLSA_DTYPE_F32) return false;
+    const int forced = g_agg_variant.load(std::memory_order_relaxed);
     if (forced >= 0) return forced == 1;
     return P > 4;
 }
@@ -173,7 +176,13 @@ static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t
 
 extern "C" {
 
-int vlsa_version(void) { return 100; }
+int vlsa_version(void) { return 101; }
+
+int vlsa_debug_set_agg_variant(int variant) {
+    if (variant < -1 || variant > 1) return VLSA_EINVAL;
+    g_agg_variant.store(variant, std::memory_order_relaxed);
+    return 0;
+}
 
 const char* vlsa_error_string(int code) {
     if (code == 0) return "success";

@@ -25,6 +25,15 @@ def coattn_scale() -> float:
     return float((torch.ones([]) * np.log(100)).exp())
 
 
+def set_agg_variant(variant: str | None) -> None:
+    """Cross-check hook: force the streaming kernel of fp32 passes ('simt' = CUDA cores, 'tc' = tcgen05) or
+    None for the automatic choice (tensor cores for P > 4)."""
+    code = {None: -1, "auto": -1, "simt": 0, "tc": 1}[variant]
+    rc = _lib.lib().vlsa_debug_set_agg_variant(code)
+    if rc:
+        raise RuntimeError(_lib.lib().vlsa_error_string(rc).decode())
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
