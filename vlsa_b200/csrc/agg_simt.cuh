@@ -77,6 +77,16 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     constexpr int NW = C::NW, CPT = C::CPT;
     static_assert(TN <= 32 && (CPT == 2 || CPT == 4), "phase S maps rows to lanes; phase B loads 8 or 16 bytes");
     constexpr bool BF16 = sizeof(XT) == 2;
+#ifdef VLSA_SIMT_NOPACK
+    constexpr bool PACKED_B = false;
+#else
+    constexpr bool PACKED_B = true;
+#endif
+#ifdef VLSA_SIMT_NOPACK
+    constexpr bool PACKED = false;
+#else
+    constexpr bool PACKED = NV <= 40;          // packed phase-A accumulators double their register count: P <= 8
+#endif
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     XT* xs = reinterpret_cast<XT*>(smem_raw);
@@ -169,7 +179,38 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
             float acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-            if (!BF16) {
+            if (!BF16 && PACKED) {
+                // packed fp32x2 FMAs (sm_100 FFMA2): two partial sums per value, half the FMA instructions
+                float2 acc2p[NV];
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc2p[i] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 xv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        xv[r] = *reinterpret_cast<const float4*>(
+                            reinterpret_cast<const float*>(xt) + size_t(4 * warp + r) * D + j * 128 + lane * 4);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float2 lo = make_float2(xv[r].x, xv[r].y), hi = make_float2(xv[r].z, xv[r].w);
+                        acc2p[r * NRED + NQ] = __ffma2_rn(lo, lo, acc2p[r * NRED + NQ]);
+                        acc2p[r * NRED + NQ] = __ffma2_rn(hi, hi, acc2p[r * NRED + NQ]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 qv = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
+                        const float2 qlo = make_float2(qv.x, qv.y), qhi = make_float2(qv.z, qv.w);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            acc2p[r * NRED + q] = __ffma2_rn(qlo, make_float2(xv[r].x, xv[r].y), acc2p[r * NRED + q]);
+                            acc2p[r * NRED + q] = __ffma2_rn(qhi, make_float2(xv[r].z, xv[r].w), acc2p[r * NRED + q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] = acc2p[i].x + acc2p[i].y;
+            } else if (!BF16) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 xv[4];
@@ -295,8 +336,17 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (4 * k4 + j < P) {
+                            float* a = acc2[(4 * k4 + j < P) ? 4 * k4 + j : 0];
+                            if (!BF16 && CPT == 4 && PACKED_B) {
+                                // FFMA2 with the weight as the broadcast scalar operand
+                                const float2 ww = make_float2(wv[j], wv[j]);
+                                const float2 r0 = __ffma2_rn(ww, make_float2(xv[0], xv[1]), make_float2(a[0], a[1]));
+                                const float2 r1 = __ffma2_rn(ww, make_float2(xv[CPT - 2], xv[CPT - 1]), make_float2(a[CPT - 2], a[CPT - 1]));
+                                a[0] = r0.x; a[1] = r0.y; a[CPT - 2] = r1.x; a[CPT - 1] = r1.y;
+                            } else {
 #pragma unroll
-                            for (int k = 0; k < CPT; ++k) acc2[(4 * k4 + j < P) ? 4 * k4 + j : 0][k] += wv[j] * xv[k];
+                                for (int k = 0; k < CPT; ++k) a[k] += wv[j] * xv[k];
+                            }
                         }
                     }
                 }
