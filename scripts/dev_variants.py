@@ -8,7 +8,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     dev = torch.device("cuda:0")
     cfgs = ((4, 50000, 32, torch.float32), (12, 50000, 32, torch.float32), (12, 10000, 32, torch.float32))
     if os.environ.get("DEV_CFGS") == "simt":
-        cfgs = ((4, 50000, 32, torch.float32), (4, 10000, 32, torch.float32), (4, 50000, 1, torch.float32))
+        cfgs = ((4, 50000, 32, torch.float32), (4, 50000, 32, torch.bfloat16), (12, 50000, 32, torch.bfloat16))
     for (P, N, B, dt) in cfgs:
         pr = synth.make_params(P, P, 1)
         Xs = [(torch.randn(N * B, 512, device=dev) * 1.1).to(dt) for _ in range(2 if B > 1 else 8)]

@@ -240,18 +240,46 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                         xf[r][0] = bf16_lo(u.x); xf[r][1] = bf16_hi(u.x); xf[r][2] = bf16_lo(u.y); xf[r][3] = bf16_hi(u.y);
                         xf[r][4] = bf16_lo(u.z); xf[r][5] = bf16_hi(u.z); xf[r][6] = bf16_lo(u.w); xf[r][7] = bf16_hi(u.w);
                     }
+                    if (PACKED) {
+                        // packed fp32x2 FMAs; the two halves of every pair are added once per 256-column block
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
+                        for (int r = 0; r < 4; ++r) {
+                            float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[r * NRED + NQ] += xf[r][k] * xf[r][k];
+                            for (int k = 0; k < 8; k += 2) {
+                                const float2 x2 = make_float2(xf[r][k], xf[r][k + 1]);
+                                a = __ffma2_rn(x2, x2, a);
+                            }
+                            acc[r * NRED + NQ] += a.x + a.y;
+                        }
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const float4 qa = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
-                        const float4 qb = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+                        for (int q = 0; q < NQ; ++q) {
+                            const float4 qa = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
+                            const float4 qb = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+                            const float2 q2[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y),
+                                                  make_float2(qb.z, qb.w)};
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) a = __ffma2_rn(q2[k], make_float2(xf[r][2 * k], xf[r][2 * k + 1]), a);
+                                acc[r * NRED + q] += a.x + a.y;
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
-                            acc[r * NRED + q] += qa.x * xf[r][0] + qa.y * xf[r][1] + qa.z * xf[r][2] + qa.w * xf[r][3] +
-                                                 qb.x * xf[r][4] + qb.y * xf[r][5] + qb.z * xf[r][6] + qb.w * xf[r][7];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) acc[r * NRED + NQ] += xf[r][k] * xf[r][k];
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const float4 qa = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
+                            const float4 qb = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r)
+                                acc[r * NRED + q] += qa.x * xf[r][0] + qa.y * xf[r][1] + qa.z * xf[r][2] + qa.w * xf[r][3] +
+                                                     qb.x * xf[r][4] + qb.y * xf[r][5] + qb.z * xf[r][6] + qb.w * xf[r][7];
+                        }
                     }
                 }
             }
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     for (int j = 0; j < 4; ++j) {
                         if (4 * k4 + j < P) {
                             float* a = acc2[(4 * k4 + j < P) ? 4 * k4 + j : 0];
-                            if (!BF16 && CPT == 4 && PACKED_B) {
+                            if (CPT == 4 && PACKED_B) {
                                 // FFMA2 with the weight as the broadcast scalar operand
                                 const float2 ww = make_float2(wv[j], wv[j]);
                                 const float2 r0 = __ffma2_rn(ww, make_float2(xv[0], xv[1]), make_float2(a[0], a[1]));
