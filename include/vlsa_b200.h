@@ -102,10 +102,23 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
                  const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
                  float* dT, float* dlogit_scale, void* stream);
 
-/* Attention read-out of ONE bag: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1]
- * (`ret_with_attn=True`, model/deepmil.py:206-213).  ml [P,2] comes from vlsa_agg_fwd.  out_A is [P,N]. */
+/* Attention read-out of ONE bag (`ret_with_attn=True`, model/deepmil.py:206-213; utils/model_inference.py:104-113).
+ * ml != NULL: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1], the softmax over the N patches with the
+ *   normalisers ml [P,2] from vlsa_agg_fwd (axis_softmax = 'V', the `cottn_score` of the forward);
+ * ml == NULL: A[p][n] = softmax over the P prototypes of scale * cos(Q_p, x_n) (axis_softmax = 'L').
+ * out_A is [P,N]. */
 int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
                   float* out_A, void* stream);
+
+/* Interpretation path, "decoupled" text-image similarities per prototype (utils/model_inference.py:115-131):
+ *   sim[b][p][r]  = cottn_score_p @ ((visual_adapter(X) / |f_b|) @ Tn_r)  =  (W O_bp + bias) . Tn_r / |f_b|
+ * (attention rows sum to one, so the N-long contraction collapses onto the pooled O [B,P,D] that vlsa_agg_fwd
+ * returns: no second pass over X), decoupled_imp = softmax over P of e^logit_scale sim, probs_2 = softmax over R of
+ * e^logit_scale mean_P sim.  f [B,D] is the un-normalised adapter output of vlsa_agg_fwd.
+ * out_sim, out_imp are [B,P,R]; out_probs is [B,R]. */
+int vlsa_interp_fwd(const float* O, const float* W, const float* bias, const float* T, int R, const float* f,
+                    const float* logit_scale, int B, int P, float* out_sim, float* out_imp, float* out_probs,
+                    void* stream);
 
 /* softmax -> w_ifmle * SurvIFMLE + w_emd * SurvEMD, value and gradient in one pass
  * (runner/vlsa_handler.py:241-258; loss/loss_surv.py:144-169 with alpha/eps; loss/loss_surv_ext.py:70-109

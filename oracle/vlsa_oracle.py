@@ -176,6 +176,34 @@ def decoupled_similarity(X, Q, W, b, T, logit_scale):
     return A.squeeze(0), probs, probs_2, dec
 
 
+def prototype_shap_imp(decoupled_similarity, logit_scale: float):
+    """utils/model_inference.py:21-78, subset by subset as the reference does (P <= ~10 in tests)."""
+    sim = torch.as_tensor(decoupled_similarity)
+    num_p, num_cls = sim.shape
+
+    def risk(sel):
+        prob = F.softmax(logit_scale * sim[sel].mean(dim=0), dim=0)
+        return float(torch.sum((num_cls - torch.arange(0, num_cls)) * prob))
+
+    def members(code):
+        return [i for i in range(num_p) if (code >> i) & 1]
+
+    n_cases = 2 ** num_p
+    V = [1.0] + [risk(members(i)) for i in range(1, n_cases)]
+    fac = [math.factorial(i) for i in range(num_p + 1)]
+    wgt = [fac[i] * fac[num_p - i - 1] / fac[num_p] for i in range(num_p)]
+    out = torch.zeros(num_p)
+    for i in range(num_p):
+        acc = 0.0
+        for j in range(n_cases):
+            sel = members(j)
+            if i in sel:
+                continue
+            acc += wgt[len(sel)] * (V[j + 2 ** i] - V[j])
+        out[i] = acc
+    return out
+
+
 def forward_with_grads(bags, prompt_features, residual, W, b, T, logit_scale, t, e,
                        res_ratio: float = 0.5, w_ifmle: float = 1.0, w_emd: float = 1.0,
                        dtype=torch.float32):

@@ -209,3 +209,38 @@ def test_loss_modules_keep_reference_signature(dev):
     assert isinstance(SurvIFMLE(reduction="sum"), torch.nn.Module) and isinstance(SurvEMD(), torch.nn.Module)
     with pytest.raises(NotImplementedError):
         SurvEMD(p=1)
+
+
+@pytest.mark.parametrize("P,R,N,kind,axis", [(12, 12, 2798, "g1", "V"), (4, 4, 1000, "g0", "L"), (7, 13, 5000, "g1", "V")])
+def test_interpretation_path_matches_reference_formula(P, R, N, kind, axis, dev):
+    """utils/model_inference.py:81-144 (`calc_text_img_similarity`): attention, decoupled similarities and their
+    softmaxes from ONE streaming pass vs the reference's formula evaluated the long way (visual_adapter over all N
+    patches) in fp64."""
+    import numpy as np
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import synth
+    from vlsa_b200.utils import calc_text_img_similarity
+    pr = synth.make_params(P, R, 40 + P)
+    net = build_net(pr, P, R, dev)
+    X = synth.make_bag(kind, N, 77 + N)
+    _, A, cottn, probs, probs2, imp, shap = calc_text_img_similarity(net, X.unsqueeze(0), axis_softmax=axis)
+    c = lambda z: z.double()
+    Q64 = O.task_res_query(c(pr["prompt_features"]), c(pr["residual_features"]), pr["res_ratio"])
+    A64, probs64, probs2_64, dec64 = O.decoupled_similarity(c(X).unsqueeze(0), Q64, c(pr["W"]), c(pr["b"]),
+                                                            c(pr["text_features"]), c(pr["logit_scale"]))
+    np.testing.assert_allclose(cottn.numpy(), A64.numpy(), rtol=2e-4, atol=1e-9)
+    if axis == "V":
+        np.testing.assert_allclose(A.numpy(), A64.numpy(), rtol=2e-4, atol=1e-9)
+    else:
+        Qn = Q64 / Q64.norm(dim=-1, keepdim=True); Xn = c(X) / c(X).norm(dim=-1, keepdim=True)
+        AL = torch.softmax(O.coattn_scale() * Qn @ Xn.T, dim=0)
+        np.testing.assert_allclose(A.numpy(), AL.numpy(), rtol=2e-4, atol=1e-7)
+    assert np.abs(probs.numpy() - probs64.numpy()).max() <= 2e-5
+    assert np.abs(probs2.numpy() - probs2_64.numpy()).max() <= 2e-5
+    ls = float(pr["logit_scale"].exp())
+    imp64 = torch.softmax(ls * dec64, dim=0)
+    assert np.abs(imp.numpy() - imp64.numpy()).max() <= 5e-5
+    shap64 = O.prototype_shap_imp(dec64.float(), ls) if P <= 9 else None
+    if shap64 is not None:
+        np.testing.assert_allclose(shap.numpy(), shap64.numpy(), atol=2e-4)
+    assert shap.shape == (P,)

@@ -155,3 +155,21 @@ def test_pack_bags_and_loader_host_side():
     packed, sizes = pack_bags(bags, out)
     assert sizes == [3, 5, 0] and packed.data_ptr() == out.data_ptr()
     assert torch.equal(packed[:3], bags[0]) and torch.equal(packed[3:8], bags[1][0])
+
+
+def test_prototype_shap_vectorised_matches_reference_loops():
+    """utils/model_inference.py:21-78: the all-subsets-at-once evaluation equals the reference's subset loop."""
+    import numpy as np
+    import torch
+    from oracle import vlsa_oracle as O
+    from vlsa_b200.utils.model_inference import evaluate_prototype_shap_imp
+    g = torch.Generator().manual_seed(3)
+    for P, R in ((1, 4), (4, 4), (7, 12), (9, 13)):
+        sim = (torch.rand(P, R, generator=g) * 2 - 1) * 0.3
+        ref = O.prototype_shap_imp(sim, 56.3)
+        got = evaluate_prototype_shap_imp(sim, 56.3)
+        np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-5, rtol=1e-4)
+        # efficiency axiom: the values add up to value(full) - value(empty)
+        full = torch.softmax(56.3 * sim.mean(0), 0)
+        total = float(((R - torch.arange(R)) * full).sum()) - 1.0
+        assert abs(float(got.sum()) - total) < 1e-3

@@ -36,6 +36,8 @@ _SIGNATURES = {
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "vlsa_attn_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_float, c_f32p, c_f32p,
                                 C.c_void_p]),
+    "vlsa_interp_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p,
+                                  c_f32p, c_f32p, C.c_void_p]),
     "vlsa_surv_loss_fwd_bwd": (C.c_int, [c_f32p, c_i64p, c_i64p, C.c_int, C.c_int, c_f32p, C.c_float, C.c_float,
                                          C.c_float, C.c_float, C.c_float, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p,
                                          C.c_void_p]),

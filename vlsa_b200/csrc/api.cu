@@ -359,19 +359,33 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
 int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
                   float* out_A, void* stream) {
     if (N == 0) return 0;
-    if (!X || !Q || !ml || !out_A || N < 0 || P < 1 || P > VLSA_MAX_P) return VLSA_EINVAL;
+    if (!X || !Q || !out_A || N < 0 || P < 1 || P > VLSA_MAX_P) return VLSA_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = (size_t(P) * VLSA_D + 32 * (P + 1)) * sizeof(float);
     const unsigned grid = unsigned((N + 31) / 32);
-    if (x_dtype == VLSA_DTYPE_F32) {
-        row_cosine_kernel<float, 0><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale,
-                                                              nullptr, ml, out_A);
-    } else if (x_dtype == VLSA_DTYPE_BF16) {
-        row_cosine_kernel<__nv_bfloat16, 0><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P,
-                                                                      coattn_scale, nullptr, ml, out_A);
-    } else {
-        return VLSA_EUNSUPPORTED;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    const bool f32 = x_dtype == VLSA_DTYPE_F32;
+    if (ml) {       // softmax over the N patches, normalisers from the forward
+        if (f32) row_cosine_kernel<float, 0><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A);
+        else row_cosine_kernel<__nv_bfloat16, 0><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A);
+    } else {        // softmax over the P prototypes per patch
+        if (f32) row_cosine_kernel<float, 2><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A);
+        else row_cosine_kernel<__nv_bfloat16, 2><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A);
     }
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_interp_fwd(const float* O, const float* W, const float* bias, const float* T, int R, const float* f,
+                    const float* logit_scale, int B, int P, float* out_sim, float* out_imp, float* out_probs,
+                    void* stream) {
+    if (B == 0) return 0;
+    if (!O || !W || !bias || !T || !f || !logit_scale || !out_sim || !out_imp || !out_probs) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    interp_sim_kernel<<<B * P, 256, 0, st>>>(O, W, bias, T, R, f, P, out_sim);
+    VLSA_CUDA(cudaGetLastError());
+    interp_softmax_kernel<<<B, VLSA_MAX_R, 0, st>>>(out_sim, P, R, logit_scale, out_imp, out_probs);
     VLSA_CUDA(cudaGetLastError());
     return 0;
 }

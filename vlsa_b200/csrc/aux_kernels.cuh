@@ -51,6 +51,7 @@ __device__ __forceinline__ void load_normalized_rows(const float* __restrict__ s
 // cos[n][q] * mult for one bag; block = 256 threads = 8 warps x 4 rows = 32 rows per block.
 // MODE 0: A[q][n] = exp(scale*cos - m_q) / l_q          (attention read-out, out is [nq, N])
 // MODE 1: out[n][q] = mult * cos                        (per-patch logits, out is [N, nq])
+// MODE 2: A[q][n] = softmax over q of scale*cos          (utils/model_inference.py:104-113, axis_softmax='L')
 template <typename XT, int MODE>
 __global__ void __launch_bounds__(256) row_cosine_kernel(const XT* __restrict__ X, long long N, const float* __restrict__ Qsrc,
                                                          int nq, float mult, const float* __restrict__ mult_log,
@@ -89,11 +90,79 @@ __global__ void __launch_bounds__(256) row_cosine_kernel(const XT* __restrict__ 
             if (r < nrows)
                 out[size_t(q) * N + row0 + r] = expf(mult * s_out[r * (nq + 1) + q] - ml[q * 2]) / ml[q * 2 + 1];
         }
+    } else if (MODE == 2) {
+        for (int r = tid; r < nrows; r += 256) {
+            float mx = -INFINITY, sum = 0.f;
+            for (int q = 0; q < nq; ++q) mx = fmaxf(mx, mult * s_out[r * (nq + 1) + q]);
+            for (int q = 0; q < nq; ++q) sum += expf(mult * s_out[r * (nq + 1) + q] - mx);
+            for (int q = 0; q < nq; ++q) out[size_t(q) * N + row0 + r] = expf(mult * s_out[r * (nq + 1) + q] - mx) / sum;
+        }
     } else {
         for (int i = tid; i < nrows * nq; i += 256) {
             const int r = i / nq, q = i % nq;
             out[size_t(row0 + r) * nq + q] = (mult * s_out[r * (nq + 1) + q]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Interpretation path (utils/model_inference.py:115-131), without a second pass over X: the attention rows sum
+// to one, so  cottn_score @ ((visual_adapter(X) / |f|) @ Tn^T)  =  (W O_p + b) . Tn_r / |f|  with the per-prototype
+// pooled features O_p the forward already produced.  grid B*P, 256 threads; out_sim is [B, P, R].
+__global__ void __launch_bounds__(256) interp_sim_kernel(const float* __restrict__ O, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, const float* __restrict__ T, int R,
+                                                         const float* __restrict__ f, int P, float* __restrict__ out_sim) {
+    constexpr int D = VLSA_D;
+    __shared__ __align__(16) float s_o[D];
+    __shared__ float s_e[D];
+    __shared__ float s_red[32];
+    const int bp = blockIdx.x, b = bp / P, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int d = tid; d < D; d += 256) s_o[d] = O[size_t(bp) * D + d];
+    float ff = 0.f;
+    for (int d = tid; d < D; d += 256) { const float v = f[size_t(b) * D + d]; ff += v * v; }
+    ff = block_sum(ff, s_red);                                   // also orders the s_o writes
+    const float invL = 1.f / sqrtf(ff);                          // image_feature / L_image_feature: no eps in the reference
+    for (int o = warp; o < D; o += 8) {
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(W + size_t(o) * D + j * 128 + lane * 4));
+            const float4 x = *reinterpret_cast<const float4*>(s_o + j * 128 + lane * 4);
+            a += w.x * x.x + w.y * x.y + w.z * x.z + w.w * x.w;
+        }
+        a = warp_sum(a);
+        if (lane == 0) s_e[o] = a + bias[o];
+    }
+    __syncthreads();
+    for (int r = warp; r < R; r += 8) {
+        float dot = 0.f, tt = 0.f;
+        for (int d = lane; d < D; d += 32) { const float t = __ldg(T + size_t(r) * D + d); dot += t * s_e[d]; tt += t * t; }
+        dot = warp_sum(dot); tt = warp_sum(tt);
+        if (lane == 0) out_sim[size_t(bp) * R + r] = dot / fmaxf(sqrtf(tt), VLSA_NORM_EPS) * invL;
+    }
+}
+
+// decoupled_imp = softmax over P of ls*sim ; probs_2 = softmax over R of ls*mean_P(sim).  grid B, 32*ceil(R/32) threads.
+__global__ void __launch_bounds__(VLSA_MAX_R) interp_softmax_kernel(const float* __restrict__ sim, int P, int R,
+                                                                    const float* __restrict__ logit_scale,
+                                                                    float* __restrict__ out_imp, float* __restrict__ out_probs) {
+    __shared__ float s_mean[VLSA_MAX_R];
+    const int b = blockIdx.x, r = threadIdx.x;
+    const float ls = expf(*logit_scale);
+    const float* s = sim + size_t(b) * P * R;
+    if (r < R) {
+        float mx = -INFINITY, sum = 0.f, mean = 0.f;
+        for (int p = 0; p < P; ++p) { mx = fmaxf(mx, ls * s[p * R + r]); mean += s[p * R + r]; }
+        for (int p = 0; p < P; ++p) sum += expf(ls * s[p * R + r] - mx);
+        for (int p = 0; p < P; ++p) out_imp[(size_t(b) * P + p) * R + r] = expf(ls * s[p * R + r] - mx) / sum;
+        s_mean[r] = ls * (mean / float(P));
+    }
+    __syncthreads();
+    if (r < R) {
+        float mx = -INFINITY, sum = 0.f;
+        for (int k = 0; k < R; ++k) mx = fmaxf(mx, s_mean[k]);
+        for (int k = 0; k < R; ++k) sum += expf(s_mean[k] - mx);
+        out_probs[size_t(b) * R + r] = expf(s_mean[r] - mx) / sum;
     }
 }
 

@@ -272,18 +272,35 @@ def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None 
 
 
 def attention_scores(X, Q, ml, scale: float | None = None):
-    """A [P,N] = softmax_N(scale * cos(Q, X)) for ONE bag, from the (max, sum) saved by the forward
-    (the ``ret_with_attn=True`` output of VLFAN.forward, model/deepmil.py:206-213)."""
+    """A [P,N] for ONE bag.  With ``ml`` (the (max, sum) saved by the forward): softmax over the N patches of
+    scale * cos(Q, X), the ``ret_with_attn=True`` output of VLFAN.forward (model/deepmil.py:206-213).  With
+    ``ml=None``: softmax over the P prototypes per patch (utils/model_inference.py:104-113, axis_softmax='L')."""
     L = _lib.lib()
     _check_cuda(X, "X", None)
     _check_cuda(Q, "Q")
-    _check_cuda(ml, "ml")
+    if ml is not None:
+        _check_cuda(ml, "ml")
     N, P = X.shape[0], Q.shape[0]
     A = torch.empty(P, N, dtype=torch.float32, device=X.device)
     rc = L.vlsa_attn_fwd(X.data_ptr(), _x_dtype_code(X), N, Q.data_ptr(), P,
-                         coattn_scale() if scale is None else float(scale), ml.data_ptr(), A.data_ptr(), _stream())
+                         coattn_scale() if scale is None else float(scale), _ptr(ml), A.data_ptr(), _stream())
     _lib.check(rc, "vlsa_attn_fwd")
     return A
+
+
+def decoupled_similarity(O, W, bias, T, f, logit_scale):
+    """Interpretation path (utils/model_inference.py:115-131) from the pooled per-prototype features O [B,P,512]
+    of the forward: returns (sim [B,P,R], decoupled_imp [B,P,R], probs_2 [B,R]).  No pass over X."""
+    for name, t in (("O", O), ("W", W), ("bias", bias), ("T", T), ("f", f), ("logit_scale", logit_scale)):
+        _check_cuda(t, name)
+    B, P, R = O.shape[0], O.shape[1], T.shape[0]
+    f32 = dict(dtype=torch.float32, device=O.device)
+    sim, imp, probs = torch.empty(B, P, R, **f32), torch.empty(B, P, R, **f32), torch.empty(B, R, **f32)
+    rc = _lib.lib().vlsa_interp_fwd(O.data_ptr(), W.data_ptr(), bias.data_ptr(), T.data_ptr(), R, f.data_ptr(),
+                                    logit_scale.data_ptr(), B, P, sim.data_ptr(), imp.data_ptr(), probs.data_ptr(),
+                                    _stream())
+    _lib.check(rc, "vlsa_interp_fwd")
+    return sim, imp, probs
 
 
 class _SurvLossFn(torch.autograd.Function):
