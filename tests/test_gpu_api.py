@@ -244,3 +244,35 @@ def test_interpretation_path_matches_reference_formula(P, R, N, kind, axis, dev)
     if shap64 is not None:
         np.testing.assert_allclose(shap.numpy(), shap64.numpy(), atol=2e-4)
     assert shap.shape == (P,)
+
+
+def test_flat_store_to_async_loader_to_forward(tmp_path, dev):
+    """f2 of SURVEY §8: flat memory-mapped store -> pinned packed steps -> AsyncBagLoader (copy stream, ring) ->
+    forward_packed gives what the reference-style per-bag loop gives on the same rows."""
+    import numpy as np
+    from vlsa_b200 import synth
+    from vlsa_b200.dataset import AsyncBagLoader, PatchFeatureStore, WSIPatchSurvStore, build_store
+    P = R = 12
+    pr = synth.make_params(P, R, 5)
+    net = build_net(pr, P, R, dev)
+    slides = {f"s{i}": synth.make_bag("g1", n, 300 + i) for i, n in enumerate([700, 33, 1500, 260, 1, 999, 4100])}
+    build_store(str(tmp_path / "st"), slides.items())
+    st = PatchFeatureStore(str(tmp_path / "st"))
+    pid2sids = {"a": ["s0", "s1"], "b": ["s2"], "c": ["s3", "s4", "s5"], "d": ["s6"], "e": ["s1"]}
+    pid2label = {k: (float(i % R), float(i % 2)) for i, k in enumerate(pid2sids)}
+    ds = WSIPatchSurvStore(st, list(pid2sids), pid2sids, pid2label)
+    got, labs = [], []
+    loader = AsyncBagLoader(ds.steps(batch_size=2), dev, depth=2)
+    with torch.no_grad():
+        for batch in loader:
+            batch.wait()
+            logits, g, Tn, inc = net.forward_packed(batch.X, batch.plan)
+            loader.release(batch)
+            got.append(inc.cpu()); labs.append(batch.labels.cpu())
+    got = torch.cat(got, 0).numpy()
+    assert torch.cat(labs, 0).tolist() == [list(pid2label[k]) for k in pid2sids]
+    with torch.no_grad():
+        for i, pid in enumerate(pid2sids):
+            X = torch.cat([slides[s] for s in pid2sids[pid]], 0).unsqueeze(0).to(dev)
+            ref = torch.softmax(net(X)[0], -1).cpu().numpy()
+            assert np.abs(got[i] - ref[0]).max() <= 2e-6

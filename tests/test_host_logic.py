@@ -173,3 +173,44 @@ def test_prototype_shap_vectorised_matches_reference_loops():
         full = torch.softmax(56.3 * sim.mean(0), 0)
         total = float(((R - torch.arange(R)) * full).sum()) - 1.0
         assert abs(float(got.sum()) - total) < 1e-3
+
+
+def test_flat_store_matches_per_slide_files(tmp_path):
+    """dataset/PatchWSI.py:197-215 vs the flat store: a patient = its slides' rows in sid order, bit-exact in fp32;
+    missing slides are skipped; bf16 stores the rounded values; steps() packs whole optimizer steps."""
+    import numpy as np
+    import torch
+    from vlsa_b200.dataset import PatchFeatureStore, WSIPatchSurvStore, build_store_from_files
+    g = torch.Generator().manual_seed(11)
+    pdir = tmp_path / "pt"; pdir.mkdir()
+    sizes = {"s0": 5, "s1": 17, "s2": 1, "s3": 300, "s4": 64}
+    feats = {}
+    for sid, n in sizes.items():
+        feats[sid] = torch.randn(n, 512, generator=g)
+        if sid == "s3":
+            np.save(pdir / (sid + ".npy"), feats[sid].numpy())
+        else:
+            torch.save(feats[sid].to(torch.float16 if sid == "s4" else torch.float32), pdir / (sid + ".pt"))
+    feats["s4"] = feats["s4"].to(torch.float16).float()
+    build_store_from_files(str(tmp_path / "st32"), str(pdir), ["s0", "s1", "s2", "s4", "missing"], "pt")
+    st = PatchFeatureStore(str(tmp_path / "st32"))
+    assert "missing" not in st and st.n_rows(["s0", "s1", "nope"]) == 22
+    pid2sids = {"pA": ["s1", "s0"], "pB": ["s2"], "pC": ["s4", "gone", "s0"]}
+    pid2label = {"pA": (3.0, 1.0), "pB": (0.0, 0.0), "pC": (7.0, 1.0)}
+    ds = WSIPatchSurvStore(st, ["pA", "pB", "pC"], pid2sids, pid2label)
+    for i, pid in enumerate(ds.pids):
+        idx, (x, extra), label = ds[i]
+        ref = torch.cat([feats[s] for s in pid2sids[pid] if s in feats and s != "s3"], 0).to(torch.float)
+        assert int(idx) == i and extra.tolist() == [0.0] and label.tolist() == list(pid2label[pid])
+        assert x.dtype == torch.float32 and torch.equal(x, ref)
+    steps = list(ds.steps(batch_size=2, pin=False, threads=2))
+    assert [s[1] for s in steps] == [[22, 1], [69]]
+    assert torch.equal(steps[0][0], torch.cat([feats["s1"], feats["s0"], feats["s2"]], 0))
+    assert steps[1][2].tolist() == [[7.0, 1.0]] and steps[1][3].tolist() == [2]
+    # bf16 store: the rounded values, half the bytes
+    from vlsa_b200.dataset import build_store
+    build_store(str(tmp_path / "st16"), [(s, feats[s]) for s in ("s0", "s3")], dtype="bfloat16")
+    st16 = PatchFeatureStore(str(tmp_path / "st16"))
+    x16 = st16.read(["s3", "s0"])
+    assert x16.dtype == torch.bfloat16 and torch.equal(x16, torch.cat([feats["s3"], feats["s0"]], 0).to(torch.bfloat16))
+    assert (tmp_path / "st16" / "features.bin").stat().st_size == 305 * 512 * 2
