@@ -56,7 +56,19 @@ __global__ void __launch_bounds__(128) k_bulk(const char* __restrict__ x, size_t
 // 32-row tile with 16 LDG.128 per lane, consumes them, __syncthreads-free; MODE 0 = no prefetch,
 // 1 = one 64 KB cp.async.bulk.prefetch.L2 per tile issued PF tiles ahead by a 9th warp (paced by a smem counter),
 // 2 = same with per-line prefetch.global.L2; FENCE = 1 adds the proxy fence after each tile (as the real kernel)
-template <int MODE, int FENCE>
+template <int KIND>
+__device__ __forceinline__ float4 ld_kind(const float* p, uint64_t pol) {
+    float4 v;
+    if (KIND == 0) return ldg_stream_f4(p, pol);
+    if (KIND == 1) asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (KIND == 2) asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (KIND == 3) asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (KIND == 4) asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (KIND == 5) asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    if (KIND == 6) asm volatile("ld.global.relaxed.gpu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+template <int MODE, int FENCE, int KIND = 0>
 __global__ void __launch_bounds__(288) k_regpath(const float* __restrict__ x, size_t bytes, int PF, float* out) {
     __shared__ volatile uint32_t prog;
     __shared__ float sink[256];
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(288) k_regpath(const float* __restrict__ x, si
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) buf[4 * j + i] = ldg_stream_f4(src + j * 512 + 128 * i, pol);
+            for (int i = 0; i < 4; ++i) buf[4 * j + i] = ld_kind<KIND>(src + j * 512 + 128 * i, pol);
     };
     issue(0);
     for (int t = 0; t < ntiles; ++t) {
@@ -154,6 +166,29 @@ int main() {
         report(nm, time_ms([&](int i) { k_regpath<2, 1><<<148, 288>>>((const float*)buf[i & 1], bytes, pf, out); }, 10));
     }
     report("regpath nofence nopf", time_ms([&](int i) { k_regpath<0, 0><<<148, 288>>>((const float*)buf[i & 1], bytes, 0, out); }, 10));
+    // the same with a large dynamic shared-memory allocation: the L1 carve-out shrinks to ~20 KB
+    {
+        auto k = k_regpath<0, 0>;
+        for (int kb : {64, 128, 160, 200}) {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
+            char nm[64]; snprintf(nm, 64, "regpath nopf, %d KB dyn smem", kb);
+            report(nm, time_ms([&](int i) { k<<<148, 288, kb * 1024>>>((const float*)buf[i & 1], bytes, 0, out); }, 10));
+        }
+    }
+    {
+        const int kb = 205;
+        auto run = [&](auto k, const char* nm) {
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024);
+            report(nm, time_ms([&](int i) { k<<<148, 288, kb * 1024>>>((const float*)buf[i & 1], bytes, 0, out); }, 10));
+        };
+        run(k_regpath<0, 0, 0>, "205KB smem: nc.no_allocate.evict_first");
+        run(k_regpath<0, 0, 1>, "205KB smem: ld.cg");
+        run(k_regpath<0, 0, 2>, "205KB smem: ld.cv");
+        run(k_regpath<0, 0, 3>, "205KB smem: ld.ca");
+        run(k_regpath<0, 0, 4>, "205KB smem: ld.nc");
+        run(k_regpath<0, 0, 5>, "205KB smem: ld.cs");
+        run(k_regpath<0, 0, 6>, "205KB smem: ld.relaxed.gpu");
+    }
     report("regpath fence   nopf", time_ms([&](int i) { k_regpath<0, 1><<<148, 288>>>((const float*)buf[i & 1], bytes, 0, out); }, 10));
     printf("cuda status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;

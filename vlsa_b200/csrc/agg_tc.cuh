@@ -69,6 +69,13 @@ struct TcCfg {
     //   16 producers: launch 72 -> weights 96, issuers 48, producers 64    (8 x 96 + 4 x 48 + 16 x 64 <= 28 x 72)
     static constexpr int REG_PROD = NPROD == 8 ? 120 : 64;
     static constexpr int REG_SOFT = 96;
+    // rows of the next tile whose loads are issued while the current tile is still being converted; the others are
+    // issued after the proxy fence (which waits for every load in flight): tile period = load latency +
+    // max(EARLY, RPW - EARLY) row conversions
+#ifndef VLSA_TC_EARLY
+#define VLSA_TC_EARLY (VLSA_TC_NPROD == 8 ? 3 : 1)
+#endif
+    static constexpr int EARLY = VLSA_TC_EARLY;
     static constexpr int W_G1 = NSOFT;            // GEMM1 issuer warp
     static constexpr int W_G2 = NSOFT + 1;        // GEMM2 issuer warp
     static constexpr int W_PF = NSOFT + 2;        // L2 prefetch warp (warp NSOFT + 3 idles: warps are allocated in fours)
@@ -363,12 +370,15 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 #pragma unroll
             for (int j = 0; j < C::RPW; ++j) {
                 process_row(j);
-                if (j < C::RPW - 1 && nvalid) issue_row(j, nptr, nrows);
+                if (j < C::EARLY && nvalid) issue_row(j, nptr, nrows);
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(full + b);
-            if (nvalid) issue_row(C::RPW - 1, nptr, nrows);
+            if (nvalid) {
+#pragma unroll
+                for (int j = C::EARLY; j < C::RPW; ++j) issue_row(j, nptr, nrows);
+            }
             ++tt;
             if (pw == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(s_prog) = tt;
             valid = nvalid; tptr = nptr; rows_left = nrows;
