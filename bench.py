@@ -54,7 +54,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None

@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     constexpr int NW = C::NW, CPT = C::CPT;
     static_assert(TN <= 32 && (CPT == 2 || CPT == 4), "phase S maps rows to lanes; phase B loads 8 or 16 bytes");
     constexpr bool BF16 = sizeof(XT) == 2;
+#ifndef VLSA_SIMT_UNROLL_B
+#define VLSA_SIMT_UNROLL_B 4
+#endif
+    constexpr int UNROLL_B = VLSA_SIMT_UNROLL_B;   // rows of phase B in flight per thread
 #ifdef VLSA_SIMT_NOPACK
     constexpr bool PACKED_B = false;
 #else
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     for (int k = 0; k < CPT; ++k) acc2[p][k] *= a;
                 }
             }
-#pragma unroll 4
+#pragma unroll UNROLL_B
             for (int r = 0; r < nvalid; ++r) {
                 float xv[CPT];
                 if (!BF16) {
