@@ -302,7 +302,7 @@ def main():
         n_global = nb * world
 
         def train_step(i):
-            handler.optimizer.zero_grad(set_to_none=True)
+            handler.bucket.zero()
             logits, _, _, _ = handler.net.forward_packed(batches[i % n_batches], plan)
             loss = handler.calc_objective_loss(logits, label, norm=n_global)
             loss.backward()

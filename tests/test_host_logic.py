@@ -214,3 +214,41 @@ def test_flat_store_matches_per_slide_files(tmp_path):
     x16 = st16.read(["s3", "s0"])
     assert x16.dtype == torch.bfloat16 and torch.equal(x16, torch.cat([feats["s3"], feats["s0"]], 0).to(torch.bfloat16))
     assert (tmp_path / "st16" / "features.bin").stat().st_size == 305 * 512 * 2
+
+
+def test_flat_bucket_attached_gradients_alias_the_bucket():
+    """FlatBucket.attach(): .grad tensors are views of the all-reduce buffer, so autograd accumulates into it, zero()
+    is one memset and pack()/unpack() copy nothing — with the same numbers as the copying path."""
+    import torch
+    from vlsa_b200.runner.dist import FlatBucket
+    torch.manual_seed(0)
+    def make():
+        return [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5)),
+                torch.nn.Parameter(torch.randn(2, 2), requires_grad=False)]
+    def loss(ps, k):
+        return (ps[0] * k).sum() ** 2 + (ps[1] ** 3).sum() * k + ps[2].sum()
+    a, b = make(), make()
+    for pa, pb in zip(a, b):
+        pb.data.copy_(pa.data)
+    plain, att = FlatBucket(a, extra=1), FlatBucket(b, extra=1)
+    att.attach()
+    assert all(p.grad.data_ptr() == seg.data_ptr() for p, seg in att._views())
+    for step in (1.0, 2.5):
+        for p in a:
+            p.grad = None
+        att.zero()
+        assert float(att.flat.abs().sum()) == 0.0
+        loss(a, step).backward(); loss(b, step).backward()
+        loss(b, step).backward()                       # accumulation into the attached views
+        plain.pack(torch.tensor([step])); att.pack(torch.tensor([step]))
+        assert torch.allclose(att.flat[:-1], 2 * plain.flat[:-1]) and float(att.tail[0]) == step
+        plain.all_reduce(); att.all_reduce(); plain.unpack(); att.unpack()
+        assert all(p.grad.data_ptr() == seg.data_ptr() for p, seg in att._views())
+        assert torch.allclose(b[0].grad, 2 * a[0].grad) and torch.allclose(b[1].grad, 2 * a[1].grad)
+    # a caller that drops the gradients (zero_grad(set_to_none=True)) falls back to the copying path
+    for p in b:
+        p.grad = None
+    att.zero()
+    loss(b, 1.0).backward()
+    att.pack(None)
+    assert torch.allclose(att.flat[:12], b[0].grad.reshape(-1))

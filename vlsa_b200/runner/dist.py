@@ -46,7 +46,11 @@ class FlatBucket:
 
     `pack()` copies the .grad tensors in (zeros where a parameter got no gradient), `all_reduce()` sums
     it over the ranks in ONE collective, `unpack()` writes the reduced gradients back.  For the BLCA model
-    this is 284 161 floats = 1.14 MB: latency-bound, so one bucket and one launch."""
+    this is 284 161 floats = 1.14 MB: latency-bound, so one bucket and one launch.
+
+    With `attach()` the parameters' .grad tensors ARE views of the bucket: autograd accumulates straight into
+    it, `zero()` clears all gradients with one memset, and pack / unpack copy nothing (a step on small bags is
+    launch-bound: this removes a dozen tiny kernels per step)."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 1):
         self.params = [p for p in params if p.requires_grad]
@@ -60,14 +64,34 @@ class FlatBucket:
     def tail(self) -> torch.Tensor:
         return self.flat[len(self.flat) - self.extra:]
 
-    def pack(self, extra_values: torch.Tensor | None = None) -> None:
+    def _views(self):
         at = 0
         for p, n in zip(self.params, self.sizes):
-            if p.grad is None:
-                self.flat[at:at + n].zero_()
-            else:
-                self.flat[at:at + n].copy_(p.grad.reshape(-1))
+            yield p, self.flat[at:at + n]
             at += n
+
+    def attach(self) -> None:
+        """Make every parameter's .grad a view of the bucket (keeps the current gradient values, if any)."""
+        for p, seg in self._views():
+            g = seg.view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+            p.grad = g
+
+    def zero(self) -> None:
+        """Zero all gradients.  Attached: one memset of the bucket; otherwise `grad = None` like zero_grad()."""
+        if all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views()):
+            self.flat.zero_()
+        else:
+            for p in self.params:
+                p.grad = None
+
+    def pack(self, extra_values: torch.Tensor | None = None) -> None:
+        for p, seg in self._views():
+            if p.grad is None:
+                seg.zero_()
+            elif p.grad.data_ptr() != seg.data_ptr():             # attached gradients already live here
+                seg.copy_(p.grad.reshape(-1))
         if self.extra:
             if extra_values is None:
                 self.tail.zero_()
@@ -79,14 +103,12 @@ class FlatBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
     def unpack(self) -> None:
-        at = 0
-        for p, n in zip(self.params, self.sizes):
-            g = self.flat[at:at + n].view_as(p)
+        for p, seg in self._views():
+            g = seg.view_as(p)
             if p.grad is None:
                 p.grad = g.clone()
-            else:
+            elif p.grad.data_ptr() != g.data_ptr():
                 p.grad.copy_(g)
-            at += n
 
 
 def all_reduce_rows(local_rows: torch.Tensor, local_idx: Sequence[int], n_total: int) -> torch.Tensor:

@@ -89,10 +89,11 @@ class VLSAHandler:
         self.output_converter = create_output_converter(cfg.get("net_output_converter", "softmax"))
         assert cfg.get("opt_name", "adam") == "adam", "only Adam is wired (cfg_vlsa_conch.yaml:111)"
         self.optimizer = torch.optim.Adam(param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5))),
-                                          lr=float(cfg.get("opt_lr", 2e-4)))
+                                          lr=float(cfg.get("opt_lr", 2e-4)), fused=self.device.type == "cuda")
         self.rank, self.world_size = vdist.world()
         self.balance_shards = balance_shards
         self.bucket = vdist.FlatBucket(self.net.parameters(), extra=1)
+        self.bucket.attach()                      # gradients live in the all-reduce bucket: no pack / unpack copies
 
     # ------------------------------------------------------------------------------------------------
     def calc_objective_loss(self, raw_pred, label, norm: int | None = None):
@@ -118,7 +119,7 @@ class VLSAHandler:
         n_sample = len(xs)
         sizes = [int(x.shape[-2]) for x in xs]
         mine = vdist.shard_indices(sizes, self.rank, self.world_size, self.balance_shards)
-        self.optimizer.zero_grad(set_to_none=True)
+        self.bucket.zero()
         bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
         if mine:
             X, plan = self._pack_local(xs, mine)
