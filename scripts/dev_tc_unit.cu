@@ -154,6 +154,91 @@ static float from16(uint16_t u, bool bf) {
     __half h; memcpy(&h, &u, 2); return __half2float(h);
 }
 
+// ---------------------------------------------------------------------------------- M = 64 layout + per-MMA cost
+// ts64 : (a) which TMEM lanes a M=64 .ts MMA reads as A rows and writes as D rows: every lane l holds A[l][k=0] = l+1,
+//            B[n][0] = 1, D pre-set to -7 -> D[lane][0] shows the source lane, -7 = not written;
+//        (b) cycles per MMA (256 back-to-back, accumulate) for M=128/64 x N=64/32, A in TMEM, and for M=64 N=32 with A
+//            in shared memory (K-major, SW128)
+__global__ void __launch_bounds__(128) ts64_test(float* Dout /*[128][32]*/, long long* cyc /*[12]*/) {
+    extern __shared__ unsigned char raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    unsigned char* sB = raw + (base - smem_u32(raw));          // B: 128 rows x 128 B (K = 64 fp16), also used as smem A
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base, 256);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    const uint32_t tm = tmem_base, lane_addr = uint32_t(32 * warp) << 16;
+    {   // A: lane tid, columns 0..31 (64 fp16): element k=0 = tid+1, rest 0.   D (cols 64..127): -7
+        uint32_t v[32];
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+        v[0] = uint32_t(__half_as_ushort(__float2half(float(tid + 1))));
+        tmem_st32(tm + lane_addr, v);
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(-7.f);
+        tmem_st32(tm + 64 + lane_addr, v);
+        tmem_st32(tm + 96 + lane_addr, v);
+        tmem_wait_st();
+    }
+    for (int i = tid; i < 128 * 64; i += 128) {
+        const int r = i / 64, k = i % 64;
+        *reinterpret_cast<__half*>(sB + sw128_offset(r, k >> 3, (k & 7) * 2)) = __float2half(k == 0 ? 1.f : 0.f);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    uint32_t phase = 0;
+    if (tid == 0) {
+        constexpr uint32_t idesc = umma_idesc(UMMA_F16, UMMA_F16, 64, 32, false, false);
+        tc_mma_ts(tm + 64, tm, umma_desc_sw128(smem_u32(sB), 16, 1024), idesc, 0);
+#ifdef TS64_LANE16
+        // second M=64 MMA on lanes 16..31 of every quadrant (A and D base lane 16), negated B row -> values * 1 too
+        tc_mma_ts(tm + 64 + (16u << 16), tm + (16u << 16), umma_desc_sw128(smem_u32(sB), 16, 1024), idesc, 0);
+#endif
+        tc_commit(&bar);
+    }
+    mbar_wait_wd(&bar, phase); phase ^= 1;
+    tc_fence_after();
+    for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[8];
+        tmem_ld8(tm + 64 + 8 * cb + lane_addr, r);
+        tmem_wait_ld();
+        for (int c = 0; c < 8; ++c) Dout[tid * 32 + 8 * cb + c] = __uint_as_float(r[c]);
+    }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    // ---- timing
+    auto timed = [&](int which, auto issue) {
+        long long t0 = 0;
+        if (tid == 0) {
+            t0 = clock64();
+            for (int i = 0; i < 256; ++i) issue(i);
+            tc_commit(&bar);
+        }
+        mbar_wait_wd(&bar, phase); phase ^= 1;
+        tc_fence_after();
+        if (tid == 0) cyc[which] = clock64() - t0;
+        __syncthreads();
+    };
+    const uint64_t bdesc = umma_desc_sw128(smem_u32(sB), 16, 1024);
+    timed(0, [&](int i) { tc_mma_ts(tm + 64, tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 64, false, false), 1); });
+    timed(1, [&](int i) { tc_mma_ts(tm + 64, tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 64, 64, false, false), 1); });
+    timed(2, [&](int i) { tc_mma_ts(tm + 64, tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 32, false, false), 1); });
+    timed(3, [&](int i) { tc_mma_ts(tm + 64, tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 64, 32, false, false), 1); });
+    timed(4, [&](int i) { tc_mma_ss(tm + 64, bdesc, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 64, 32, false, false), 1); });
+    timed(5, [&](int i) { tc_mma_ss(tm + 64, bdesc, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 32, false, false), 1); });
+    timed(6, [&](int i) { tc_mma_ss(tm + 64, bdesc, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 16, false, false), 1); });
+    timed(7, [&](int i) { tc_mma_ts(tm + 64, tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 128, false, false), 1); });
+    // independent accumulators
+    timed(8, [&](int i) { tc_mma_ts(tm + 64 + 64 * (i & 1), tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 64, false, false), 1); });
+    timed(9, [&](int i) { tc_mma_ts(tm + 64 + 48 * (i & 3), tm + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 32, false, false), 1); });
+    timed(10, [&](int i) { tc_mma_ss(tm + 64 + 24 * (i & 7), bdesc, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 128, 16, false, false), 1); });
+#ifdef TS64_LANE16
+    timed(11, [&](int i) { const uint32_t lb = (i & 1) ? (16u << 16) : 0u;
+                           tc_mma_ts(tm + 64 + lb, tm + lb + (i & 3) * 8, bdesc, umma_idesc(UMMA_F16, UMMA_F16, 64, 64, false, false), 1); });
+#endif
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 256);
+}
+
 int main(int argc, char** argv) {
     const char* t = argc > 1 ? argv[1] : "ts";
     srand(7);
@@ -181,6 +266,24 @@ int main(int argc, char** argv) {
         }
         printf("[ts] A in TMEM (lane = row, 2 fp16 per column, low half first): max err %.3e  (D[0][0..1] = %f %f)\n", err, Dh[0], Dh[1]);
         return err < 1e-2 ? 0 : 2;
+    }
+    if (!strcmp(t, "ts64")) {
+        float* dD; long long* dC;
+        cudaMalloc(&dD, 128 * 32 * 4); cudaMalloc(&dC, 12 * 8); cudaMemset(dC, 0, 96);
+        ts64_test<<<1, 128, 16384 + 1024>>>(dD, dC);
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("[ts64] kernel: %s\n", cudaGetErrorString(e));
+        if (e != cudaSuccess) return 1;
+        std::vector<float> Dh(128 * 32); long long C[12];
+        cudaMemcpy(Dh.data(), dD, Dh.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(C, dC, 96, cudaMemcpyDeviceToHost);
+        printf("[ts64] D lane -> value (= source A lane + 1, -7 = untouched), columns 0 and 31:\n");
+        for (int l = 0; l < 128; ++l) printf("%s%3d:%4.0f/%4.0f", l % 8 ? "  " : "\n   ", l, Dh[l * 32], Dh[l * 32 + 31]);
+        const char* names[12] = {"ts M128 N64", "ts M64 N64", "ts M128 N32", "ts M64 N32", "ss M64 N32 (A smem K-major)",
+                                 "ss M128 N32", "ss M128 N16", "ts M128 N128", "ts M128 N64, 2 accumulators", "ts M128 N32, 4 accumulators",
+                                 "ss M128 N16, 8 accumulators", "ts M64 N64, lanes 0 / 16 alternating"};
+        printf("\n[ts64] cycles per MMA (256 back-to-back, K=16):\n");
+        for (int i = 0; i < 12; ++i) printf("   %-40s %.1f\n", names[i], C[i] / 256.0);
+        return 0;
     }
     if (!strcmp(t, "rz")) {
         float* dD; cudaMalloc(&dD, 2 * 128 * 32 * 4);
