@@ -280,3 +280,35 @@ def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dev):
     assert np.abs(a["inc"] - b_["inc"]).max() <= IF_TOL
     np.testing.assert_allclose(a["g"], b_["g"], atol=2e-6)
     assert np.abs(a["d_res"] - b_["d_res"]).max() <= max(GRAD_RTOL * np.abs(a["d_res"]).max(), 1e-7)
+
+
+def test_backward_accuracy_regression_case(dev):
+    """The case that exposed a 700x loss of gradient accuracy when the lo-plane products shared an accumulator with
+    the hi-plane ones (tensor-core backward): gradients must stay at fp32 grade, not merely inside GRAD_RTOL."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import ops, synth
+    P = R = 12
+    sizes = [2798, 1000, 37]
+    bags = [synth.make_bag("g1", n, 100 + i) for i, n in enumerate(sizes)]
+    pr = synth.make_params(P, R, 7)
+    t, e = synth.make_labels(len(sizes), R, 9)
+    ref = O.forward_with_grads(bags, pr["prompt_features"], pr["residual_features"], pr["W"], pr["b"],
+                               pr["text_features"], pr["logit_scale"], t, e, dtype=torch.float64)
+    X = torch.cat(bags, 0).to(dev)
+    plan = ops.make_plan(sizes, dev)
+    try:
+        for variant in ("tc", "simt"):
+            ops.set_agg_variant(variant)
+            leaf = lambda z: z.detach().clone().to(dev).requires_grad_(True)
+            res, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))
+            Q = pr["res_ratio"] * res + pr["prompt_features"].to(dev)
+            logits, g, Tn, inc, ml = ops.aggregate(X, plan, Q, W, b, T, ls)
+            total, *_ = ops.surv_loss(logits, t.to(dev), e.to(dev), ls)
+            total.backward()
+            torch.cuda.synchronize()
+            gref = ref["d_residual"].numpy()
+            err = np.abs(res.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
+            assert err <= 2e-5, f"{variant}: d_residual relative error {err:.2e}"
+            assert abs(total.item() - ref["loss"].item()) <= 2e-6 * max(1.0, abs(ref["loss"].item())), variant
+    finally:
+        ops.set_agg_variant(None)

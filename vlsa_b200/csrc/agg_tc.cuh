@@ -16,9 +16,8 @@
 //     restricted to the feature range 128 (j >> 3) .. +127 (zeros elsewhere): every accumulator only sees
 //     8 non-zero steps, and the 16 partial sums of a score (2 parts x 4 ranges x 2 planes) are added in fp32
 //     registers.  TMEM quadrant q therefore owns prototypes 4 q .. 4 q + 3 completely;
-//   * the per-row weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); the lo plane of X
-//     only meets the first term, in the same accumulator as (hi plane . first term), the second term has its own
-//     columns; tcgen05.mma needs A and B in the same
+//   * the per-row weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); products with
+//     the hi and the lo plane of X accumulate in separate TMEM columns; tcgen05.mma needs A and B in the same
 //     16-bit format (fp16 x bf16 traps), hence fp16 weights with the lazy-rescale range control below.
 //
 // Warp roles (20 warps, 1 persistent CTA / SM, static round-robin over chunks):
@@ -57,7 +56,7 @@ struct TcCfg {
     // floats: rowinfo[NBUF][TR][4] | alpha[16] | cand[2][16] | lsum[16]
     static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 32 + 16;
     static constexpr int OFF_BAR = OFF_F + NFLOAT * 4;
-    static constexpr int NBAR = 2 * NBUF + 10;
+    static constexpr int NBAR = 2 * NBUF + 8;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16 + 1024;
     static constexpr int NSOFT = 8;               // weight ("softmax") warps
 #ifndef VLSA_TC_NPROD
@@ -90,12 +89,11 @@ struct TcCfg {
     // streams at 7.3 TB/s, an L2 prefetch ahead of it only costs bandwidth (6.1 TB/s at 2 tiles, 4.8 at 8).
     static constexpr int PF = VLSA_TC_PF;
     static constexpr int QPITCH = D + 1;          // prologue staging of Qn (aliases the ring)
-    // TMEM columns: Qn operand | O^T accumulators: 4 blocks of 128 d x ((hi + lo).t0 16 | hi.t1 16) | 2 x scores
+    // TMEM columns: Qn operand | O^T accumulators: 4 blocks of 128 d x (hi.t0 16 | hi.t1 16 | lo.t0 16) | scores
     static constexpr int TM_Q = 0;
-    static constexpr int D2W = 2 * NP;            // 32 columns per 128-feature block: (hi + lo planes) . t0 | hi . t1
+    static constexpr int D2W = 3 * NP;            // 48 columns per 128-feature block
     static constexpr int TM_D2 = 256;
-    static constexpr int TM_D1 = TM_D2 + 4 * D2W;   // 384: TWO score buffers of 64 columns
-                                                   //      [hi plane rows 0..31 | lo plane rows 0..31], tile tt uses tt & 1
+    static constexpr int TM_D1 = TM_D2 + 4 * D2W;   // 448: scores [hi plane rows 0..31 | lo plane rows 0..31]
     static constexpr int TMEM_COLS = 512;
     // forward, online softmax with lazy rescaling: on (re)set the reference is the running maximum + HEADROOM;
     // the TMEM accumulators are rescaled only when a tile maximum exceeds the reference by more than MARGIN, so
@@ -150,12 +148,12 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint64_t* full = bars;                       // [NBUF] producers (8 warps)      -> GEMM1, weight warps (row info)
     uint64_t* empty = bars + C::NBUF;            // [NBUF] GEMM2 commit             -> producers
-    uint64_t* s_ready = bars + 2 * C::NBUF;      // [2]    GEMM1 commit             -> weight warps
-    uint64_t* s_free = s_ready + 2;              // [2]    weight warps (8)         -> GEMM1
-    uint64_t* w_ready = s_ready + 4;             // [2]    weight warps (8)         -> GEMM2
-    uint64_t* w_free = s_ready + 6;              // [2]    GEMM2 commit             -> weight warps
-    uint64_t* d2_done = s_ready + 8;             //        last GEMM2 of a chunk    -> weight warps (drain)
-    uint64_t* d2_free = s_ready + 9;             //        weight warps (8)         -> GEMM2 of the next chunk
+    uint64_t* s_ready = bars + 2 * C::NBUF;      //        GEMM1 commit             -> weight warps
+    uint64_t* s_free = s_ready + 1;              //        weight warps (8)         -> GEMM1
+    uint64_t* w_ready = s_ready + 2;             // [2]    weight warps (8)         -> GEMM2
+    uint64_t* w_free = s_ready + 4;              // [2]    GEMM2 commit             -> weight warps
+    uint64_t* d2_done = s_ready + 6;             //        last GEMM2 of a chunk    -> weight warps (drain)
+    uint64_t* d2_free = s_ready + 7;             //        weight warps (8)         -> GEMM2 of the next chunk
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::NBAR);
     uint32_t* s_prog = tmem_ptr + 1;             // tiles filled so far (paces the L2 prefetcher)
 
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 
     if (tid == 0) {
         for (int s = 0; s < C::NBUF; ++s) { mbar_init(full + s, C::NPROD); mbar_init(empty + s, 1); }
-        for (int k = 0; k < 2; ++k) { mbar_init(s_ready + k, 1); mbar_init(s_free + k, C::NSOFT); }
+        mbar_init(s_ready, 1); mbar_init(s_free, C::NSOFT);
         for (int s = 0; s < 2; ++s) { mbar_init(w_ready + s, C::NSOFT); mbar_init(w_free + s, 1); }
         mbar_init(d2_done, 1); mbar_init(d2_free, C::NSOFT);
         *s_prog = 0u;
@@ -426,7 +424,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         if (elect_one()) {
             constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * TR, false, false);
             const uint64_t desc0 = umma_desc_sw128(smem_u32(ring), 16, 1024);
-            const uint32_t tq0 = tmem + C::TM_Q;
+            const uint32_t d1 = tmem + C::TM_D1, tq0 = tmem + C::TM_Q;
             uint32_t tt = 0;
             for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
                 int bag; long long r0, r1;
@@ -434,9 +432,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                 const int ntiles = int((r1 - r0 + TR - 1) / TR);
                 for (int t = 0; t < ntiles; ++t, ++tt) {
                     const uint32_t b = tt % C::NBUF, u = tt / C::NBUF;
-                    // two score buffers: GEMM1 of tile tt only waits for the weight warps to have read tile tt - 2
-                    const uint32_t k1 = tt & 1u, d1 = tmem + C::TM_D1 + 64 * k1;
-                    mbar_wait_wd(s_free + k1, ((tt >> 1) & 1u) ^ 1u);
+                    mbar_wait_wd(s_free, (tt & 1u) ^ 1u);           // scores of the previous tile have been read
                     mbar_wait_wd(full + b, u & 1u);
                     tc_fence_after();
                     const uint64_t tb = umma_desc_advance(desc0, b * C::TILE);
@@ -447,7 +443,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                             tc_mma_ts(d1, tq0 + (s * 4 + ks) * 8, umma_desc_advance(tb, s * C::SLOT + ks * 32), idesc1,
                                       (s | ks) != 0);
                     }
-                    tc_commit(s_ready + k1);
+                    tc_commit(s_ready);
                 }
             }
         }
@@ -471,19 +467,16 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     tc_fence_after();
                     const uint64_t tb = umma_desc_advance(a0, b * C::TILE), wb = umma_desc_advance(w0, i * C::WBUF);
                     const uint32_t acc0 = t != 0;
-                    // 16 MMAs into 4 accumulators (feature blocks); every tcgen05.mma of these shapes occupies the pipe
-                    // for 45-63 cycles whatever M, N and the operand sources are (scripts/dev_tc_unit.cu ts64)
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {                  // 16 tile rows per step
-                        const uint64_t bd = umma_desc_advance(wb, ks * 32);
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t d2 = tmem + C::TM_D2 + g * C::D2W;
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            tc_mma_ss(tmem + C::TM_D2 + g * C::D2W, umma_desc_advance(tb, (2 * g) * C::SLOT + ks * 2048), bd,
-                                      idesc_hi, ks ? 1u : acc0);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            tc_mma_ss(tmem + C::TM_D2 + g * C::D2W,      // lo plane . t0 joins (hi plane . t0)
-                                      umma_desc_advance(tb, (2 * g) * C::SLOT + ks * 2048 + C::PLANE), bd, idesc_lo, 1u);
+                        for (int ks = 0; ks < 2; ++ks) {              // 16 tile rows per step
+                            const uint64_t ah = umma_desc_advance(tb, (2 * g) * C::SLOT + ks * 2048);
+                            const uint64_t bd = umma_desc_advance(wb, ks * 32);
+                            tc_mma_ss(d2, ah, bd, idesc_hi, ks ? 1u : acc0);
+                            tc_mma_ss(d2 + 2 * NP, umma_desc_advance(ah, C::PLANE), bd, idesc_lo, ks ? 1u : acc0);
+                        }
                     }
                     tc_commit(empty + b);
                     tc_commit(w_free + i);
@@ -523,19 +516,18 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             for (int t = 0; t < ntiles; ++t, ++tt) {
                 const uint32_t i = tt & 1u, v = tt >> 1, b = tt % C::NBUF, u = tt / C::NBUF;
                 const int nvalid = min(TR, chunk_nrows - t * TR);
-                const uint32_t k1 = tt & 1u;
-                mbar_wait_wd(s_ready + k1, (tt >> 1) & 1u);
+                mbar_wait_wd(s_ready, tt & 1u);
                 tc_fence_after();
                 float sc2[2];
                 {
                     // 32 partial scores of this lane's (prototype, part, range): rows 16 half .. +15 x (hi | lo plane)
                     uint32_t sa[16], sb[16];
-                    tmem_ld16(tq + C::TM_D1 + 64 * k1 + 16 * half, sa);
-                    tmem_ld16(tq + C::TM_D1 + 64 * k1 + 32 + 16 * half, sb);
+                    tmem_ld16(tq + C::TM_D1 + 16 * half, sa);
+                    tmem_ld16(tq + C::TM_D1 + 32 + 16 * half, sb);
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_free + k1);
+                    if (lane == 0) mbar_arrive(s_free);
                     // add the planes, then a transposed butterfly over the 8 lanes (part, range) of this prototype:
                     // lane bits 4, 3, 2 select which half of the rows a lane keeps -> rows n0, n0 + 1
                     float a8[8], a4[4];
@@ -597,7 +589,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 #pragma unroll
                             for (int j = 0; j < 16; ++j) al[j] = s_alpha[j];
 #pragma unroll 1
-                            for (int k = 4 * half; k < 4 * half + 4; ++k) {
+                            for (int k = 6 * half; k < 6 * half + 6; ++k) {
                                 uint32_t o[16];
                                 tmem_ld16(tq + C::TM_D2 + 16 * k, o);
                                 tmem_wait_ld();
@@ -647,7 +639,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 #pragma unroll
                             for (int j = 0; j < 16; ++j) al[j] = s_alpha[j];
 #pragma unroll 1
-                            for (int k = 4 * half; k < 4 * half + 4; ++k) {
+                            for (int k = 6 * half; k < 6 * half + 6; ++k) {
                                 uint32_t o[16];
                                 tmem_ld16(tq + C::TM_D2 + 16 * k, o);
                                 tmem_wait_ld();
@@ -694,14 +686,15 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             for (int j = 0; j < 16; ++j) mul[j] = BWD ? s_alpha[j] : __uint_as_float(uint32_t(exE) << 23);
 #pragma unroll 1
             for (int g = 2 * half; g < 2 * half + 2; ++g) {
-                uint32_t o0[16], o1[16];
+                uint32_t o0[16], o1[16], o2[16];
                 tmem_ld16(tq + C::TM_D2 + g * C::D2W, o0);
                 tmem_ld16(tq + C::TM_D2 + g * C::D2W + 16, o1);
+                tmem_ld16(tq + C::TM_D2 + g * C::D2W + 32, o2);
                 tmem_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (j < P) po[size_t(j) * D + 128 * g + 32 * q + lane] =
-                        mul[j] * fmaf(__uint_as_float(o1[j]), 0x1p-11f, __uint_as_float(o0[j]));
+                        mul[j] * (fmaf(__uint_as_float(o1[j]), 0x1p-11f, __uint_as_float(o2[j])) + __uint_as_float(o0[j]));
             }
             tc_fence_before();
             __syncwarp();
