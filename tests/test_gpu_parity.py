@@ -283,8 +283,11 @@ def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dev):
 
 
 def test_backward_accuracy_regression_case(dev):
-    """The case that exposed a 700x loss of gradient accuracy when the lo-plane products shared an accumulator with
-    the hi-plane ones (tensor-core backward): gradients must stay at fp32 grade, not merely inside GRAD_RTOL."""
+    """An ill-conditioned step (delta_p = dv . O_p / P cancels heavily, so the gradients amplify any error of the
+    forward's pooled features): the reference's own fp32 arithmetic is 5e-4 away from its fp64 run here.  The
+    tensor-core path (split accumulators, near-exact O) must stay at 2e-5 — this is the case that exposed a 700x loss
+    of gradient accuracy when the lo-plane products shared an accumulator with the hi-plane ones — and the CUDA-core
+    path must stay within a small multiple of what fp32 arithmetic in the reference's order gives."""
     from oracle import vlsa_oracle as O
     from vlsa_b200 import ops, synth
     P = R = 12
@@ -294,6 +297,11 @@ def test_backward_accuracy_regression_case(dev):
     t, e = synth.make_labels(len(sizes), R, 9)
     ref = O.forward_with_grads(bags, pr["prompt_features"], pr["residual_features"], pr["W"], pr["b"],
                                pr["text_features"], pr["logit_scale"], t, e, dtype=torch.float64)
+    ref32 = O.forward_with_grads(bags, pr["prompt_features"], pr["residual_features"], pr["W"], pr["b"],
+                                 pr["text_features"], pr["logit_scale"], t, e, dtype=torch.float32)
+    gref = ref["d_residual"].numpy()
+    err_ref32 = np.abs(ref32["d_residual"].double().numpy() - gref).max() / np.abs(gref).max()
+    assert err_ref32 > 1e-4                      # the case is ill-conditioned for fp32 arithmetic (measured 5e-4)
     X = torch.cat(bags, 0).to(dev)
     plan = ops.make_plan(sizes, dev)
     try:
@@ -306,9 +314,9 @@ def test_backward_accuracy_regression_case(dev):
             total, *_ = ops.surv_loss(logits, t.to(dev), e.to(dev), ls)
             total.backward()
             torch.cuda.synchronize()
-            gref = ref["d_residual"].numpy()
             err = np.abs(res.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
-            assert err <= 2e-5, f"{variant}: d_residual relative error {err:.2e}"
-            assert abs(total.item() - ref["loss"].item()) <= 2e-6 * max(1.0, abs(ref["loss"].item())), variant
+            bound = 2e-5 if variant == "tc" else 3 * err_ref32
+            assert err <= bound, f"{variant}: d_residual relative error {err:.2e} (fp32 reference ops: {err_ref32:.2e})"
+            assert abs(total.item() - ref["loss"].item()) <= (2e-6 if variant == "tc" else 1e-4) * abs(ref["loss"].item()), variant
     finally:
         ops.set_agg_variant(None)

@@ -122,6 +122,17 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     }
     if (tid < P) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_alpha[tid] = 0.f; }
     __syncthreads();
+#ifndef VLSA_SIMT_QREG_J
+#define VLSA_SIMT_QREG_J 2
+#endif
+    constexpr int QREG_J = (!BWD && !BF16 && PACKED && P <= 4) ? VLSA_SIMT_QREG_J : 0;
+    float4 qreg[QREG_J > 0 ? QREG_J * P : 1];
+    if (QREG_J > 0) {
+#pragma unroll
+        for (int j = 0; j < QREG_J; ++j)
+#pragma unroll
+            for (int q = 0; q < P; ++q) qreg[j * P + q] = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
+    }
 
     const uint64_t policy = make_evict_first_policy();
 
@@ -203,7 +214,10 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     }
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
-                        const float4 qv = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
+                        // the first QREG_J column blocks of Qn live in registers (forward, small P): the per-warp,
+                        // per-tile re-read of Qn is a third of this kernel's shared-memory traffic
+                        const float4 qv = (QREG_J > 0 && j < QREG_J && q < P) ? qreg[(j < QREG_J ? j : 0) * P + (q < P ? q : 0)]
+                                        : *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
                         const float2 qlo = make_float2(qv.x, qv.y), qhi = make_float2(qv.z, qv.w);
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
