@@ -125,13 +125,16 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
 #ifndef VLSA_SIMT_QREG_J
 #define VLSA_SIMT_QREG_J 2
 #endif
-    constexpr int QREG_J = (!BWD && !BF16 && PACKED && P <= 4) ? VLSA_SIMT_QREG_J : 0;
-    float4 qreg[QREG_J > 0 ? QREG_J * P : 1];
+#ifndef VLSA_SIMT_QREG_J_BWD
+#define VLSA_SIMT_QREG_J_BWD 2
+#endif
+    constexpr int QREG_J = (!BF16 && PACKED && P <= 4) ? (BWD ? VLSA_SIMT_QREG_J_BWD : VLSA_SIMT_QREG_J) : 0;
+    float4 qreg[QREG_J > 0 ? QREG_J * NQ : 1];
     if (QREG_J > 0) {
 #pragma unroll
         for (int j = 0; j < QREG_J; ++j)
 #pragma unroll
-            for (int q = 0; q < P; ++q) qreg[j * P + q] = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
+            for (int q = 0; q < P; ++q) qreg[j * NQ + q] = *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
     }
 
     const uint64_t policy = make_evict_first_policy();
@@ -181,6 +184,11 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 s_alpha[tid] = __ldg(prm.delta + size_t(bag) * P + tid);
             }
             __syncthreads();
+            if (QREG_J > 0) {                   // the bag's extra query row dv / P joins the register-resident Qn
+#pragma unroll
+                for (int j = 0; j < QREG_J; ++j)
+                    qreg[j * NQ + P] = *reinterpret_cast<const float4*>(qs + P * D + j * 128 + lane * 4);
+            }
         }
         for (long long row = r0; row < r1; row += TN, ++it) {
             const int stage = it % STAGES;
@@ -214,9 +222,9 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     }
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
-                        // the first QREG_J column blocks of Qn live in registers (forward, small P): the per-warp,
+                        // the first QREG_J column blocks of the query rows live in registers (small P): the per-warp,
                         // per-tile re-read of Qn is a third of this kernel's shared-memory traffic
-                        const float4 qv = (QREG_J > 0 && j < QREG_J && q < P) ? qreg[(j < QREG_J ? j : 0) * P + (q < P ? q : 0)]
+                        const float4 qv = (QREG_J > 0 && j < QREG_J) ? qreg[(j < QREG_J ? j : 0) * NQ + q]
                                         : *reinterpret_cast<const float4*>(qs + q * D + j * 128 + lane * 4);
                         const float2 qlo = make_float2(qv.x, qv.y), qhi = make_float2(qv.z, qv.w);
 #pragma unroll
