@@ -129,6 +129,23 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
 #define VLSA_SIMT_QREG_J_BWD 2
 #endif
     constexpr int QREG_J = (!BF16 && PACKED && P <= 4) ? (BWD ? VLSA_SIMT_QREG_J_BWD : VLSA_SIMT_QREG_J) : 0;
+#ifndef VLSA_SIMT_QREG_JB
+#define VLSA_SIMT_QREG_JB 2
+#endif
+    // bf16 storage: a lane owns 8 consecutive columns per 256-column block, i.e. two float4 of every query row
+    constexpr int QREG_JB = (BF16 && PACKED && P <= 4) ? VLSA_SIMT_QREG_JB : 0;
+    float4 qregb[QREG_JB > 0 ? QREG_JB * 2 * NQ : 1];
+    auto load_qregb = [&](int q) {
+#pragma unroll
+        for (int j = 0; j < QREG_JB; ++j) {
+            qregb[(j * NQ + q) * 2 + 0] = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
+            qregb[(j * NQ + q) * 2 + 1] = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+        }
+    };
+    if (QREG_JB > 0) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) load_qregb(q);
+    }
     float4 qreg[QREG_J > 0 ? QREG_J * NQ : 1];
     if (QREG_J > 0) {
 #pragma unroll
@@ -189,6 +206,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 for (int j = 0; j < QREG_J; ++j)
                     qreg[j * NQ + P] = *reinterpret_cast<const float4*>(qs + P * D + j * 128 + lane * 4);
             }
+            if (QREG_JB > 0) load_qregb(P);
         }
         for (long long row = r0; row < r1; row += TN, ++it) {
             const int stage = it % STAGES;
@@ -280,8 +298,11 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                         }
 #pragma unroll
                         for (int q = 0; q < NQ; ++q) {
-                            const float4 qa = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
-                            const float4 qb = *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
+                            const bool in_reg = QREG_JB > 0 && j < QREG_JB;
+                            const float4 qa = in_reg ? qregb[((j < QREG_JB ? j : 0) * NQ + q) * 2 + 0]
+                                                     : *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8);
+                            const float4 qb = in_reg ? qregb[((j < QREG_JB ? j : 0) * NQ + q) * 2 + 1]
+                                                     : *reinterpret_cast<const float4*>(qs + q * D + j * 256 + lane * 8 + 4);
                             const float2 q2[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y),
                                                   make_float2(qb.z, qb.w)};
 #pragma unroll
