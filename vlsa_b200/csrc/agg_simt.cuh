@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     };
     if (tid == 0) for (int s = 0; s < STAGES - 1; ++s) produce();
 
+    constexpr float LAZY_MARGIN = 16.f;
+    float lpart[(P + NW - 1) / NW];
+#pragma unroll
+    for (int k = 0; k < (P + NW - 1) / NW; ++k) lpart[k] = 0.f;
     float acc2[P][CPT];
 #pragma unroll
     for (int p = 0; p < P; ++p)
@@ -353,18 +357,21 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 const bool live = lane < nvalid;
                 const float s = live ? prm.scale * (dot / nrm) : -INFINITY;
                 if (!BWD) {
-                    const float tmax = warp_max(s);
+                    // online softmax with a LAZY reference: it only moves (one warp_max, accumulators rescaled) when a
+                    // row beats it by more than LAZY_MARGIN; otherwise a tile costs one vote and no shuffle chain.  Any
+                    // reference gives the same (m, l, O) triple up to the common factor the merge removes; weights stay
+                    // <= e^LAZY_MARGIN.  The per-prototype sum l is kept per lane and reduced once per chunk.
                     const float mo = s_m[p];
-                    const float mn = fmaxf(mo, tmax);
-                    const float w = expf(s - mn);
-                    const float wsum = warp_sum(w);
-                    if (lane < TN) wt[lane * PP + p] = w;
-                    if (lane == 0) {
-                        const float a = expf(mo - mn);
-                        s_alpha[p] = a;
-                        s_l[p] = s_l[p] * a + wsum;
-                        s_m[p] = mn;
+                    float mn = mo, a = 1.f;
+                    if (__any_sync(0xffffffffu, s > mo + LAZY_MARGIN)) {        // always on the first tile (mo = -inf)
+                        mn = warp_max(s);
+                        a = expf(mo - mn);
                     }
+                    const float w = expf(s - mn);
+                    float& lp = lpart[(p - warp) / NW];
+                    lp = fmaf(lp, a, w);
+                    if (lane < TN) wt[lane * PP + p] = w;
+                    if (lane == 0) { s_alpha[p] = a; s_m[p] = mn; }
                 } else {
                     const float a = expf(s - s_m[p]) * s_l[p];                 // A_pn (deepmil.py:198)
                     const float u = red[rl * NRED + P];                         // (dv . x_n) / P
@@ -441,11 +448,18 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     for (int k = 0; k < CPT; ++k) acc2[p][k] = 0.f;
                 }
                 if (!BWD) {
-                    __syncthreads();           // phase-B readers of s_alpha are done before the reset below
-                    if (tid < P) {
-                        prm.part_m[size_t(c) * P + tid] = s_m[tid];
-                        prm.part_l[size_t(c) * P + tid] = s_l[tid];
-                        s_m[tid] = -INFINITY; s_l[tid] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < (P + NW - 1) / NW; ++k) {
+                        const int p = warp + k * NW;                    // the prototypes phase S of this warp owns
+                        if (p < P) {
+                            const float l = warp_sum(lpart[k]);
+                            if (lane == 0) {
+                                prm.part_m[size_t(c) * P + p] = s_m[p];
+                                prm.part_l[size_t(c) * P + p] = l;
+                                s_m[p] = -INFINITY;
+                            }
+                        }
+                        lpart[k] = 0.f;
                     }
                 }
             }
