@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     float* s_m = sc;                       // running max        (fwd) | saved max        (bwd)
     float* s_l = sc + VLSA_MAX_P;          // running sum        (fwd) | 1 / saved sum    (bwd)
     float* s_alpha = sc + 2 * VLSA_MAX_P;  // per-tile rescale   (fwd) | delta_p          (bwd)
+    float* s_lw = sc + 3 * VLSA_MAX_P;     // [NW][P] per-warp softmax sums at a chunk end (fused forward)
+    int* s_flag = reinterpret_cast<int*>(sc + 5 * VLSA_MAX_P);   // "a row beat the lazy reference" (fused forward)
     uint64_t* full = reinterpret_cast<uint64_t*>(
         (reinterpret_cast<uintptr_t>(sc + 6 * VLSA_MAX_P) + 7) & ~uintptr_t(7));
 
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
         for (int d = lane; d < D; d += 32) qs[p * D + d] = __ldg(q + d) * inv;
     }
     if (tid < P) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_alpha[tid] = 0.f; }
+    if (tid == 0) *s_flag = 0;
     __syncthreads();
 #ifndef VLSA_SIMT_QREG_J
 #define VLSA_SIMT_QREG_J 2
@@ -181,6 +184,11 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     if (tid == 0) for (int s = 0; s < STAGES - 1; ++s) produce();
 
     constexpr float LAZY_MARGIN = 16.f;
+    // forward with all 4 (P + 1) per-warp values in one butterfly group (P <= 7): the weights of a warp's own rows are
+    // computed straight from the butterfly result against the current lazy reference — no separate softmax phase, no
+    // barrier before it; a tile whose rows beat the reference takes the rare path below
+    constexpr bool FUSED_S = !BWD && NV <= 32;
+    float lpart_f = 0.f;                       // fused forward: this lane's (row, prototype) share of the sum l
     float lpart[(P + NW - 1) / NW];
 #pragma unroll
     for (int k = 0; k < (P + NW - 1) / NW; ++k) lpart[k] = 0.f;
@@ -221,6 +229,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
             mbar_wait(full + stage, parity);
 
             // ---------------- phase A: NQ dots + sum of squares for rows 4*warp .. 4*warp+3 --------
+            int fr = 0, fq = 0; bool fact = false; float fs = 0.f, fw = 0.f;     // fused forward: this lane's (row, prototype)
             float acc[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) acc[i] = 0.f;
@@ -345,12 +354,51 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 if (NV - g * 32 >= 32) tot = warp_reduce_transpose<32>(v);
                 else tot = warp_reduce_transpose<(NV % 32 == 0 ? 32 : NV % 32)>(v);
                 const int idx = g * 32 + lane;
-                if (idx < NV) red[(4 * warp + idx / NRED) * NRED + idx % NRED] = tot;
+                if (!FUSED_S) {
+                    if (idx < NV) red[(4 * warp + idx / NRED) * NRED + idx % NRED] = tot;
+                } else {
+                    // lane i < NV holds value (row r = i / NRED of this warp, column q = i % NRED; q == NQ: |x_r|^2)
+                    fr = lane / NRED; fq = lane % NRED;
+                    const float ssv = __shfl_sync(0xffffffffu, tot, (fr * NRED + NQ) & 31);
+                    fact = lane < NV && fq < P;
+                    const int rowl = 4 * warp + fr;
+                    const float nrm = fmaxf(sqrtf(ssv), VLSA_NORM_EPS);
+                    fs = (fact && rowl < nvalid) ? prm.scale * (tot / nrm) : -INFINITY;
+                    const float mo = fact ? s_m[fq < P ? fq : 0] : 0.f;
+                    fw = fact ? expf(fs - mo) : 0.f;                 // tentative: right unless the reference moves
+                    if (fact) { wt[rowl * PP + fq] = fw; red[rowl * NRED + fq] = fs; }
+                    if (__any_sync(0xffffffffu, fact && fs > mo + LAZY_MARGIN) && lane == 0) *s_flag = 1;
+                }
             }
             __syncthreads();
+            bool grew = false;
+            if (FUSED_S) {
+                grew = *reinterpret_cast<volatile int*>(s_flag) != 0;      // block-uniform
+                if (grew) {
+                    // rare (always on the first tile of a chunk): move the reference of the prototypes that were beaten,
+                    // rewrite the tile's weights; one warp per prototype, lane = row
+                    for (int p = warp; p < P; p += NW) {
+                        const float sv = lane < TN ? red[lane * NRED + p] : -INFINITY;
+                        const float tmax = warp_max(sv);
+                        const float mo = s_m[p];
+                        const float mn = tmax > mo + LAZY_MARGIN ? tmax : mo;
+                        if (lane < TN) wt[lane * PP + p] = sv == -INFINITY ? 0.f : expf(sv - mn);
+                        if (lane == 0) { s_alpha[p] = expf(mo - mn); s_m[p] = mn; }
+                    }
+                    __syncthreads();
+                    if (tid == 0) *s_flag = 0;
+                    if (fact) {
+                        const int qq = fq < P ? fq : 0;
+                        fw = fs == -INFINITY ? 0.f : expf(fs - s_m[qq]);
+                        lpart_f = fmaf(lpart_f, s_alpha[qq], fw);
+                    }
+                } else if (fact) {
+                    lpart_f += fw;
+                }
+            }
 
             // ---------------- phase S: per-(row, p) weights; lane = row, warp handles p = warp, warp+NW ----
-            for (int p = warp; p < P; p += NW) {
+            for (int p = warp; p < P && !FUSED_S; p += NW) {
                 const int rl = lane < TN ? lane : 0;
                 const float dot = red[rl * NRED + p], ss = red[rl * NRED + NQ];
                 const float nrm = fmaxf(sqrtf(ss), VLSA_NORM_EPS);
@@ -378,10 +426,10 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     if (lane < TN) wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
                 }
             }
-            __syncthreads();
+            if (!FUSED_S) __syncthreads();
 
             // ---------------- phase B: acc2[p][:] (+)= sum_r w[r][p] * x[r][CPT*tid .. CPT*tid+CPT-1] ---------
-            if (!BWD) {
+            if (!BWD && (!FUSED_S || grew)) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     const float a = s_alpha[p];
@@ -447,7 +495,23 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
 #pragma unroll
                     for (int k = 0; k < CPT; ++k) acc2[p][k] = 0.f;
                 }
-                if (!BWD) {
+                if (FUSED_S) {
+                    // l_p = sum over the 4 rows of every warp: lanes (r, q) -> lane q by two shuffles, warps via smem
+                    float v = lpart_f;
+                    v += __shfl_down_sync(0xffffffffu, v, 2 * NRED);
+                    v += __shfl_down_sync(0xffffffffu, v, NRED);
+                    if (lane < P) s_lw[warp * P + lane] = v;
+                    lpart_f = 0.f;
+                    __syncthreads();
+                    if (tid < P) {
+                        float l = 0.f;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) l += s_lw[w * P + tid];
+                        prm.part_m[size_t(c) * P + tid] = s_m[tid];
+                        prm.part_l[size_t(c) * P + tid] = l;
+                        s_m[tid] = -INFINITY;
+                    }
+                } else if (!BWD) {
 #pragma unroll
                     for (int k = 0; k < (P + NW - 1) / NW; ++k) {
                         const int p = warp + k * NW;                    // the prototypes phase S of this warp owns
