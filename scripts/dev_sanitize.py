@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from vlsa_b200 import ops, synth
 dev = torch.device("cuda:0")
-for variant in ("tc", "simt"):
+for variant in (os.environ.get("DEV_VARIANTS", "tc,simt").split(",")):
     ops.set_agg_variant(variant)
     for P, sizes in ((12, [2798, 1000, 37, 1]), (4, [513, 64])):
         bags = [synth.make_bag("g1", n, 100 + i) for i, n in enumerate(sizes)]

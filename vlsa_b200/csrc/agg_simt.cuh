@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                         const float mo = s_m[p];
                         const float mn = tmax > mo + LAZY_MARGIN ? tmax : mo;
                         if (lane < TN) wt[lane * PP + p] = sv == -INFINITY ? 0.f : expf(sv - mn);
+                        __syncwarp();                                   // every lane has read s_m[p]
                         if (lane == 0) { s_alpha[p] = expf(mo - mn); s_m[p] = mn; }
                     }
                     __syncthreads();
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     float& lp = lpart[(p - warp) / NW];
                     lp = fmaf(lp, a, w);
                     if (lane < TN) wt[lane * PP + p] = w;
+                    __syncwarp();                                       // every lane has read s_m[p]
                     if (lane == 0) { s_alpha[p] = a; s_m[p] = mn; }
                 } else {
                     const float a = expf(s - s_m[p]) * s_l[p];                 // A_pn (deepmil.py:198)
