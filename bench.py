@@ -248,7 +248,7 @@ def main():
     W, b = net.mil_encoder.visual_adapter.weight.detach(), net.mil_encoder.visual_adapter.bias.detach()
     T, ls = net.forward_text_only().contiguous(), net.logit_scale.detach()
     ws = ops._workspace(plan, P, dev)
-    use_tc = args.dtype == "fp32" and P > 4 and os.environ.get("VLSA_AGG_VARIANT", "")[:1] != "s" \
+    use_tc = args.dtype == "fp32" and P > 5 and os.environ.get("VLSA_AGG_VARIANT", "")[:1] != "s" \
         or os.environ.get("VLSA_AGG_VARIANT", "")[:1] == "t" and args.dtype == "fp32"
     kernel_name = "agg_tc_kernel<false> (tcgen05)" if use_tc else "agg_simt_kernel<P,false,XT>"
     two_level = plan.total_chunks >= 8 * nb

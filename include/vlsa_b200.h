@@ -49,7 +49,7 @@ extern "C" {
 int vlsa_version(void);
 const char* vlsa_error_string(int code);
 /* Development / cross-check hook (process-wide, the only piece of global state in the library): which streaming
- * kernel serves fp32 passes.  -1 = automatic (tcgen05 kernel for P > 4, CUDA-core kernel otherwise), 0 = CUDA-core
+ * kernel serves fp32 passes.  -1 = automatic (tcgen05 kernel for P > 5, CUDA-core kernel otherwise), 0 = CUDA-core
  * kernel, 1 = tcgen05 kernel.  Both compute the same function (reference: model/deepmil.py:187-203); the parity
  * tests run every case through both. */
 int vlsa_debug_set_agg_variant(int variant);

@@ -21,7 +21,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
 
     cfgs = [(4, 50000, 32), (12, 50000, 32), (16, 50000, 32), (12, 10000, 32), (12, 2798, 32)]
     if os.environ.get("DEV_QUICK"): cfgs = cfgs[:2]
-    if os.environ.get("DEV_PSWEEP"): cfgs = [(p_, 50000, 32) for p_ in (2, 4, 5, 6, 8, 10, 12)]
+    if os.environ.get("DEV_PSWEEP"): cfgs = [(p_, 50000, 32) for p_ in [int(x) for x in os.environ.get('DEV_PLIST', '2,4,5,6,8,10,12').split(',')]]
     for (P, N, B) in cfgs:
         pr = synth.make_params(P, P, 1)
         Xs = [torch.randn(N * B, 512, device=dev) * 1.1 + 0.7 for _ in range(2)]

@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
     // computed straight from the butterfly result against the current lazy reference — no separate softmax phase, no
     // barrier before it; a tile whose rows beat the reference takes the rare path below
     constexpr bool FUSED_S = !BWD && NV <= 32;
+    // backward with one butterfly group (P <= 6): the weight of (row, prototype) needs only that row's values and the
+    // saved per-bag (m, 1/l, delta): computed by the lane that holds the score, no softmax phase and no barrier for it
+    constexpr bool FUSED_W = BWD && NV <= 32;
     float lpart_f = 0.f;                       // fused forward: this lane's (row, prototype) share of the sum l
     float lpart[(P + NW - 1) / NW];
 #pragma unroll
@@ -354,7 +357,19 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 if (NV - g * 32 >= 32) tot = warp_reduce_transpose<32>(v);
                 else tot = warp_reduce_transpose<(NV % 32 == 0 ? 32 : NV % 32)>(v);
                 const int idx = g * 32 + lane;
-                if (!FUSED_S) {
+                if (FUSED_W) {
+                    // lane i < NV: (row r = i / NRED, column q = i % NRED); q < P: Qn_q . x, q == P: (dv . x) / P, q == NQ: |x|^2
+                    const int r = lane / NRED, q = lane % NRED;
+                    const float ssv = __shfl_sync(0xffffffffu, tot, (r * NRED + NQ) & 31);
+                    const float uv = __shfl_sync(0xffffffffu, tot, (r * NRED + P) & 31);
+                    const int rowl = 4 * warp + r;
+                    if (lane < NV && q < P) {
+                        const float nrm = fmaxf(sqrtf(ssv), VLSA_NORM_EPS);
+                        const float sv = prm.scale * (tot / nrm);
+                        const float a = expf(sv - s_m[q]) * s_l[q];                      // A_pn (deepmil.py:198)
+                        wt[rowl * PP + q] = rowl < nvalid ? prm.scale * a * (uv - s_alpha[q]) / nrm : 0.f;
+                    }
+                } else if (!FUSED_S) {
                     if (idx < NV) red[(4 * warp + idx / NRED) * NRED + idx % NRED] = tot;
                 } else {
                     // lane i < NV holds value (row r = i / NRED of this warp, column q = i % NRED; q == NQ: |x_r|^2)
@@ -399,7 +414,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
             }
 
             // ---------------- phase S: per-(row, p) weights; lane = row, warp handles p = warp, warp+NW ----
-            for (int p = warp; p < P && !FUSED_S; p += NW) {
+            for (int p = warp; p < P && !FUSED_S && !FUSED_W; p += NW) {
                 const int rl = lane < TN ? lane : 0;
                 const float dot = red[rl * NRED + p], ss = red[rl * NRED + NQ];
                 const float nrm = fmaxf(sqrtf(ss), VLSA_NORM_EPS);
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     if (lane < TN) wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
                 }
             }
-            if (!FUSED_S) __syncthreads();
+            if (!FUSED_S && !FUSED_W) __syncthreads();
 
             // ---------------- phase B: acc2[p][:] (+)= sum_r w[r][p] * x[r][CPT*tid .. CPT*tid+CPT-1] ---------
             if (!BWD && (!FUSED_S || grew)) {

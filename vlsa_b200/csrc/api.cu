@@ -147,7 +147,7 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
 }
 
 // Which streaming kernel serves an fp32 pass (forward or backward): the tcgen05 variant or the CUDA-core one.
-// Default: tensor cores for P > 4 (the CUDA-core kernel is faster at P <= 4).  Cross-checking hooks:
+// Default: tensor cores for P > 5 (the CUDA-core kernel is faster at P <= 5).  Cross-checking hooks:
 // the environment variable VLSA_AGG_VARIANT=simt|tc and vlsa_debug_set_agg_variant() force one of them.
 #include <atomic>
 static std::atomic<int> g_agg_variant{[] {
@@ -161,7 +161,7 @@ static bool agg_use_tc(int P, int x_dtype) {
     if (x_dtype != VLSA_DTYPE_F32) return false;
     const int forced = g_agg_variant.load(std::memory_order_relaxed);
     if (forced >= 0) return forced == 1;
-    return P > 4;
+    return P > 5;
 }
 
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {

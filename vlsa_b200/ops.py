@@ -27,7 +27,7 @@ def coattn_scale() -> float:
 
 def set_agg_variant(variant: str | None) -> None:
     """Cross-check hook: force the streaming kernel of fp32 passes ('simt' = CUDA cores, 'tc' = tcgen05) or
-    None for the automatic choice (tensor cores for P > 4)."""
+    None for the automatic choice (tensor cores for P > 5)."""
     code = {None: -1, "auto": -1, "simt": 0, "tc": 1}[variant]
     rc = _lib.lib().vlsa_debug_set_agg_variant(code)
     if rc:
