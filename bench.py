@@ -311,8 +311,8 @@ def main():
             handler.bucket.unpack()
             handler.optimizer.step()
 
-        n_train = max(3, min(args.steps, 10))
-        for i in range(3):
+        n_train = max(3, min(args.steps, 20))
+        for i in range(5):
             train_step(i)
         sync_all()
         t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
