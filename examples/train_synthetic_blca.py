@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""BASELINE configs[2] as a runnable example: slide-sharded VLSA training on a synthetic TCGA-BLCA-like cohort.
+
+    python examples/train_synthetic_blca.py                                  # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        examples/train_synthetic_blca.py --patients 373                      # 8 GPUs, bags sharded per step
+
+Pipeline (all of it is the accelerated path): synthetic patients -> flat memory-mapped feature store
+(`vlsa_b200.dataset.build_store`) -> `WSIPatchSurvStore` (same items as the reference's `WSIPatchSurv`) ->
+`VLSAHandler._train_each_epoch` with `cfg_vlsa_conch.yaml`-style settings (batch of 32 bags per optimizer step, bags
+LPT-sharded over the ranks, ONE flat-bucket NCCL all-reduce, Adam) -> `test_model` -> concordance index.
+
+The cohort has a planted signal so that learning is visible: a patient's latent risk tilts a fraction of its patches
+towards one of the prototype directions, and the (discretised) survival time decreases with the risk; 45 % of the
+patients are events (BLCA: 169 / 373).  There is no network access in this image, so CONCH text features and real
+slides are replaced by fixed random tensors of the same shapes (P = 12 prototypes, R = 12 time bins).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def concordance_index(risk: np.ndarray, t: np.ndarray, e: np.ndarray) -> float:
+    """Harrell's C on (time bin, event) labels: comparable pairs = (i an event, t_i < t_j)."""
+    num = den = 0.0
+    for i in np.where(e > 0)[0]:
+        later = t > t[i]
+        den += later.sum()
+        num += (risk[i] > risk[later]).sum() + 0.5 * (risk[i] == risk[later]).sum()
+    return float(num / max(den, 1.0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--patients", type=int, default=128)
+    ap.add_argument("--min-n", type=int, default=1000)
+    ap.add_argument("--max-n", type=int, default=20000)
+    ap.add_argument("--epochs", type=int, default=4)
+    ap.add_argument("--P", type=int, default=12)
+    ap.add_argument("--R", type=int, default=12)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vlsa_b200 import synth
+    from vlsa_b200.dataset import PatchFeatureStore, WSIPatchSurvStore, build_store
+    from vlsa_b200.model import VLSA
+    from vlsa_b200.runner import VLSAHandler
+
+    P, R = args.P, args.R
+    torch.manual_seed(args.seed)
+    pr = synth.make_params(P, R, 1)
+    g = torch.Generator().manual_seed(args.seed)
+    # ---- cohort (identical on every rank: same seed) ---------------------------------------------------
+    sizes = np.exp(np.random.default_rng(args.seed).uniform(np.log(args.min_n), np.log(args.max_n), args.patients)).astype(int)
+    risk = torch.rand(args.patients, generator=g)
+    event = (torch.rand(args.patients, generator=g) < 0.45).float()
+    tbin = ((1.0 - risk) * R * (0.6 + 0.4 * torch.rand(args.patients, generator=g))).clamp(0, R - 1).floor()
+    direction = torch.nn.functional.normalize(pr["prompt_features"][0], dim=0)
+
+    def slides():
+        for i in range(args.patients):
+            x = synth.make_bag("g1", int(sizes[i]), 5000 + i)
+            k = max(1, int(0.05 * sizes[i]))
+            x[:k] += (6.0 * risk[i]) * direction * x[:k].norm(dim=-1, keepdim=True) / 25.0      # planted signal
+            yield f"slide{i:04d}", x
+
+    store_dir = os.path.join(tempfile.gettempdir(), f"vlsa_b200_store_{args.seed}_{args.patients}_{args.max_n}")
+    if rank == 0 and not os.path.exists(os.path.join(store_dir, "index.json")):
+        t0 = time.time()
+        meta = build_store(store_dir, slides())
+        print(f"[store] {meta['rows']} rows ({meta['rows'] * 2048 / 1e9:.2f} GB) in {time.time() - t0:.1f} s -> {store_dir}", flush=True)
+    if world > 1:
+        dist.barrier()
+    store = PatchFeatureStore(store_dir)
+    pids = [f"p{i:04d}" for i in range(args.patients)]
+    pid2sids = {p: [f"slide{i:04d}"] for i, p in enumerate(pids)}
+    pid2label = {p: (float(tbin[i]), float(event[i])) for i, p in enumerate(pids)}
+    ds = WSIPatchSurvStore(store, pids, pid2sids, pid2label)
+
+    class OneBagLoader:            # DataLoader(batch_size=1) of the reference: (idx [1], (feats [1,N,512], extra), label [1,2])
+        def __len__(self): return len(ds)
+        def __iter__(self):
+            for i in range(len(ds)):
+                idx, (feats, _), label = ds[i]
+                yield idx, (feats.unsqueeze(0),), label.unsqueeze(0)
+
+    cfg = {"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4,
+           "opt_weight_decay": 1e-5, "bp_every_batch": 32, "net_output_converter": "softmax"}
+    net = VLSA(text_encoder_cfg={"name": "mahmoodlab/conch"},
+               image_encoder_cfg=dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, query="Text", num_query=P,
+                                      gated_query=False, query_pooling="mean", pred_head="default",
+                                      query_text_method="TaskRes", query_text_res_ratio=0.5),
+               prompt_learner_cfg={"name": "CoOp"}, text_features=pr["text_features"],
+               query_prompt_features=pr["prompt_features"], vlsa_api="CONCH", path_clip_model=None)
+    handler = VLSAHandler(cfg, net=net, device=dev)
+    loader = OneBagLoader()
+    for epoch in range(args.epochs):
+        torch.cuda.synchronize(); t0 = time.time()
+        out = handler._train_each_epoch(epoch, loader)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        pred = handler.test_model(handler.net, loader)["pred"]
+        inc = pred["y_hat"].numpy()                                            # incidence function [n, R]
+        score = (inc * np.arange(R)[None, :]).sum(1)                           # expected time bin: low = high risk
+        c = concordance_index(-score, pred["y"][:, 0].numpy(), pred["y"][:, 1].numpy())
+        if rank == 0:
+            print(f"[epoch {epoch}] loss {np.mean(out['loss']):.4f}  C-index {c:.3f}  train {dt:.2f} s "
+                  f"({args.patients / dt:.0f} bags/s incl. store reads and H2D, {world} GPU(s))", flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,3 +118,38 @@ def test_two_rank_step_equals_single_process_step(tmp_path):
     torch.testing.assert_close(r1["preds"], r0["preds"], rtol=0, atol=0)
     # and the parameters actually moved
     assert not torch.equal(ref_state["mil_encoder.visual_adapter.weight"], synth.make_params(P, R, 5)["W"])
+
+
+def _worker_bcast(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vlsa_b200.model import VLSA
+        from vlsa_b200.runner import VLSAHandler
+        torch.manual_seed(1000 + rank)                        # replicas start from DIFFERENT random states
+        pr = synth.make_params(P, R, 5)
+        net = VLSA({"name": "mahmoodlab/conch"},
+                   dict(name="VLFAN", dim_in=512, use_feat_proj=False, query="Text", num_query=P, gated_query=False,
+                        query_pooling="mean", pred_head="default", query_text_method="TaskRes", query_text_res_ratio=0.5),
+                   {"name": "CoOp"}, text_features=pr["text_features"], query_prompt_features=pr["prompt_features"],
+                   vlsa_api="CONCH", path_clip_model=None)
+        before = net.mil_encoder.visual_adapter.weight.detach().clone()
+        h = VLSAHandler(dict(task="vlsa", arch="VLSA", opt_name="adam"), net, device="cpu")
+        state = {k: v.detach().clone() for k, v in h.net.state_dict().items()}
+        torch.save({"before": before, "state": state}, os.path.join(out_dir, f"b{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_handler_broadcasts_rank0_parameters(tmp_path):
+    """Replicas built from different random states (nn.Linear / randn initialisers) must be identical before the
+    first step: the handler broadcasts rank 0's parameters at construction, like DDP."""
+    port = _free_port()
+    mp.spawn(_worker_bcast, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    b0, b1 = torch.load(tmp_path / "b0.pt"), torch.load(tmp_path / "b1.pt")
+    assert not torch.equal(b0["before"], b1["before"])                    # they did start differently
+    for k in b0["state"]:
+        assert torch.equal(b0["state"][k], b1["state"][k]), k
+    assert torch.equal(b0["state"]["mil_encoder.visual_adapter.weight"], b0["before"])   # rank 0 is the source

@@ -111,6 +111,24 @@ class FlatBucket:
                 p.grad.copy_(g)
 
 
+def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
+    """Make every rank start from rank `src`'s parameters and buffers (one flat broadcast), as DDP does at
+    construction: replicas that were initialised from different random states must not average gradients."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    tensors = [t for t in list(module.parameters()) + list(module.buffers()) if t.is_floating_point()]
+    if not tensors:
+        return
+    flat = torch.cat([t.detach().reshape(-1).float() for t in tensors])
+    dist.broadcast(flat, src=src)
+    at = 0
+    with torch.no_grad():
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[at:at + n].view_as(t).to(t.dtype))
+            at += n
+
+
 def all_reduce_rows(local_rows: torch.Tensor, local_idx: Sequence[int], n_total: int) -> torch.Tensor:
     """Assemble the [n_total, R] prediction matrix from every rank's rows (each row owned by one rank)."""
     out = torch.zeros(n_total, local_rows.shape[-1], dtype=local_rows.dtype, device=local_rows.device)

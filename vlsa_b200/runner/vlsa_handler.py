@@ -91,6 +91,7 @@ class VLSAHandler:
         self.optimizer = torch.optim.Adam(param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5))),
                                           lr=float(cfg.get("opt_lr", 2e-4)), fused=self.device.type == "cuda")
         self.rank, self.world_size = vdist.world()
+        vdist.broadcast_module(self.net)          # identical replicas before the first step
         self.balance_shards = balance_shards
         self.bucket = vdist.FlatBucket(self.net.parameters(), extra=1)
         self.bucket.attach()                      # gradients live in the all-reduce bucket: no pack / unpack copies
