@@ -112,16 +112,26 @@ def main():
                query_prompt_features=pr["prompt_features"], vlsa_api="CONCH", path_clip_model=None)
     handler = VLSAHandler(cfg, net=net, device=dev)
     loader = OneBagLoader()
+    bs = cfg["bp_every_batch"]
+    sizes_all = [store.n_rows(pid2sids[p]) for p in pids]
     for epoch in range(args.epochs):
         torch.cuda.synchronize(); t0 = time.time()
-        out = handler._train_each_epoch(epoch, loader)
+        handler.net.train()
+        losses = []
+        for s0 in range(0, len(pids), bs):                   # one optimizer step = 32 patients (vlsa_handler.py:260-289)
+            ids = list(range(s0, min(s0 + bs, len(pids))))
+            # lazy bags: a rank only reads the patients of its own shard from the store
+            xs = [(lambda i=i: ds[i][1][0].unsqueeze(0)) for i in ids]
+            ys = [torch.tensor(pid2label[pids[i]]).reshape(1, 2) for i in ids]
+            loss, _ = handler._update_network(xs, ys, sizes=[sizes_all[i] for i in ids])
+            losses.append(loss)
         torch.cuda.synchronize(); dt = time.time() - t0
         pred = handler.test_model(handler.net, loader)["pred"]
         inc = pred["y_hat"].numpy()                                            # incidence function [n, R]
         score = (inc * np.arange(R)[None, :]).sum(1)                           # expected time bin: low = high risk
         c = concordance_index(-score, pred["y"][:, 0].numpy(), pred["y"][:, 1].numpy())
         if rank == 0:
-            print(f"[epoch {epoch}] loss {np.mean(out['loss']):.4f}  C-index {c:.3f}  train {dt:.2f} s "
+            print(f"[epoch {epoch}] loss {np.mean(losses):.4f}  C-index {c:.3f}  train {dt:.2f} s "
                   f"({args.patients / dt:.0f} bags/s incl. store reads and H2D, {world} GPU(s))", flush=True)
     if world > 1:
         dist.destroy_process_group()

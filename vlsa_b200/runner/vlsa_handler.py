@@ -107,23 +107,39 @@ class VLSAHandler:
         bags = [xs[i][0] if xs[i].dim() == 3 else xs[i] for i in idx]
         sizes = [int(b.shape[0]) for b in bags]
         if bags and not bags[0].is_cuda:
-            host, _ = pack_bags(bags)
+            # two pinned staging buffers, reused alternately: the async copy of one step may still be reading its
+            # buffer while the next step is packed (cudaHostAlloc per step would dominate small steps)
+            self._pin_slot = 1 - getattr(self, "_pin_slot", 0)
+            pins = self.__dict__.setdefault("_pins", [None, None])
+            ev = self.__dict__.setdefault("_pin_events", [None, None])
+            if ev[self._pin_slot] is not None:
+                ev[self._pin_slot].synchronize()
+            host, _ = pack_bags(bags, pins[self._pin_slot])
+            pins[self._pin_slot] = host
             X = host[: sum(sizes)].to(self.device, non_blocking=True)
+            if self.device.type == "cuda":
+                ev[self._pin_slot] = torch.cuda.Event()
+                ev[self._pin_slot].record()
         elif bags:
             X = torch.cat(bags, 0) if len(bags) > 1 else bags[0].contiguous()
         else:
             X = torch.empty(0, ops.D_FEAT, device=self.device)
         return X, ops.make_plan(sizes, self.device)
 
-    def _update_network(self, xs, ys):
-        """One optimizer step on the bags `xs` (list of [1,N_i,512]) with labels `ys` (list of [1,2])."""
+    def _update_network(self, xs, ys, sizes: Sequence[int] | None = None):
+        """One optimizer step on the bags `xs` (list of [1,N_i,512]) with labels `ys` (list of [1,2]).
+
+        `xs[i]` may also be a zero-argument callable returning the bag (then `sizes` gives the N_i): only the bags of
+        this rank's shard are fetched, so with a lazy dataset every rank reads 1/world of the step from storage."""
         n_sample = len(xs)
-        sizes = [int(x.shape[-2]) for x in xs]
+        if sizes is None:
+            sizes = [int(x.shape[-2]) for x in xs]
         mine = vdist.shard_indices(sizes, self.rank, self.world_size, self.balance_shards)
         self.bucket.zero()
         bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
         if mine:
-            X, plan = self._pack_local(xs, mine)
+            local = {i: (xs[i]() if callable(xs[i]) else xs[i]) for i in mine}
+            X, plan = self._pack_local(local, mine)
             logits, _, _, _ = self.net.forward_packed(X, plan)                       # [B_local, R]
             sel = torch.as_tensor(mine, device=self.device)
             pred_loss = self.calc_objective_loss(logits, bag_label[sel], norm=n_sample)   # sum_local / n_sample
