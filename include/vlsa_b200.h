@@ -102,13 +102,33 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
                  const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
                  float* dT, float* dlogit_scale, void* stream);
 
+/* Pooled per-prototype features only: O[b][p] = softmax_n(scale * qdir_p . x_n / |x_n|) @ X_b  (model/deepmil.py:187-200),
+ * for the VLFAN configurations whose tail is not "mean over P -> Linear": gated_query (deepmil.py:192-195),
+ * query_pooling 'max' | 'weight' | 'attention' | 'gated_attention' (deepmil.py:133-150), pred_head 'Identity'
+ * (deepmil.py:111-114).  The tail of those variants is P x 512 work and stays with the caller.
+ * q_prenorm = 0: qdir_p = Q_p / |Q_p| as in vlsa_agg_fwd.  q_prenorm = 1: qdir_p = Q_p as given — the gated query
+ * passes Qn_p - Qn_gate, the difference of two unit rows (A_[:, :-1] - A_[:, -1:] is linear in the query).
+ * Same plan and workspace as vlsa_agg_fwd.  out_ml [B,P,2], out_O [B,P,D]. */
+int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                        int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
+                        void* workspace, size_t workspace_bytes, float* out_ml, float* out_O, void* stream);
+
+/* Backward of vlsa_agg_pooled_fwd for an arbitrary gradient d_O [B,P,D] (one row per prototype):
+ *   dS_pn = A_pn (d_O_p . x_n - d_O_p . O_p),  dqdir_p = scale * sum_n dS_pn x_n / |x_n|,
+ * dQ [P,D] = dqdir pushed through the row normalisation (q_prenorm = 0) or dqdir itself (q_prenorm = 1), summed
+ * over the B bags.  One pass over X with 2 P + 1 dot products per row (CUDA-core kernel for every P and dtype). */
+int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                        int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
+                        const float* ml, const float* O, const float* d_O, void* workspace, size_t workspace_bytes,
+                        float* dQ, void* stream);
+
 /* Attention read-out of ONE bag (`ret_with_attn=True`, model/deepmil.py:206-213; utils/model_inference.py:104-113).
  * ml != NULL: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1], the softmax over the N patches with the
  *   normalisers ml [P,2] from vlsa_agg_fwd (axis_softmax = 'V', the `cottn_score` of the forward);
  * ml == NULL: A[p][n] = softmax over the P prototypes of scale * cos(Q_p, x_n) (axis_softmax = 'L').
- * out_A is [P,N]. */
-int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
-                  float* out_A, void* stream);
+ * q_prenorm as in vlsa_agg_pooled_fwd (0 everywhere except the gated query).  out_A is [P,N]. */
+int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, int q_prenorm, float coattn_scale,
+                  const float* ml, float* out_A, void* stream);
 
 /* Interpretation path, "decoupled" text-image similarities per prototype (utils/model_inference.py:115-131):
  *   sim[b][p][r]  = cottn_score_p @ ((visual_adapter(X) / |f_b|) @ Tn_r)  =  (W O_bp + bias) . Tn_r / |f_b|

@@ -30,6 +30,7 @@ __all__ = [
     "coattn_scale", "task_res_query", "vlfan_forward", "vlsa_forward", "logit_pooling",
     "vlsa_forward_zero_shot", "softmax_converter", "surv_ifmle", "convert_survival_label",
     "cdf_loss_p2_raw", "surv_emd", "objective_loss", "decoupled_similarity", "forward_with_grads",
+    "query_pooling", "vlfan_forward_variant",
 ]
 
 
@@ -61,6 +62,57 @@ def vlfan_forward(X, Q, W, b, ret_with_attn: bool = False, scale: torch.Tensor |
     if ret_with_attn:
         return f, A.detach()                                 # deepmil.py:206-213
     return f
+
+
+def query_pooling(out, method: str, pool_params=None):
+    """model/deepmil.py:133-150 over the P co-attention outputs: out [1,P,D] -> (pooled [1,D], scores | None).
+    ``pool_params``: 'weight' -> {"weight": [1,P]}; 'attention' (model/layers.py:126-155, returns the RAW logits) ->
+    {"attention.0.weight", "attention.0.bias", "attention.2.weight", "attention.2.bias"}; 'gated_attention'
+    (model/layers.py:85-123, eval mode: dropout off; returns the softmaxed scores) -> {"fc1.0.weight", "fc1.0.bias",
+    "score.0.weight", "score.0.bias", "fc2.weight", "fc2.bias"}."""
+    if method == "mean":
+        return torch.mean(out, dim=1), None                  # deepmil.py:135-137
+    if method == "max":
+        return torch.max(out, dim=1)[0], None                # deepmil.py:139-141
+    if method == "weight":
+        weight = F.softmax(pool_params["weight"], dim=-1).unsqueeze(0)     # deepmil.py:148  [1,1,P]
+        return torch.matmul(weight, out).squeeze(1), None    # deepmil.py:149
+    if method == "attention":
+        h = torch.tanh(F.linear(out, pool_params["attention.0.weight"], pool_params["attention.0.bias"]))
+        A_ = F.linear(h, pool_params["attention.2.weight"], pool_params["attention.2.bias"])   # layers.py:144
+        A_ = torch.transpose(A_, 2, 1)                       # layers.py:145  [1,1,P]
+        attn = F.softmax(A_, dim=2)                          # layers.py:146
+        return torch.matmul(attn, out).squeeze(1), A_.squeeze(1)          # layers.py:147-150
+    if method == "gated_attention":
+        emb = torch.tanh(F.linear(out, pool_params["fc1.0.weight"], pool_params["fc1.0.bias"]))        # layers.py:111
+        scr = torch.sigmoid(F.linear(out, pool_params["score.0.weight"], pool_params["score.0.bias"]))  # layers.py:112
+        A_ = F.linear(emb.mul(scr), pool_params["fc2.weight"], pool_params["fc2.bias"])               # layers.py:113-114
+        A_ = torch.transpose(A_, 2, 1)                       # layers.py:115
+        A = F.softmax(A_, dim=2)                             # layers.py:116
+        return torch.matmul(A, out).squeeze(1), A.squeeze(1)              # layers.py:117-123
+    raise ValueError(method)
+
+
+def vlfan_forward_variant(X, Q, W, b, gated_query: bool = False, pooling: str = "mean", pool_params=None,
+                          pred_head: str = "default", scale: torch.Tensor | None = None):
+    """model/deepmil.py:170-215 with the config-reachable switches no shipped VLSA config enables:
+    gated_query (Q has P+1 rows, the last one is the gate, deepmil.py:192-195), query_pooling (deepmil.py:133-150),
+    pred_head 'Identity' (deepmil.py:111-114).  Returns (f [1,D], A [1,P,N], pooling scores | None, out [1,P,D])."""
+    assert X.shape[0] == 1                                   # deepmil.py:175
+    if scale is None:
+        scale = (torch.ones([]) * np.log(100)).exp()         # deepmil.py:122
+    scale = scale.to(X.dtype)
+    Qn = F.normalize(Q.unsqueeze(0), dim=-1)                 # deepmil.py:187
+    norm_X = F.normalize(X, dim=-1)                          # deepmil.py:189
+    A_ = torch.matmul(Qn, norm_X.transpose(1, 2))            # deepmil.py:190
+    if gated_query:
+        A_ = A_[:, :-1, :] - A_[:, -1:, :]                   # deepmil.py:195
+    A_ = scale * A_                                          # deepmil.py:197
+    A = F.softmax(A_, dim=-1)                                # deepmil.py:198
+    out = torch.matmul(A, X)                                 # deepmil.py:200
+    pooled, ext = query_pooling(out, pooling, pool_params)   # deepmil.py:203
+    f = pooled if pred_head == "Identity" else F.linear(pooled, W, b)     # deepmil.py:111-118,204
+    return f, A.detach(), (None if ext is None else ext.detach()), out
 
 
 def vlsa_forward(X, Q, W, b, T, logit_scale):

@@ -65,3 +65,48 @@ def rebuild_inputs(name, case):
     t = torch.from_numpy(case["t"].copy()) if "t" in case else None
     e = torch.from_numpy(case["e"].copy()) if "e" in case else None
     return bags, params, t, e
+
+
+# ---- VLFAN variants: cases and seeded inputs shared by the generator and the tests -----------------
+VARIANT_CASES = [
+    dict(P=4, gated=True, pooling="mean", pred_head="default", hid=32, kind="g1", ns=(1000, 37), seed=31001),
+    dict(P=12, gated=True, pooling="mean", pred_head="default", hid=32, kind="g0", ns=(2798,), seed=31002),
+    dict(P=4, gated=False, pooling="max", pred_head="default", hid=32, kind="g1", ns=(1000, 513), seed=31003),
+    dict(P=12, gated=False, pooling="weight", pred_head="default", hid=32, kind="g1", ns=(300, 2000, 64), seed=31004),
+    dict(P=8, gated=False, pooling="attention", pred_head="default", hid=32, kind="g1", ns=(1000, 129), seed=31005),
+    dict(P=6, gated=False, pooling="gated_attention", pred_head="default", hid=32, kind="g0", ns=(700,), seed=31006),
+    dict(P=4, gated=False, pooling="mean", pred_head="Identity", hid=32, kind="g1", ns=(1000,), seed=31007),
+    dict(P=3, gated=True, pooling="attention", pred_head="Identity", hid=32, kind="g1", ns=(257, 1), seed=31008),
+    dict(P=16, gated=True, pooling="max", pred_head="default", hid=32, kind="g1", ns=(1500, 33), seed=31009),
+]
+
+
+def variant_name(case):
+    return "variant_P{P}_{g}_{pooling}_{h}_{kind}".format(g="gated" if case["gated"] else "plain",
+                                                          h="id" if case["pred_head"] == "Identity" else "lin", **case)
+
+
+def variant_inputs(case):
+    """Seeded inputs of a variant case: bags, the queries Q [P (+1), 512] (prototype directions + 0.5 * randn, like the
+    TaskRes query), the pooling parameters, the gradient seeds G [1,512] per bag; W, b from the shipped checkpoint."""
+    ck = _ckpt()
+    seed, P, hid = case["seed"], case["P"], case["hid"]
+    g = torch.Generator().manual_seed(seed)
+    nq = P + 1 if case["gated"] else P
+    proto = torch.nn.functional.normalize(torch.randn(nq, 512, generator=g), dim=-1)
+    Q = (0.5 * torch.randn(nq, 512, generator=g) + proto).contiguous()
+    pool = {}
+    if case["pooling"] == "weight":
+        pool["weight"] = torch.randn(1, P, generator=g)
+    elif case["pooling"] == "attention":
+        pool = {"attention.0.weight": torch.randn(hid, 512, generator=g) / 512 ** 0.5,
+                "attention.0.bias": 0.1 * torch.randn(hid, generator=g),
+                "attention.2.weight": torch.randn(1, hid, generator=g) / hid ** 0.5,
+                "attention.2.bias": 0.1 * torch.randn(1, generator=g)}
+    elif case["pooling"] == "gated_attention":
+        pool = {"fc1.0.weight": torch.randn(hid, 512, generator=g) / 512 ** 0.5, "fc1.0.bias": 0.1 * torch.randn(hid, generator=g),
+                "score.0.weight": torch.randn(hid, 512, generator=g) / 512 ** 0.5, "score.0.bias": 0.1 * torch.randn(hid, generator=g),
+                "fc2.weight": torch.randn(1, hid, generator=g) / hid ** 0.5, "fc2.bias": 0.1 * torch.randn(1, generator=g)}
+    bags = [synth.make_bag(case["kind"], n, seed + 10 + i) for i, n in enumerate(case["ns"])]
+    G = [torch.randn(1, 512, generator=g) for _ in bags]
+    return {"Q": Q, "pool": pool, "bags": bags, "G": G, "W": ck["W"], "b": ck["b"]}

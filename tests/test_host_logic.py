@@ -73,8 +73,7 @@ def test_reference_api_surface():
     assert net.forward_text_only().shape == (4, 512)
     assert callable(enc.visual_adapter) and enc.visual_adapter(torch.zeros(1, 3, 512)).shape == (1, 3, 512)
     assert float(enc.query_div_loss()) >= 0
-    for bad in (dict(use_feat_proj=True), dict(gated_query=True), dict(query_pooling="max"), dict(pred_head="Identity"),
-                dict(dim_in=1024)):
+    for bad in (dict(use_feat_proj=True), dict(dim_in=1024), dict(num_query=17)):
         from vlsa_b200.model import VLFAN
         kw = dict(dim_in=512, use_feat_proj=False, num_query=4)
         kw.update(bad)
@@ -83,6 +82,43 @@ def test_reference_api_surface():
     from vlsa_b200.model import load_model
     with pytest.raises(NotImplementedError):
         load_model("TransMIL")
+
+
+def test_vlfan_variants_keep_reference_parameters_and_fail_loudly_on_cpu():
+    """gated_query / query_pooling / pred_head variants construct with the reference's parameter names
+    and shapes (model/deepmil.py:89-118, model/layers.py:85-155); their pooled features come from the CUDA kernels, so
+    a CPU bag raises instead of falling back."""
+    from vlsa_b200.model import VLFAN
+    from vlsa_b200.model.prompt_adapter import PromptAdapter
+    kw = dict(dim_in=512, dim_hid=256, use_feat_proj=False, num_query=6)
+    enc = VLFAN(gated_query=True, query_pooling="gated_attention", **kw)
+    keys = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert keys == {"Q": (7, 512), "query_pooling.fc1.0.weight": (256, 512), "query_pooling.fc1.0.bias": (256,),
+                    "query_pooling.score.0.weight": (256, 512), "query_pooling.score.0.bias": (256,),
+                    "query_pooling.fc2.weight": (1, 256), "query_pooling.fc2.bias": (1,),
+                    "visual_adapter.weight": (512, 512), "visual_adapter.bias": (512,)}
+    assert not enc.fused_tail and float(enc.query_div_loss()) >= 0
+    Qd, prenorm = enc.query_directions()
+    assert prenorm and Qd.shape == (6, 512)
+    enc = VLFAN(query_pooling="attention", pred_head="Identity", **kw)
+    assert set(enc.state_dict()) == {"Q", "query_pooling.attention.0.weight", "query_pooling.attention.0.bias",
+                                     "query_pooling.attention.2.weight", "query_pooling.attention.2.bias"}
+    enc = VLFAN(query_pooling="weight", **kw)
+    assert tuple(enc.state_dict()["query_pooling"].shape) == (1, 6)
+    pooled, ext = enc.forward_query_pooling(torch.randn(2, 6, 512))
+    assert pooled.shape == (2, 512) and ext is None
+    assert VLFAN(query_pooling="max", **kw).forward_query_pooling(torch.ones(1, 6, 512))[0].shape == (1, 512)
+    assert VLFAN(**kw).fused_tail
+    with pytest.raises((ValueError, RuntimeError)):
+        enc(torch.randn(1, 10, 512))                                   # CPU tensor: no fallback
+    # gated Text query: P + 1 rows, the last one from the negative prompt (prompt_adapter.py:73-81,127-134)
+    qnet = PromptAdapter(None, method="TaskRes", num_prompts=6, pretrained_prompt_features=torch.randn(6, 512),
+                         load_negative_prompts=True, pretrained_neg_prompt_features=torch.randn(3, 512))
+    assert qnet().shape == (7, 512) and qnet.get_raw_prompt_features().shape == (7, 512)
+    assert set(qnet.state_dict()) == {"residual_features", "neg_residual_features"}
+    with pytest.raises(RuntimeError):
+        PromptAdapter(None, method="TaskRes", num_prompts=6, pretrained_prompt_features=torch.randn(6, 512),
+                      load_negative_prompts=True)
 
 
 def test_no_cpu_fallback():

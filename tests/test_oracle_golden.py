@@ -93,3 +93,46 @@ def test_decoupled_identity(real_bag, ckpt_params):
     # identical up to the bias term handling: A rows sum to 1 so b passes through the mean
     np.testing.assert_allclose(probs.numpy(), probs_2.numpy(), atol=1e-10)
     np.testing.assert_allclose(A.sum(dim=1).numpy(), np.ones(12), atol=1e-12)
+
+
+# ---- VLFAN variants ----------------------------------------------------------------------------
+from golden_util import VARIANT_CASES, variant_inputs, variant_name  # noqa: E402
+
+
+def oracle_variant(case, inp, dtype):
+    """The oracle's variant forward over the bags of a case + autograd of sum(f * G): -> dict like the golden record."""
+    c = lambda z: z.to(dtype)
+    Q = c(inp["Q"]).clone().requires_grad_(True)
+    pool = {k: c(v).clone().requires_grad_(True) for k, v in inp["pool"].items()}
+    b = c(inp["b"]).clone().requires_grad_(True)
+    scale = torch.tensor(O.coattn_scale(), dtype=dtype)
+    fs, loss = [], 0
+    for X, G in zip(inp["bags"], inp["G"]):
+        f, A, ext, _ = O.vlfan_forward_variant(c(X).unsqueeze(0), Q, c(inp["W"]), b, case["gated"], case["pooling"],
+                                               pool, case["pred_head"], scale=scale)
+        fs.append(f.detach())
+        loss = loss + (f * c(G)).sum()
+    loss.backward()
+    rec = {"f": torch.cat(fs, 0).numpy(), "d_Q": Q.grad.numpy(), "attn_head": A[0, :, :64].numpy()}
+    if ext is not None:
+        rec["pool_scores"] = ext.numpy()
+    if case["pooling"] == "weight":
+        rec["d_pool_weight"] = pool["weight"].grad.numpy()
+    elif case["pooling"] in ("attention", "gated_attention"):
+        rec["d_pool_last"] = pool["attention.2.weight" if case["pooling"] == "attention" else "fc2.weight"].grad.numpy()
+    if case["pred_head"] != "Identity":
+        rec["d_b"] = b.grad.numpy()
+    return rec
+
+
+@pytest.mark.parametrize("case", VARIANT_CASES, ids=variant_name)
+def test_variant_oracle_matches_reference(case):
+    gold = load_case(variant_name(case))
+    inp = variant_inputs(case)
+    np.testing.assert_allclose([x.double().sum().item() for x in inp["bags"]], gold["x_sum"], rtol=1e-12)
+    for tag, dtype, tol in (("f32", torch.float32, 2e-5), ("f64", torch.float64, 1e-11)):
+        rec = oracle_variant(case, inp, dtype)
+        for key, val in rec.items():
+            ref = gold[f"{key}_{tag}"]
+            np.testing.assert_allclose(val, ref, rtol=10 * tol, atol=tol * max(1.0, float(np.abs(ref).max())),
+                                       err_msg=f"{key}_{tag}")

@@ -34,7 +34,12 @@ _SIGNATURES = {
                                c_f32p, c_f32p, c_f32p,
                                C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
-    "vlsa_attn_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_float, c_f32p, c_f32p,
+    "vlsa_agg_pooled_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+                                      C.c_int, C.c_float, C.c_void_p, C.c_size_t, c_f32p, c_f32p, C.c_void_p]),
+    "vlsa_agg_pooled_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+                                      C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, c_f32p,
+                                      C.c_void_p]),
+    "vlsa_attn_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p,
                                 C.c_void_p]),
     "vlsa_interp_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p,
                                   c_f32p, c_f32p, C.c_void_p]),

@@ -19,13 +19,16 @@ struct AggParams {
     int chunk_rows;             // rows per chunk (multiple of TN)
     int total_chunks;
     const float* Q;             // [P, D] un-normalised queries
+    int q_prenorm;              // 1: rows of Q are the score directions as they are (gated queries: the difference
+                                //    of two unit vectors, deepmil.py:192-195); 0: normalise them (deepmil.py:187)
     float scale;                // exp(fp32(log 100)), deepmil.py:122
     // forward outputs: per-chunk partials
     float* part_m;              // [chunks, P]
     float* part_l;              // [chunks, P]
     float* part_O;              // [chunks, P, D]  (backward: partial dQn)
     // backward inputs (per bag)
-    const float* dv;            // [B, D]   d loss / d pooled  (already divided by P inside the kernel)
+    const float* dv;            // MODE 1: [B, D] d loss / d pooled (divided by P inside the kernel)
+                                // MODE 2: [B, P, D] d loss / d O_p, one gradient row per prototype
     const float* ml;            // [B, P, 2] (max, sum) from forward
     const float* delta;         // [B, P]   dO_p . O_p
 };
@@ -37,15 +40,18 @@ struct AggParams {
 #define VLSA_AGG_STAGES 2
 #endif
 
-template <int P, bool BWD, typename XT>
+// MODE 0: forward.  MODE 1: backward of the mean-pooled path (one gradient row dv / P shared by all prototypes).
+// MODE 2: backward with a gradient row per prototype (any pooling over the P outputs: max, weight, attention).
+template <int P, int MODE, typename XT>
 struct AggCfg {
+    static constexpr bool BWD = MODE != 0, GEN = MODE == 2;
     static constexpr int D = VLSA_D;
     static constexpr int NW = VLSA_AGG_WARPS;          // warps per CTA (several CTAs share an SM)
     static constexpr int THREADS = 32 * NW;
     static constexpr int TN = 4 * NW;                  // rows per tile (4 rows per warp in phase A)
     static constexpr int CPT = D / THREADS;            // feature columns per thread in phase B
     static constexpr int STAGES = VLSA_AGG_STAGES;
-    static constexpr int NQ = BWD ? P + 1 : P;         // query rows resident in smem
+    static constexpr int NQ = GEN ? 2 * P : (BWD ? P + 1 : P);   // query (+ gradient) rows resident in smem
     static constexpr int NRED = NQ + 1;                // + sum of squares
     static constexpr int PP = (P + 3) & ~3;            // weights per row, float4-padded
     static constexpr int NV = 4 * NRED;                // values reduced per warp per tile
@@ -70,9 +76,10 @@ __device__ __forceinline__ void chunk_info(const AggParams& p, int c, int& bag, 
     r1 = r0 + p.chunk_rows < b1 ? r0 + p.chunk_rows : b1;
 }
 
-template <int P, bool BWD, typename XT>
-__global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(const AggParams prm) {
-    using C = AggCfg<P, BWD, XT>;
+template <int P, int MODE, typename XT>
+__global__ void __launch_bounds__(AggCfg<P, MODE, XT>::THREADS) agg_simt_kernel(const AggParams prm) {
+    using C = AggCfg<P, MODE, XT>;
+    constexpr bool BWD = C::BWD, GEN = C::GEN;
     constexpr int D = C::D, TN = C::TN, STAGES = C::STAGES, NQ = C::NQ, NRED = C::NRED, PP = C::PP, NV = C::NV;
     constexpr int NW = C::NW, CPT = C::CPT;
     static_assert(TN <= 32 && (CPT == 2 || CPT == 4), "phase S maps rows to lanes; phase B loads 8 or 16 bytes");
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
         float ss = 0.f;
         for (int d = lane; d < D; d += 32) { const float v = __ldg(q + d); ss += v * v; }
         ss = warp_sum(ss);
-        const float inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+        const float inv = prm.q_prenorm ? 1.f : 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
         for (int d = lane; d < D; d += 32) qs[p * D + d] = __ldg(q + d) * inv;
     }
     if (tid < P) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_alpha[tid] = 0.f; }
@@ -131,12 +138,12 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
 #ifndef VLSA_SIMT_QREG_J_BWD
 #define VLSA_SIMT_QREG_J_BWD 2
 #endif
-    constexpr int QREG_J = (!BF16 && PACKED && P <= 4) ? (BWD ? VLSA_SIMT_QREG_J_BWD : VLSA_SIMT_QREG_J) : 0;
+    constexpr int QREG_J = (!BF16 && PACKED && P <= 4 && !GEN) ? (BWD ? VLSA_SIMT_QREG_J_BWD : VLSA_SIMT_QREG_J) : 0;
 #ifndef VLSA_SIMT_QREG_JB
 #define VLSA_SIMT_QREG_JB 2
 #endif
     // bf16 storage: a lane owns 8 consecutive columns per 256-column block, i.e. two float4 of every query row
-    constexpr int QREG_JB = (BF16 && PACKED && P <= 4) ? VLSA_SIMT_QREG_JB : 0;
+    constexpr int QREG_JB = (BF16 && PACKED && P <= 4 && !GEN) ? VLSA_SIMT_QREG_JB : 0;
     float4 qregb[QREG_JB > 0 ? QREG_JB * 2 * NQ : 1];
     auto load_qregb = [&](int q) {
 #pragma unroll
@@ -206,10 +213,14 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
         int bag; long long r0, r1;
         chunk_info(prm, c, bag, r0, r1);
         if (BWD) {
-            // per-bag operands: extra query row dv_b / P, saved (m, 1/l), delta_p = (dv . O_p) / P
+            // per-bag operands: extra query row(s) dv_b / P | dO_b, saved (m, 1/l), delta_p = (dv . O_p) / P | dO_p . O_p
             __syncthreads();
-            const float invP = 1.f / float(P);
-            for (int d = tid; d < D; d += C::THREADS) qs[P * D + d] = __ldg(prm.dv + size_t(bag) * D + d) * invP;
+            if (GEN) {
+                for (int i = tid; i < P * D; i += C::THREADS) qs[P * D + i] = __ldg(prm.dv + size_t(bag) * P * D + i);
+            } else {
+                const float invP = 1.f / float(P);
+                for (int d = tid; d < D; d += C::THREADS) qs[P * D + d] = __ldg(prm.dv + size_t(bag) * D + d) * invP;
+            }
             if (tid < P) {
                 s_m[tid] = __ldg(prm.ml + (size_t(bag) * P + tid) * 2);
                 s_l[tid] = 1.f / __ldg(prm.ml + (size_t(bag) * P + tid) * 2 + 1);
@@ -358,10 +369,11 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                 else tot = warp_reduce_transpose<(NV % 32 == 0 ? 32 : NV % 32)>(v);
                 const int idx = g * 32 + lane;
                 if (FUSED_W) {
-                    // lane i < NV: (row r = i / NRED, column q = i % NRED); q < P: Qn_q . x, q == P: (dv . x) / P, q == NQ: |x|^2
+                    // lane i < NV: (row r = i / NRED, column q = i % NRED); q < P: Qn_q . x, q == P (+ q): gradient row . x,
+                    // q == NQ: |x|^2
                     const int r = lane / NRED, q = lane % NRED;
                     const float ssv = __shfl_sync(0xffffffffu, tot, (r * NRED + NQ) & 31);
-                    const float uv = __shfl_sync(0xffffffffu, tot, (r * NRED + P) & 31);
+                    const float uv = __shfl_sync(0xffffffffu, tot, (r * NRED + P + (GEN && q < P ? q : 0)) & 31);
                     const int rowl = 4 * warp + r;
                     if (lane < NV && q < P) {
                         const float nrm = fmaxf(sqrtf(ssv), VLSA_NORM_EPS);
@@ -439,7 +451,7 @@ __global__ void __launch_bounds__(AggCfg<P, BWD, XT>::THREADS) agg_simt_kernel(c
                     if (lane == 0) { s_alpha[p] = a; s_m[p] = mn; }
                 } else {
                     const float a = expf(s - s_m[p]) * s_l[p];                 // A_pn (deepmil.py:198)
-                    const float u = red[rl * NRED + P];                         // (dv . x_n) / P
+                    const float u = red[rl * NRED + P + (GEN ? p : 0)];         // (dv . x_n) / P | dO_p . x_n
                     if (lane < TN) wt[lane * PP + p] = live ? prm.scale * a * (u - s_alpha[p]) / nrm : 0.f;
                 }
             }

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                 float ss = 0.f;
                 for (int d = lane; d < D; d += 32) { const float v = __ldg(prm.Q + size_t(p) * D + d); ss += v * v; }
                 ss = warp_sum(ss);
-                inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+                inv = prm.q_prenorm ? 1.f : 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
             }
             for (int d = lane; d < D; d += 32) qn[p * C::QPITCH + d] = p < P ? __ldg(prm.Q + size_t(p) * D + d) * inv : 0.f;
         }

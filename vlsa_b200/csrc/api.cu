@@ -119,10 +119,10 @@ static AggWorkspace carve(void* base, int total_chunks, int B, int P) {
     return w;
 }
 
-template <int P, bool BWD, typename XT>
+template <int P, int MODE, typename XT>
 static int launch_agg(const AggParams& prm, cudaStream_t st) {
-    using C = AggCfg<P, BWD, XT>;
-    auto kern = agg_simt_kernel<P, BWD, XT>;
+    using C = AggCfg<P, MODE, XT>;
+    auto kern = agg_simt_kernel<P, MODE, XT>;
     VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
     int occ = 1;
     VLSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM));
@@ -168,15 +168,15 @@ static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t
     if (agg_use_tc(P, x_dtype)) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, false, float>(prm, st);
-        else rc = launch_agg<kP, false, __nv_bfloat16>(prm, st);
+        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
+        else rc = launch_agg<kP, 0, __nv_bfloat16>(prm, st);
     });
     return rc;
 }
 
 extern "C" {
 
-int vlsa_version(void) { return 101; }
+int vlsa_version(void) { return 102; }
 
 int vlsa_debug_set_agg_variant(int variant) {
     if (variant < -1 || variant > 1) return VLSA_EINVAL;
@@ -339,8 +339,8 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
         if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {
-            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, true, float>(prm, st);
-            else rc = launch_agg<kP, true, __nv_bfloat16>(prm, st);
+            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 1, float>(prm, st);
+            else rc = launch_agg<kP, 1, __nv_bfloat16>(prm, st);
             if (rc) return rc;
         });
     }
@@ -356,8 +356,83 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     return 0;
 }
 
-int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, float coattn_scale, const float* ml,
-                  float* out_A, void* stream) {
+int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                        int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
+                        void* workspace, size_t workspace_bytes, float* out_ml, float* out_O, void* stream) {
+    if (B == 0) return 0;
+    if (!cu_rows || !chunk_start || !Q || !out_ml || !out_O) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
+        return VLSA_EINVAL;
+    if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (total_chunks > 0 && (!X || !workspace)) return VLSA_EINVAL;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
+    if (total_chunks > 0 && (base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes)
+        return VLSA_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AggParams prm{};
+    prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
+    prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
+    int rc = launch_agg_fwd(prm, P, x_dtype, st);
+    if (rc) return rc;
+    const int S = merge_fwd_splits(total_chunks, B, P);
+    if (S > 0) {
+        merge_fwd_split_kernel<<<dim3(S, P, B), 128, 0, st>>>(ws.part_m, ws.part_l, ws.part_O, chunk_start, P, S,
+                                                                ws.l2_m, ws.l2_l, ws.l2_O);
+        VLSA_CUDA(cudaGetLastError());
+    }
+    VLSA_DISPATCH_P(P, {
+        merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
+                                                                     S > 0 ? ws.l2_O : ws.part_O, chunk_start, S,
+                                                                     out_ml, out_O, nullptr);
+    });
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+                        int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
+                        const float* ml, const float* O, const float* d_O, void* workspace, size_t workspace_bytes,
+                        float* dQ, void* stream) {
+    if (!cu_rows || !chunk_start || !Q || !ml || !O || !d_O || !dQ || !workspace) return VLSA_EINVAL;
+    if (B < 1 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
+        return VLSA_EINVAL;
+    if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (total_chunks > 0 && !X) return VLSA_EINVAL;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    delta_gen_kernel<<<B, 256, 0, st>>>(d_O, O, P, ws.delta);
+    VLSA_CUDA(cudaGetLastError());
+    AggParams prm{};
+    prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
+    prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
+    prm.dv = d_O; prm.ml = ml; prm.delta = ws.delta;
+    int rc = 0;
+    VLSA_DISPATCH_P(P, {
+        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 2, float>(prm, st);
+        else rc = launch_agg<kP, 2, __nv_bfloat16>(prm, st);
+        if (rc) return rc;
+    });
+    const int Sb = merge_bwd_splits(total_chunks, P);
+    if (Sb > 0) {
+        merge_bwd_split_kernel<<<dim3(Sb, P), 128, 0, st>>>(ws.part_O, total_chunks, P, Sb, ws.l2_O);
+        VLSA_CUDA(cudaGetLastError());
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.l2_O, Sb, P, Q, dQ, q_prenorm);
+    } else {
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ, q_prenorm);
+    }
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, int q_prenorm, float coattn_scale,
+                  const float* ml, float* out_A, void* stream) {
     if (N == 0) return 0;
     if (!X || !Q || !out_A || N < 0 || P < 1 || P > VLSA_MAX_P) return VLSA_EINVAL;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -366,11 +441,11 @@ int vlsa_attn_fwd(const void* X, int x_dtype, int64_t N, const float* Q, int P, 
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
     const bool f32 = x_dtype == VLSA_DTYPE_F32;
     if (ml) {       // softmax over the N patches, normalisers from the forward
-        if (f32) row_cosine_kernel<float, 0><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A);
-        else row_cosine_kernel<__nv_bfloat16, 0><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A);
+        if (f32) row_cosine_kernel<float, 0><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A, q_prenorm);
+        else row_cosine_kernel<__nv_bfloat16, 0><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, ml, out_A, q_prenorm);
     } else {        // softmax over the P prototypes per patch
-        if (f32) row_cosine_kernel<float, 2><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A);
-        else row_cosine_kernel<__nv_bfloat16, 2><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A);
+        if (f32) row_cosine_kernel<float, 2><<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A, q_prenorm);
+        else row_cosine_kernel<__nv_bfloat16, 2><<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, Q, P, coattn_scale, nullptr, nullptr, out_A, q_prenorm);
     }
     VLSA_CUDA(cudaGetLastError());
     return 0;
@@ -431,12 +506,12 @@ int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, i
     if (x_dtype == VLSA_DTYPE_F32) {
         auto kern = row_cosine_kernel<float, 1>;
         VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kern<<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, T, R, 0.f, logit_scale, nullptr, patch_logits);
+        kern<<<grid, 256, smem, st>>>(static_cast<const float*>(X), N, T, R, 0.f, logit_scale, nullptr, patch_logits, 0);
     } else if (x_dtype == VLSA_DTYPE_BF16) {
         auto kern = row_cosine_kernel<__nv_bfloat16, 1>;
         VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         kern<<<grid, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(X), N, T, R, 0.f, logit_scale, nullptr,
-                                      patch_logits);
+                                      patch_logits, 0);
     } else {
         return VLSA_EUNSUPPORTED;
     }

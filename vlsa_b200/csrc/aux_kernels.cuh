@@ -36,14 +36,15 @@ __device__ __forceinline__ int slot_col(int lane, int i) {
 }
 
 // Normalise `nq` rows of `src` [nq, D] into shared memory `dst` (row-major), whole block cooperates.
-__device__ __forceinline__ void load_normalized_rows(const float* __restrict__ src, int nq, float* dst) {
+__device__ __forceinline__ void load_normalized_rows(const float* __restrict__ src, int nq, float* dst,
+                                                     bool prenorm = false) {
     constexpr int D = VLSA_D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int r = warp; r < nq; r += nw) {
         float ss = 0.f;
         for (int d = lane; d < D; d += 32) { const float v = __ldg(src + size_t(r) * D + d); ss += v * v; }
         ss = warp_sum(ss);
-        const float inv = 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+        const float inv = prenorm ? 1.f : 1.f / fmaxf(sqrtf(ss), VLSA_NORM_EPS);
         for (int d = lane; d < D; d += 32) dst[r * D + d] = __ldg(src + size_t(r) * D + d) * inv;
     }
 }
@@ -55,12 +56,13 @@ __device__ __forceinline__ void load_normalized_rows(const float* __restrict__ s
 template <typename XT, int MODE>
 __global__ void __launch_bounds__(256) row_cosine_kernel(const XT* __restrict__ X, long long N, const float* __restrict__ Qsrc,
                                                          int nq, float mult, const float* __restrict__ mult_log,
-                                                         const float* __restrict__ ml, float* __restrict__ out) {
+                                                         const float* __restrict__ ml, float* __restrict__ out,
+                                                         int q_prenorm = 0) {
     constexpr int D = VLSA_D;
     extern __shared__ __align__(16) float s_q[];            // [nq][D] + [32][nq+1] staging
     float* s_out = s_q + size_t(nq) * D;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    load_normalized_rows(Qsrc, nq, s_q);
+    load_normalized_rows(Qsrc, nq, s_q, q_prenorm != 0);
     __syncthreads();
     if (mult_log) mult = expf(*mult_log);
     const long long row0 = (long long)blockIdx.x * 32;

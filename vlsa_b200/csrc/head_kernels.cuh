@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict_
         if (out_O) out_O[(size_t(b) * P + p) * D + d] = op;
         vs += op;
     }
-    out_v[size_t(b) * D + d] = vs / float(P);               // torch.mean over P (deepmil.py:136)
+    if (out_v) out_v[size_t(b) * D + d] = vs / float(P);    // torch.mean over P (deepmil.py:136)
     if (blockIdx.y == 0 && tid < P) {
         out_ml[(size_t(b) * P + tid) * 2 + 0] = s_mx[tid];
         float lt = 0.f;
@@ -348,6 +348,20 @@ __global__ void __launch_bounds__(256) delta_kernel(const float* __restrict__ dv
     }
 }
 
+// delta[b][p] = dO[b][p] . O[b][p] for a gradient row per prototype (any pooling over the P outputs).  grid B.
+__global__ void __launch_bounds__(256) delta_gen_kernel(const float* __restrict__ dO, const float* __restrict__ O, int P,
+                                                        float* __restrict__ delta) {
+    constexpr int D = VLSA_D;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = warp; p < P; p += 8) {
+        const size_t at = (size_t(b) * P + p) * D;
+        float a = 0.f;
+        for (int k = lane; k < D; k += 32) a += dO[at + k] * O[at + k];
+        a = warp_sum(a);
+        if (lane == 0) delta[size_t(b) * P + p] = a;
+    }
+}
+
 // dTn[r] = ls * sum_b dlogits[b][r] g[b] ; dT[r] = (dTn - Tn (Tn.dTn)) / |T_r| ; block 0 also reduces dls.
 // grid R, 256 threads.
 __global__ void __launch_bounds__(256) text_bwd_kernel(const float* __restrict__ T, int R, const float* __restrict__ g,
@@ -381,10 +395,11 @@ __global__ void __launch_bounds__(256) text_bwd_kernel(const float* __restrict__
     }
 }
 
-// dQn[p] = sum over all chunks of the partials (fixed order); dQ[p] = (dQn - Qn (Qn.dQn)) / |Q_p|.
-// grid P, 512 threads.
+// dQn[p] = sum over all chunks of the partials (fixed order); dQ[p] = (dQn - Qn (Qn.dQn)) / |Q_p|, or dQn itself
+// when the rows of Q entered the scores as they are (prenorm).  grid P, 512 threads.
 __global__ void __launch_bounds__(512) merge_bwd_kernel(const float* __restrict__ part, int total_chunks, int P,
-                                                        const float* __restrict__ Q, float* __restrict__ dQ) {
+                                                        const float* __restrict__ Q, float* __restrict__ dQ,
+                                                        int prenorm = 0) {
     constexpr int D = VLSA_D;
     __shared__ float s_red[32];
     const int p = blockIdx.x, d = threadIdx.x;
@@ -398,6 +413,7 @@ __global__ void __launch_bounds__(512) merge_bwd_kernel(const float* __restrict_
     }
     for (; c < total_chunks; ++c) a0 += part[(size_t(c) * P + p) * D + d];
     const float dqn = (a0 + a1) + (a2 + a3);
+    if (prenorm) { dQ[size_t(p) * D + d] = dqn; return; }      // block-uniform
     const float q = Q[size_t(p) * D + d];
     const float qq = block_sum(q * q, s_red);
     const float inv = 1.f / fmaxf(sqrtf(qq), VLSA_NORM_EPS);

@@ -1,9 +1,14 @@
 """Vision end of VLSA on B200: ``VLFAN`` (language-guided aggregation), ``FeatMIL`` and ``logit_pooling``.
 
 Same constructor arguments, attributes, method names and state-dict keys as model/deepmil.py:16-215 of
-liupei101/VLSA; the arithmetic runs in libvlsa_b200.so (no PyTorch fallback).  Configurations of VLFAN that
-no shipped VLSA config enables (feat_proj, gated_query, query_pooling != 'mean', pred_head 'Identity')
-raise NotImplementedError instead of silently running something else.
+liupei101/VLSA; the arithmetic over the N patches runs in libvlsa_b200.so (no PyTorch fallback).
+
+Shipped configuration (mean over P -> Linear): everything up to the visual feature is one fused CUDA path
+(``ops.encode`` / ``ops.aggregate``).  Config-reachable variants that no shipped VLSA config enables —
+``gated_query``, ``query_pooling`` in {max, weight, attention, gated_attention}, ``pred_head='Identity'`` — share the
+same streaming kernels through ``ops.pooled`` (O [B,P,512] with a gradient row per prototype on the way back); only
+their P x 512 tail (the pooling modules below, state-dict compatible with model/layers.py:85-155) is torch ops on the
+GPU.  ``use_feat_proj=True`` (a Linear + LayerNorm over all N rows whose backward needs dX) raises NotImplementedError.
 """
 from __future__ import annotations
 
@@ -51,6 +56,40 @@ class FeatMIL(nn.Module):
         return self.network(X.squeeze(0))
 
 
+class Gated_Attention_Pooling(nn.Module):
+    """model/layers.py:85-123 (Ilse et al. 2018) over the P per-prototype features: [B, P, d] -> [B, d]."""
+
+    def __init__(self, in_dim, hid_dim, dropout=0.5):
+        super().__init__()
+        self.fc1 = nn.Sequential(nn.Linear(in_dim, hid_dim), nn.Tanh(), nn.Dropout(dropout))
+        self.score = nn.Sequential(nn.Linear(in_dim, hid_dim), nn.Sigmoid(), nn.Dropout(dropout))
+        self.fc2 = nn.Linear(hid_dim, 1)
+
+    def forward(self, x, ret_raw_attn=False):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        A_ = self.fc2(self.fc1(x).mul(self.score(x))).transpose(2, 1)      # [B, 1, P]
+        A = F.softmax(A_, dim=2)
+        out = torch.matmul(A, x).squeeze(1)
+        return (out, A_.squeeze(1)) if ret_raw_attn else (out, A.squeeze(1))
+
+
+class Attention_Pooling(nn.Module):
+    """model/layers.py:126-155: [B, P, d] -> [B, d] and the RAW attention logits [B, P] (ret_raw_attn defaults True)."""
+
+    def __init__(self, in_dim=1024, hid_dim=512):
+        super().__init__()
+        self.attention = nn.Sequential(nn.Linear(in_dim, hid_dim), nn.Tanh(), nn.Linear(hid_dim, 1))
+
+    def forward(self, x, ret_raw_attn=True):
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        A_ = self.attention(x).transpose(2, 1)                              # [B, 1, P]
+        attn = F.softmax(A_, dim=2)
+        out = torch.matmul(attn, x).squeeze(1)
+        return (out, A_.squeeze(1)) if ret_raw_attn else (out, attn.squeeze(1))
+
+
 class VLFAN(nn.Module):
     def __init__(self, dim_in=1024, dim_hid=256, use_feat_proj=True, drop_rate=0.25, query="Parameter", num_query=10,
                  gated_query=False, query_pooling="mean", pred_head="default", dim_reduction=4, keep_ratio=0.8,
@@ -61,14 +100,8 @@ class VLFAN(nn.Module):
         if use_feat_proj:
             raise NotImplementedError("use_feat_proj=True (Feat_Projecter) is not on the accelerated path "
                                       "(cfg_vlsa_conch.yaml:49 sets it False)")
-        if gated_query:
-            raise NotImplementedError("gated_query=True is not on the accelerated path")
-        if query_pooling != "mean":
-            raise NotImplementedError(f"query_pooling={query_pooling!r}: only 'mean' is on the accelerated path "
-                                      "(cfg_vlsa_conch.yaml:58)")
-        if pred_head == "Identity":
-            raise NotImplementedError("pred_head='Identity' is not on the accelerated path")
         assert query in ["Parameter", "Text"]
+        assert query_pooling in ["mean", "max", "weight", "attention", "gated_attention"]
         if not (1 <= num_query <= ops.MAX_P):
             raise NotImplementedError(f"num_query must be in 1..{ops.MAX_P}, got {num_query}")
         self._pos_gated_query = -1
@@ -79,10 +112,17 @@ class VLFAN(nn.Module):
         if self.query_type != "Parameter":
             self.Q = None                                   # call reset_query later (deepmil.py:94-96)
         else:
-            self.Q = nn.Parameter(torch.randn(num_query, dim_in))
-        self.query_pooling = query_pooling
+            self.Q = nn.Parameter(torch.randn(num_query + 1 if gated_query else num_query, dim_in))
+        if query_pooling == "attention":                    # deepmil.py:102-109
+            self.query_pooling = Attention_Pooling(dim_in, dim_hid)
+        elif query_pooling == "gated_attention":
+            self.query_pooling = Gated_Attention_Pooling(dim_in, dim_hid, dropout=drop_rate)
+        elif query_pooling == "weight":
+            self.query_pooling = nn.Parameter(torch.randn(1, num_query))
+        else:
+            self.query_pooling = query_pooling
         self.pred_head = pred_head
-        self.visual_adapter = nn.Linear(dim_in, dim_in)
+        self.visual_adapter = nn.Identity() if pred_head == "Identity" else nn.Linear(dim_in, dim_in)
         self.use_custom_coattn = True
         self.coattn_logit_scale = torch.ones([]) * np.log(100)      # CPU scalar, not a buffer (deepmil.py:122)
 
@@ -95,7 +135,32 @@ class VLFAN(nn.Module):
         self.Q = query_network
 
     def forward_query_pooling(self, X):
-        return torch.mean(X, dim=1), None
+        """[B, P, C] -> [B, C] (deepmil.py:133-150); P x 512 work."""
+        if isinstance(self.query_pooling, str):
+            if self.query_pooling == "mean":
+                return torch.mean(X, dim=1), None
+            return torch.max(X, dim=1)[0], None
+        if callable(self.query_pooling):
+            return self.query_pooling(X)
+        weight = F.softmax(self.query_pooling, dim=-1).unsqueeze(0)         # [1, 1, P]
+        return torch.matmul(weight, X).squeeze(1), None
+
+    @property
+    def fused_tail(self) -> bool:
+        """True for the shipped configuration: mean over P and the Linear adapter run inside the CUDA path."""
+        return (not self.gated_query and isinstance(self.query_pooling, str) and self.query_pooling == "mean"
+                and isinstance(self.visual_adapter, nn.Linear))
+
+    def query_directions(self):
+        """(rows that enter the scores, prenorm flag).  Gated query (deepmil.py:192-195): A_[:, :-1] - A_[:, -1:] is
+        linear in the normalised query, so the P + 1 unit rows collapse to P difference rows used as they are."""
+        Q = self.get_query()
+        if not self.gated_query:
+            return Q, False
+        assert self._pos_gated_query == -1, "The gated query is placed at the end by default."
+        assert Q.shape[0] == self.num_query + 1, f"Query number is expected to be {self.num_query + 1}."
+        Qn = F.normalize(Q, dim=-1)
+        return Qn[:-1] - Qn[-1:], True
 
     def get_query(self):
         assert self.Q is not None, f"You have to call `reset_query` to reset query for query_type ({self.query_type})."
@@ -104,26 +169,46 @@ class VLFAN(nn.Module):
     def query_div_loss(self, last_div=True, **kws):
         Q = self.get_query()
         norm_Q = F.normalize(Q, dim=-1)
-        sim = norm_Q @ norm_Q.T
-        sim = sim[~torch.eye(len(Q), dtype=torch.bool, device=sim.device)]
+        if len(Q) == self.num_query + 1 and last_div:           # deepmil.py:160-162: the gate row against the rest
+            sim = norm_Q[-1:] @ norm_Q[:-1].T
+        else:
+            sim = norm_Q @ norm_Q.T
+            sim = sim[~torch.eye(len(Q), dtype=torch.bool, device=sim.device)]
         return sim.abs().mean()
 
     # ---- fused path ----------------------------------------------------------------------------
     def encode_packed(self, X: torch.Tensor, plan: "ops.BagPlan"):
         """Packed bags [total_rows, D] -> visual features f [B, D] (differentiable w.r.t. Q, W, b)."""
-        Q = self.get_query()
-        f, ml = ops.encode(X, plan, Q, self.visual_adapter.weight, self.visual_adapter.bias,
-                           float(self.get_coattn_logit_scale()))
+        if self.fused_tail:
+            f, ml = ops.encode(X, plan, self.get_query(), self.visual_adapter.weight, self.visual_adapter.bias,
+                               float(self.get_coattn_logit_scale()))
+            return f, ml
+        f, ml, _ = self.encode_packed_ext(X, plan)
         return f, ml
+
+    def encode_packed_ext(self, X: torch.Tensor, plan: "ops.BagPlan"):
+        """Variant tail: streaming kernels -> O [B, P, D] -> pooling over P -> adapter.  Returns (f, ml, pooling
+        scores or None)."""
+        Qd, prenorm = self.query_directions()
+        O, ml = ops.pooled(X, plan, Qd, prenorm, float(self.get_coattn_logit_scale()))
+        pooled_out, pooled_ext = self.forward_query_pooling(O)
+        return self.visual_adapter(pooled_out), ml, pooled_ext
 
     def forward(self, X, ret_with_attn=False):
         """X [1, N, C] -> visual_features [1, C] (and A [1, P, N] detached), deepmil.py:170-215."""
         assert X.shape[0] == 1
         Xp = X[0].contiguous()
         plan = ops.make_plan([Xp.shape[0]], Xp.device)
-        f, ml = self.encode_packed(Xp, plan)
+        if self.fused_tail:
+            f, ml = self.encode_packed(Xp, plan)
+            pooled_ext = None
+        else:
+            f, ml, pooled_ext = self.encode_packed_ext(Xp, plan)
         if ret_with_attn:
-            A = ops.attention_scores(Xp, self.get_query().detach().contiguous(), ml[0],
-                                     float(self.get_coattn_logit_scale()))
-            return f, A.unsqueeze(0)
+            Qd, prenorm = self.query_directions()
+            A = ops.attention_scores(Xp, Qd.detach().contiguous(), ml[0], float(self.get_coattn_logit_scale()),
+                                     q_prenorm=prenorm).unsqueeze(0)
+            if pooled_ext is not None:
+                return f, (A, pooled_ext.detach())                  # deepmil.py:208-209
+            return f, A
         return f

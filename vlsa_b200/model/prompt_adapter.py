@@ -14,14 +14,16 @@ import torch.nn as nn
 class PromptAdapter(nn.Module):
     def __init__(self, prompt_encoder=None, tokenizer=None, method: str = "default", num_prompts: int = 4,
                  pretrained_prompt_features: torch.Tensor | None = None, res_ratio: float = 0.5,
-                 load_negative_prompts: bool = False, **kwargs) -> None:
+                 load_negative_prompts: bool = False, pretrained_neg_prompt_features: torch.Tensor | None = None,
+                 **kwargs) -> None:
         super().__init__()
         assert method in ["default", "FC", "Adapter", "TaskRes"]
         if method in ("FC", "Adapter"):
             raise NotImplementedError(f"PromptAdapter method {method!r} is outside the accelerated path "
                                       "(every shipped VLSA config uses TaskRes for the query and 'default' for ranks)")
-        if load_negative_prompts:
-            raise NotImplementedError("gated_query / negative prompts are not part of the accelerated path")
+        if load_negative_prompts and pretrained_neg_prompt_features is None:
+            raise RuntimeError("gated query: pass `pretrained_neg_prompt_features` ([1, 512], the mean encoding of the "
+                               "negative texts, prompt_adapter.py:73-81)")
         if pretrained_prompt_features is None:
             raise RuntimeError("vlsa_b200 does not run the CONCH text tower: pass `pretrained_prompt_features` "
                                "([num_prompts, 512], the encoded prototype sentences)")
@@ -32,14 +34,25 @@ class PromptAdapter(nn.Module):
         if method == "TaskRes":
             # prompt_adapter.py:94 — randn init, res_ratio 0.5
             self.residual_features = nn.Parameter(torch.randn(num_prompts, self.prompt_features.shape[-1]))
-            self.neg_residual_features = None
+            self.neg_residual_features = nn.Parameter(torch.randn(1, self.prompt_features.shape[-1])) \
+                if load_negative_prompts else None                                 # prompt_adapter.py:95-99
             self.res_ratio = res_ratio
+        if load_negative_prompts:
+            neg = pretrained_neg_prompt_features.detach().clone().float().reshape(-1, self.prompt_features.shape[-1])
+            self.register_buffer("neg_prompt_features", neg.mean(0, keepdim=True), persistent=False)
 
     def get_raw_prompt_features(self):
-        return self.prompt_features.clone()
+        raw = self.prompt_features.clone()
+        if hasattr(self, "neg_prompt_features"):
+            raw = torch.cat([raw, self.neg_prompt_features.clone()], dim=0)        # [P + 1, d]
+        return raw
 
     def forward(self):
         prompt_features = self.prompt_features.clone()
         if self.method == "TaskRes":
-            return self.res_ratio * self.residual_features + prompt_features      # prompt_adapter.py:125-126
+            text_features = self.res_ratio * self.residual_features + prompt_features      # prompt_adapter.py:125-126
+            if hasattr(self, "neg_prompt_features"):                                       # prompt_adapter.py:127-134
+                neg = self.res_ratio * self.neg_residual_features + self.neg_prompt_features.clone()
+                text_features = torch.cat([text_features, neg], dim=0)                    # [P + 1, d]
+            return text_features
         return prompt_features

@@ -48,7 +48,8 @@ class VLSA(nn.Module):
                               if k.startswith("query_text")}                         # model/vlsa.py:82-87
             query_text_cfg.update(num_prompts=image_encoder_cfg["num_query"],
                                   load_negative_prompts=image_encoder_cfg.get("gated_query", False),
-                                  pretrained_prompt_features=query_prompt_features)
+                                  pretrained_prompt_features=query_prompt_features,
+                                  pretrained_neg_prompt_features=kwargs.get("query_neg_prompt_features"))
             for drop in ("load_path", "load_idx"):
                 query_text_cfg.pop(drop, None)               # prototype sentences are encoded outside
             self.mil_encoder.reset_query(PromptAdapter(None, **query_text_cfg))
@@ -103,6 +104,14 @@ class VLSA(nn.Module):
     # ---- batched entry -------------------------------------------------------------
     def _fused(self, Xp, plan, text_features):
         enc = self.mil_encoder
+        if not enc.fused_tail:
+            # VLFAN variants: streaming kernels -> O [B,P,512]; pooling over P, adapter and the cosine
+            # head (model/vlsa.py:186-192) are B x 512 torch ops
+            f, ml = enc.encode_packed(Xp, plan)
+            Tn = torch.nn.functional.normalize(text_features, dim=-1)
+            g = torch.nn.functional.normalize(f, dim=-1)
+            logits = self.logit_scale.exp() * g @ Tn.t()
+            return logits, g, Tn, torch.softmax(logits.detach(), dim=-1), ml
         return ops.aggregate(Xp, plan, enc.get_query(), enc.visual_adapter.weight, enc.visual_adapter.bias,
                              text_features, self.logit_scale, float(enc.get_coattn_logit_scale()))
 

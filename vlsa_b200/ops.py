@@ -261,6 +261,61 @@ class _EncodeFn(torch.autograd.Function):
         return None, None, dQ, dW, db, None
 
 
+class _PooledFn(torch.autograd.Function):
+    """Per-prototype pooled features O [B, P, D] (deepmil.py:187-200) for the VLFAN variants whose tail is not
+    "mean over P -> Linear".  Differentiable w.r.t. the query directions; the gradient d_O may be anything."""
+
+    @staticmethod
+    def forward(ctx, X, plan, Q, q_prenorm, scale):
+        Qc = Q.detach().contiguous()
+        B, P = plan.num_bags, Qc.shape[0]
+        if X.dim() != 2 or X.shape[1] != D_FEAT or X.shape[0] != plan.total_rows:
+            raise ValueError(f"packed X must be [{plan.total_rows}, {D_FEAT}], got {tuple(X.shape)}")
+        if not (1 <= P <= MAX_P):
+            raise ValueError(f"num_query P={P} outside 1..{MAX_P}")
+        _check_cuda(X, "X", None)
+        _check_cuda(Qc, "Q")
+        if Qc.shape[1] != D_FEAT:
+            raise ValueError("Q must be [P, 512]")
+        f32 = dict(dtype=torch.float32, device=X.device)
+        ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
+        ws = _workspace(plan, P, X.device)
+        sc = coattn_scale() if scale is None else float(scale)
+        rc = _lib.lib().vlsa_agg_pooled_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+                                            plan.chunk_start.data_ptr(), B, plan.chunk_rows, plan.total_chunks,
+                                            Qc.data_ptr(), P, int(bool(q_prenorm)), sc, ws.data_ptr(), ws.numel(),
+                                            ml.data_ptr(), O.data_ptr(), _stream())
+        _lib.check(rc, "vlsa_agg_pooled_fwd")
+        ctx.plan, ctx.scale, ctx.ws, ctx.prenorm = plan, sc, ws, int(bool(q_prenorm))
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(X, Qc, ml, O)
+        ctx.mark_non_differentiable(ml)
+        return O, ml
+
+    @staticmethod
+    def backward(ctx, d_O, _d_ml):
+        if d_O is None:
+            return (None,) * 5
+        X, Q, ml, O = ctx.saved_tensors
+        plan = ctx.plan
+        P = Q.shape[0]
+        d_O = d_O.contiguous().float()
+        dQ = torch.empty(P, D_FEAT, dtype=torch.float32, device=X.device)
+        rc = _lib.lib().vlsa_agg_pooled_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+                                            plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
+                                            plan.total_chunks, Q.data_ptr(), P, ctx.prenorm, ctx.scale, ml.data_ptr(),
+                                            O.data_ptr(), d_O.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                            dQ.data_ptr(), _stream())
+        _lib.check(rc, "vlsa_agg_pooled_bwd")
+        return None, None, dQ, None, None
+
+
+def pooled(X, plan: BagPlan, Q, q_prenorm: bool = False, scale: float | None = None):
+    """Packed bags -> (O [B,P,D], ml [B,P,2]): the P softmax-weighted sums of every bag, before any pooling over P.
+    ``q_prenorm=True``: the rows of Q are used as score directions without normalisation (gated queries)."""
+    return _PooledFn.apply(X, plan, Q, q_prenorm, scale)
+
+
 def encode(X, plan: BagPlan, Q, W, bias, scale: float | None = None):
     """Fused VLFAN forward on a packed batch: returns (f [B,D], ml [B,P,2])."""
     return _EncodeFn.apply(X, plan, Q, W, bias, scale)
@@ -271,7 +326,7 @@ def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None 
     return _AggregateFn.apply(X, plan, Q, W, bias, T, logit_scale, scale)
 
 
-def attention_scores(X, Q, ml, scale: float | None = None):
+def attention_scores(X, Q, ml, scale: float | None = None, q_prenorm: bool = False):
     """A [P,N] for ONE bag.  With ``ml`` (the (max, sum) saved by the forward): softmax over the N patches of
     scale * cos(Q, X), the ``ret_with_attn=True`` output of VLFAN.forward (model/deepmil.py:206-213).  With
     ``ml=None``: softmax over the P prototypes per patch (utils/model_inference.py:104-113, axis_softmax='L')."""
@@ -282,7 +337,7 @@ def attention_scores(X, Q, ml, scale: float | None = None):
         _check_cuda(ml, "ml")
     N, P = X.shape[0], Q.shape[0]
     A = torch.empty(P, N, dtype=torch.float32, device=X.device)
-    rc = L.vlsa_attn_fwd(X.data_ptr(), _x_dtype_code(X), N, Q.data_ptr(), P,
+    rc = L.vlsa_attn_fwd(X.data_ptr(), _x_dtype_code(X), N, Q.data_ptr(), P, int(bool(q_prenorm)),
                          coattn_scale() if scale is None else float(scale), _ptr(ml), A.data_ptr(), _stream())
     _lib.check(rc, "vlsa_attn_fwd")
     return A
