@@ -72,9 +72,11 @@ size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P);
  * X is read exactly once.  out_ml / out_O / out_v / out_f are what vlsa_agg_bwd needs later
  * (out_O may be NULL when no backward follows).  out_if and out_Tn may be NULL.
  * Encoder-only use (VLFAN.forward alone, deepmil.py:170-215): T = NULL stops after f; out_g, out_logits,
- * out_if, out_Tn are then ignored. */
+ * out_if, out_Tn are then ignored.
+ * q_prenorm = 0 everywhere except the gated query (deepmil.py:192-195), which passes the P difference rows
+ * Qn_p - Qn_gate with q_prenorm = 1: they enter the scores as they are (see vlsa_agg_pooled_fwd). */
 int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
-                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
                  float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream);
@@ -94,9 +96,10 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, con
  * gradient; d_g [B,D] (gradient w.r.t. the returned image features) and d_f [B,D] (gradient w.r.t. the
  * adapter output) may be NULL.  Encoder-only use (VLFAN.forward alone): T = NULL, then d_f is required and
  * f, g, logits, d_logits, dT, dlogit_scale are ignored.
- * Outputs are overwritten (not accumulated): dQ [P,D], dW [D,D], db [D], dT [R,D], dlogit_scale [1]. */
+ * Outputs are overwritten (not accumulated): dQ [P,D], dW [D,D], db [D], dT [R,D], dlogit_scale [1].
+ * With q_prenorm = 1, dQ is the gradient w.r.t. the rows as passed (no normalisation Jacobian). */
 int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
-                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
                  const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
@@ -121,6 +124,15 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
                         int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
                         const float* ml, const float* O, const float* d_O, void* workspace, size_t workspace_bytes,
                         float* dQ, void* stream);
+
+/* Gradient of vlsa_agg_pooled_fwd w.r.t. the patch rows themselves, for callers that train a module in front of the
+ * aggregation — VLFAN's `feat_proj` (Linear + LayerNorm over every row, model/layers.py:65-82, deepmil.py:176-179):
+ *   dx_n = sum_p ( A_pn d_O_p + (scale dS_pn / |x_n|) qdir_p ) - (sum_p dS_pn s_pn) x_n / |x_n|^2.
+ * X [total_rows, D] fp32 (the projected rows), cu_rows [B+1] device, max_rows = the longest bag.  out_dX [total_rows, D].
+ * One read of X, one write of dX. */
+int vlsa_agg_pooled_bwd_dx(const float* X, const int64_t* cu_rows, int B, int64_t max_rows, const float* Q, int P,
+                           int q_prenorm, float coattn_scale, const float* ml, const float* O, const float* d_O,
+                           float* out_dX, void* stream);
 
 /* Attention read-out of ONE bag (`ret_with_attn=True`, model/deepmil.py:206-213; utils/model_inference.py:104-113).
  * ml != NULL: A[p][n] = exp(scale * cos(Q_p, x_n) - ml[p][0]) / ml[p][1], the softmax over the N patches with the

@@ -94,11 +94,16 @@ def query_pooling(out, method: str, pool_params=None):
 
 
 def vlfan_forward_variant(X, Q, W, b, gated_query: bool = False, pooling: str = "mean", pool_params=None,
-                          pred_head: str = "default", scale: torch.Tensor | None = None):
+                          pred_head: str = "default", scale: torch.Tensor | None = None, proj_params=None):
     """model/deepmil.py:170-215 with the config-reachable switches no shipped VLSA config enables:
     gated_query (Q has P+1 rows, the last one is the gate, deepmil.py:192-195), query_pooling (deepmil.py:133-150),
-    pred_head 'Identity' (deepmil.py:111-114).  Returns (f [1,D], A [1,P,N], pooling scores | None, out [1,P,D])."""
+    pred_head 'Identity' (deepmil.py:111-114), use_feat_proj (``proj_params``: the Feat_Projecter state dict,
+    model/layers.py:65-82, deepmil.py:176-179).  Returns (f [1,D], A [1,P,N], pooling scores | None, out [1,P,D])."""
     assert X.shape[0] == 1                                   # deepmil.py:175
+    if proj_params is not None:
+        h = F.linear(X.view(-1, X.shape[2]), proj_params["projecter.0.weight"], proj_params["projecter.0.bias"])
+        h = F.layer_norm(h, (h.shape[-1],), proj_params["projecter.1.weight"], proj_params["projecter.1.bias"])
+        X = h.view(1, -1, h.shape[-1])                       # layers.py:74-79
     if scale is None:
         scale = (torch.ones([]) * np.log(100)).exp()         # deepmil.py:122
     scale = scale.to(X.dtype)

@@ -39,7 +39,7 @@ def main():
         P, hid = case["P"], case["hid"]
         rec = {}
         for tag, dtype in (("f32", torch.float32), ("f64", torch.float64)):
-            enc = deepmil.VLFAN(dim_in=512, dim_hid=hid, use_feat_proj=False, drop_rate=0.25, query="Parameter",
+            enc = deepmil.VLFAN(dim_in=512, dim_hid=hid, use_feat_proj=bool(case.get("feat_proj")), drop_rate=0.25, query="Parameter",
                                 num_query=P, gated_query=case["gated"], query_pooling=case["pooling"],
                                 pred_head=case["pred_head"])
             enc.eval()
@@ -52,6 +52,8 @@ def main():
                     enc.query_pooling.copy_(inp["pool"]["weight"])
                 elif case["pooling"] in ("attention", "gated_attention"):
                     enc.query_pooling.load_state_dict(inp["pool"])
+                if case.get("feat_proj"):
+                    enc.feat_proj.load_state_dict(inp["proj"])
             enc.to(dtype)
             enc.coattn_logit_scale = enc.coattn_logit_scale.exp().to(dtype).log()   # keep the fp32 value of exp(log 100)
             fs = []
@@ -74,6 +76,11 @@ def main():
                 rec[f"d_pool_last_{tag}"] = dict(enc.query_pooling.named_parameters())[last].grad.numpy()
             if case["pred_head"] != "Identity":
                 rec[f"d_b_{tag}"] = enc.visual_adapter.bias.grad.numpy()
+            if case.get("feat_proj"):
+                pg = dict(enc.feat_proj.named_parameters())
+                rec[f"d_proj_w_rows_{tag}"] = pg["projecter.0.weight"].grad[:4].numpy()
+                rec[f"d_proj_w_fro_{tag}"] = pg["projecter.0.weight"].grad.double().norm().numpy()
+                rec[f"d_proj_ln_w_{tag}"] = pg["projecter.1.weight"].grad.numpy()
         name = variant_name(case)
         np.savez_compressed(os.path.join(HERE, name + ".npz"),
                             x_sum=np.array([x.double().sum().item() for x in inp["bags"]]), **rec)

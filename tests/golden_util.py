@@ -78,12 +78,16 @@ VARIANT_CASES = [
     dict(P=4, gated=False, pooling="mean", pred_head="Identity", hid=32, kind="g1", ns=(1000,), seed=31007),
     dict(P=3, gated=True, pooling="attention", pred_head="Identity", hid=32, kind="g1", ns=(257, 1), seed=31008),
     dict(P=16, gated=True, pooling="max", pred_head="default", hid=32, kind="g1", ns=(1500, 33), seed=31009),
+    dict(P=4, gated=False, pooling="mean", pred_head="default", hid=32, kind="g1", ns=(1000, 37), seed=31010, feat_proj=True),
+    dict(P=12, gated=True, pooling="mean", pred_head="default", hid=32, kind="g0", ns=(700, 1), seed=31011, feat_proj=True),
+    dict(P=6, gated=False, pooling="attention", pred_head="default", hid=32, kind="g1", ns=(513,), seed=31012, feat_proj=True),
 ]
 
 
 def variant_name(case):
-    return "variant_P{P}_{g}_{pooling}_{h}_{kind}".format(g="gated" if case["gated"] else "plain",
+    name = "variant_P{P}_{g}_{pooling}_{h}_{kind}".format(g="gated" if case["gated"] else "plain",
                                                           h="id" if case["pred_head"] == "Identity" else "lin", **case)
+    return name + ("_proj" if case.get("feat_proj") else "")
 
 
 def variant_inputs(case):
@@ -109,4 +113,10 @@ def variant_inputs(case):
                 "fc2.weight": torch.randn(1, hid, generator=g) / hid ** 0.5, "fc2.bias": 0.1 * torch.randn(1, generator=g)}
     bags = [synth.make_bag(case["kind"], n, seed + 10 + i) for i, n in enumerate(case["ns"])]
     G = [torch.randn(1, 512, generator=g) for _ in bags]
-    return {"Q": Q, "pool": pool, "bags": bags, "G": G, "W": ck["W"], "b": ck["b"]}
+    proj = None
+    if case.get("feat_proj"):               # Feat_Projecter (model/layers.py:65-82): Linear near the identity + LayerNorm
+        proj = {"projecter.0.weight": torch.eye(512) + 0.3 * torch.randn(512, 512, generator=g) / 512 ** 0.5,
+                "projecter.0.bias": 0.1 * torch.randn(512, generator=g),
+                "projecter.1.weight": 1.0 + 0.1 * torch.randn(512, generator=g),
+                "projecter.1.bias": 0.1 * torch.randn(512, generator=g)}
+    return {"Q": Q, "pool": pool, "bags": bags, "G": G, "W": ck["W"], "b": ck["b"], "proj": proj}

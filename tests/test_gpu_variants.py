@@ -18,7 +18,7 @@ def dev():
 
 def build_encoder(case, inp, dev):
     from vlsa_b200.model.deepmil import VLFAN
-    enc = VLFAN(dim_in=512, dim_hid=case["hid"], use_feat_proj=False, drop_rate=0.25, query="Parameter",
+    enc = VLFAN(dim_in=512, dim_hid=case["hid"], use_feat_proj=bool(case.get("feat_proj")), drop_rate=0.25, query="Parameter",
                 num_query=case["P"], gated_query=case["gated"], query_pooling=case["pooling"],
                 pred_head=case["pred_head"]).eval()
     with torch.no_grad():
@@ -30,6 +30,8 @@ def build_encoder(case, inp, dev):
             enc.query_pooling.copy_(inp["pool"]["weight"])
         elif case["pooling"] in ("attention", "gated_attention"):
             enc.query_pooling.load_state_dict(inp["pool"])
+        if case.get("feat_proj"):
+            enc.feat_proj.load_state_dict(inp["proj"])
     return enc.to(dev)
 
 
@@ -46,7 +48,7 @@ def test_variant_matches_reference_golden(case, dev):
     gold = load_case(variant_name(case))
     inp = variant_inputs(case)
     enc = build_encoder(case, inp, dev)
-    assert not enc.fused_tail
+    assert enc.fused_tail == (case["pooling"] == "mean" and case["pred_head"] == "default" and not case.get("feat_proj"))
     fs, loss = [], 0
     for X, G in zip(inp["bags"], inp["G"]):
         f, attn = enc(X.unsqueeze(0).to(dev), ret_with_attn=True)
@@ -67,6 +69,11 @@ def test_variant_matches_reference_golden(case, dev):
         close(dict(enc.query_pooling.named_parameters())[last].grad.cpu().numpy(), gold, "d_pool_last")
     if case["pred_head"] != "Identity":
         close(enc.visual_adapter.bias.grad.cpu().numpy(), gold, "d_b")
+    if case.get("feat_proj"):
+        pg = dict(enc.feat_proj.named_parameters())
+        close(pg["projecter.0.weight"].grad[:4].cpu().numpy(), gold, "d_proj_w_rows")
+        close(pg["projecter.1.weight"].grad.cpu().numpy(), gold, "d_proj_ln_w")
+        close(pg["projecter.0.weight"].grad.double().norm().cpu().numpy(), gold, "d_proj_w_fro", floor=1e-5)
 
 
 @pytest.mark.parametrize("P,dtype", [(1, torch.float32), (3, torch.float32), (4, torch.float32), (5, torch.float32),
@@ -144,3 +151,46 @@ def test_vlsa_module_with_variant_encoder_trains(dev):
         assert gr is not None and torch.isfinite(gr).all() and gr.abs().max() > 0
     assert pool["attention.2.bias"].grad.abs().max() == 0          # a softmax ignores a common shift of its logits
     assert net.mil_encoder.Q.grad.shape == (P + 1, 512) and net.mil_encoder.Q.grad[-1].abs().max() > 0
+
+
+@pytest.mark.parametrize("P,prenorm", [(1, False), (4, False), (12, True), (16, False)])
+def test_gradient_wrt_patch_rows_against_oracle(P, prenorm, dev):
+    """vlsa_agg_pooled_bwd_dx through ops.pooled (any gradient per prototype) and through ops.encode (mean + Linear):
+    dX against fp64 autograd of the oracle's formula, ragged bags incl. an empty and a 1-row bag."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import ops, synth
+    g = torch.Generator().manual_seed(1200 + P)
+    sizes = [300, 0, 1, 700, 129]
+    bags = [synth.make_bag("g1" if i % 2 else "g0", n, 5000 + i) for i, n in enumerate(sizes)]
+    Q = torch.nn.functional.normalize(torch.randn(P, 512, generator=g), dim=-1) + 0.5 * torch.randn(P, 512, generator=g)
+    if prenorm:
+        Qn = torch.nn.functional.normalize(torch.randn(P + 1, 512, generator=g), dim=-1)
+        Q = (Qn[:-1] - Qn[-1:]).contiguous()
+    W = torch.randn(512, 512, generator=g) / 22.0
+    bias = 0.1 * torch.randn(512, generator=g)
+    dO = torch.randn(len(sizes), P, 512, generator=g)
+    df = torch.randn(len(sizes), 512, generator=g)
+    X64 = torch.cat(bags).double().requires_grad_(True)
+    qdir = Q.double() if prenorm else torch.nn.functional.normalize(Q.double(), dim=-1)
+    outs, at = [], 0
+    for n in sizes:
+        Xb = X64[at:at + n]
+        at += n
+        if n == 0:
+            outs.append(torch.zeros(P, 512, dtype=torch.float64))
+            continue
+        S = float(O.coattn_scale()) * qdir @ torch.nn.functional.normalize(Xb, dim=-1).t()
+        outs.append(torch.softmax(S, dim=-1) @ Xb)
+    O64 = torch.stack(outs)
+    f64 = O64.mean(dim=1) @ W.double().t() + bias.double()
+    ref_pooled, = torch.autograd.grad((O64 * dO.double()).sum(), X64, retain_graph=True)
+    ref_encode, = torch.autograd.grad((f64 * df.double()).sum(), X64)
+    plan = ops.make_plan(sizes, dev)
+    Xg = torch.cat(bags).to(dev).requires_grad_(True)
+    Og, _ = ops.pooled(Xg, plan, Q.to(dev), prenorm)
+    got_pooled, = torch.autograd.grad((Og * dO.to(dev)).sum(), Xg)
+    fg, _ = ops.encode(Xg, plan, Q.to(dev), W.to(dev), bias.to(dev), None, prenorm)
+    got_encode, = torch.autograd.grad((fg * df.to(dev)).sum(), Xg)
+    for got, ref, what in ((got_pooled, ref_pooled, "pooled"), (got_encode, ref_encode, "encode")):
+        err = (got.cpu().double() - ref).abs().max().item()
+        assert err <= 2e-5 * ref.abs().max().item(), (what, err, ref.abs().max().item())

@@ -73,7 +73,7 @@ def test_reference_api_surface():
     assert net.forward_text_only().shape == (4, 512)
     assert callable(enc.visual_adapter) and enc.visual_adapter(torch.zeros(1, 3, 512)).shape == (1, 3, 512)
     assert float(enc.query_div_loss()) >= 0
-    for bad in (dict(use_feat_proj=True), dict(dim_in=1024), dict(num_query=17)):
+    for bad in (dict(dim_in=1024), dict(num_query=17)):
         from vlsa_b200.model import VLFAN
         kw = dict(dim_in=512, use_feat_proj=False, num_query=4)
         kw.update(bad)
@@ -97,7 +97,7 @@ def test_vlfan_variants_keep_reference_parameters_and_fail_loudly_on_cpu():
                     "query_pooling.score.0.weight": (256, 512), "query_pooling.score.0.bias": (256,),
                     "query_pooling.fc2.weight": (1, 256), "query_pooling.fc2.bias": (1,),
                     "visual_adapter.weight": (512, 512), "visual_adapter.bias": (512,)}
-    assert not enc.fused_tail and float(enc.query_div_loss()) >= 0
+    assert not enc.fused_tail and not enc.mean_linear_tail and float(enc.query_div_loss()) >= 0
     Qd, prenorm = enc.query_directions()
     assert prenorm and Qd.shape == (6, 512)
     enc = VLFAN(query_pooling="attention", pred_head="Identity", **kw)
@@ -108,7 +108,12 @@ def test_vlfan_variants_keep_reference_parameters_and_fail_loudly_on_cpu():
     pooled, ext = enc.forward_query_pooling(torch.randn(2, 6, 512))
     assert pooled.shape == (2, 512) and ext is None
     assert VLFAN(query_pooling="max", **kw).forward_query_pooling(torch.ones(1, 6, 512))[0].shape == (1, 512)
-    assert VLFAN(**kw).fused_tail
+    assert VLFAN(**kw).fused_tail and VLFAN(gated_query=True, **kw).fused_tail
+    enc = VLFAN(dim_in=512, use_feat_proj=True, num_query=6)
+    assert not enc.fused_tail and enc.mean_linear_tail
+    assert {k for k in enc.state_dict() if k.startswith("feat_proj")} == {
+        "feat_proj.projecter.0.weight", "feat_proj.projecter.0.bias", "feat_proj.projecter.1.weight",
+        "feat_proj.projecter.1.bias"}
     with pytest.raises((ValueError, RuntimeError)):
         enc(torch.randn(1, 10, 512))                                   # CPU tensor: no fallback
     # gated Text query: P + 1 rows, the last one from the negative prompt (prompt_adapter.py:73-81,127-134)

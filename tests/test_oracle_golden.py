@@ -105,11 +105,12 @@ def oracle_variant(case, inp, dtype):
     Q = c(inp["Q"]).clone().requires_grad_(True)
     pool = {k: c(v).clone().requires_grad_(True) for k, v in inp["pool"].items()}
     b = c(inp["b"]).clone().requires_grad_(True)
+    proj = None if inp["proj"] is None else {k: c(v).clone().requires_grad_(True) for k, v in inp["proj"].items()}
     scale = torch.tensor(O.coattn_scale(), dtype=dtype)
     fs, loss = [], 0
     for X, G in zip(inp["bags"], inp["G"]):
         f, A, ext, _ = O.vlfan_forward_variant(c(X).unsqueeze(0), Q, c(inp["W"]), b, case["gated"], case["pooling"],
-                                               pool, case["pred_head"], scale=scale)
+                                               pool, case["pred_head"], scale=scale, proj_params=proj)
         fs.append(f.detach())
         loss = loss + (f * c(G)).sum()
     loss.backward()
@@ -122,6 +123,10 @@ def oracle_variant(case, inp, dtype):
         rec["d_pool_last"] = pool["attention.2.weight" if case["pooling"] == "attention" else "fc2.weight"].grad.numpy()
     if case["pred_head"] != "Identity":
         rec["d_b"] = b.grad.numpy()
+    if proj is not None:
+        rec["d_proj_w_rows"] = proj["projecter.0.weight"].grad[:4].numpy()
+        rec["d_proj_w_fro"] = proj["projecter.0.weight"].grad.double().norm().numpy()
+        rec["d_proj_ln_w"] = proj["projecter.1.weight"].grad.numpy()
     return rec
 
 

@@ -24,12 +24,12 @@ _SIGNATURES = {
     "vlsa_agg_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32)]),
     "vlsa_agg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
-                               C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
+                               C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "vlsa_agg_partial_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                        C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
     "vlsa_agg_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
-                               C.c_float, c_f32p, c_f32p, C.c_int, c_f32p,
+                               C.c_int, C.c_float, c_f32p, c_f32p, C.c_int, c_f32p,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                c_f32p, c_f32p, c_f32p,
                                C.c_void_p, C.c_size_t,
@@ -39,6 +39,8 @@ _SIGNATURES = {
     "vlsa_agg_pooled_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                       C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, c_f32p,
                                       C.c_void_p]),
+    "vlsa_agg_pooled_bwd_dx": (C.c_int, [c_f32p, c_i64p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p,
+                                         c_f32p, c_f32p, c_f32p, C.c_void_p]),
     "vlsa_attn_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p, c_f32p,
                                 C.c_void_p]),
     "vlsa_interp_fwd": (C.c_int, [c_f32p, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, c_f32p, C.c_int, C.c_int, c_f32p,

@@ -230,7 +230,7 @@ size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P) {
 }
 
 int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
-                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
                  float* out_if, float* out_ml, float* out_O, float* out_Tn, void* stream) {
@@ -240,6 +240,7 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
     if (total_chunks > 0 && (!X || !workspace)) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
@@ -250,6 +251,7 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
+    prm.q_prenorm = q_prenorm;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
 
     int rc = launch_agg_fwd(prm, P, x_dtype, st);
@@ -295,7 +297,7 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, con
 }
 
 int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
-                 int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale, const float* W,
+                 int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
                  const float* d_f, void* workspace, size_t workspace_bytes, float* dQ, float* dW, float* db,
@@ -307,6 +309,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if (B < 1 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
     if (total_chunks > 0 && !X) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
@@ -332,7 +335,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
-    prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta;
+    prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta; prm.q_prenorm = q_prenorm;
     int rc = 0;
     if (agg_use_tc(P, x_dtype)) {
         rc = launch_agg_tc<true>(prm, P, st);
@@ -348,9 +351,9 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if (Sb > 0) {
         merge_bwd_split_kernel<<<dim3(Sb, P), 128, 0, st>>>(ws.part_O, total_chunks, P, Sb, ws.l2_O);
         VLSA_CUDA(cudaGetLastError());
-        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.l2_O, Sb, P, Q, dQ);
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.l2_O, Sb, P, Q, dQ, q_prenorm);
     } else {
-        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ);
+        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ, q_prenorm);
     }
     VLSA_CUDA(cudaGetLastError());
     return 0;
@@ -427,6 +430,23 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     } else {
         merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ, q_prenorm);
     }
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_agg_pooled_bwd_dx(const float* X, const int64_t* cu_rows, int B, int64_t max_rows, const float* Q, int P,
+                           int q_prenorm, float coattn_scale, const float* ml, const float* O, const float* d_O,
+                           float* out_dX, void* stream) {
+    if (B == 0 || max_rows == 0) return 0;
+    if (!X || !cu_rows || !Q || !ml || !O || !d_O || !out_dX) return VLSA_EINVAL;
+    if (B < 0 || max_rows < 0 || P < 1 || P > VLSA_MAX_P || (q_prenorm != 0 && q_prenorm != 1)) return VLSA_EINVAL;
+    const long long tiles = (max_rows + 127) / 128;
+    if (tiles > 0x7fffffffLL || B > 65535) return VLSA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem = (size_t(2 * P) * VLSA_D + 3 * P) * sizeof(float);
+    VLSA_CUDA(cudaFuncSetAttribute(agg_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    agg_dx_kernel<<<dim3(unsigned(tiles), unsigned(B)), 256, smem, st>>>(X, reinterpret_cast<const long long*>(cu_rows), Q, P,
+                                                                         q_prenorm, coattn_scale, ml, O, d_O, out_dX);
     VLSA_CUDA(cudaGetLastError());
     return 0;
 }
@@ -589,7 +609,7 @@ int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_ho
     if (rc == 0) rc = static_cast<int>(cudaStreamWaitEvent(sc, landed, 0));
     if (rc == 0)
         rc = vlsa_agg_fwd(ws.X, x_dtype, reinterpret_cast<const int64_t*>(ws.cu_rows), ws.chunk_start, B, chunk_rows,
-                          total_chunks, Q, P, coattn_scale, W, bias, T, R, logit_scale, ws.agg, ws.agg_bytes, ws.v,
+                          total_chunks, Q, P, 0, coattn_scale, W, bias, T, R, logit_scale, ws.agg, ws.agg_bytes, ws.v,
                           ws.f, ws.g, ws.logits, ws.inc, ws.ml, nullptr, nullptr, sc);
     if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(out_if_host, ws.inc, size_t(B) * R * 4, cudaMemcpyDeviceToHost, sc));
     if (rc == 0 && out_logits_host)

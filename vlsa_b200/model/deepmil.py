@@ -4,11 +4,13 @@ Same constructor arguments, attributes, method names and state-dict keys as mode
 liupei101/VLSA; the arithmetic over the N patches runs in libvlsa_b200.so (no PyTorch fallback).
 
 Shipped configuration (mean over P -> Linear): everything up to the visual feature is one fused CUDA path
-(``ops.encode`` / ``ops.aggregate``).  Config-reachable variants that no shipped VLSA config enables —
-``gated_query``, ``query_pooling`` in {max, weight, attention, gated_attention}, ``pred_head='Identity'`` — share the
-same streaming kernels through ``ops.pooled`` (O [B,P,512] with a gradient row per prototype on the way back); only
-their P x 512 tail (the pooling modules below, state-dict compatible with model/layers.py:85-155) is torch ops on the
-GPU.  ``use_feat_proj=True`` (a Linear + LayerNorm over all N rows whose backward needs dX) raises NotImplementedError.
+(``ops.encode`` / ``ops.aggregate``); ``gated_query`` rides the same path (its P + 1 unit rows collapse to P difference
+rows the kernels take as they are).  The other config-reachable variants no shipped VLSA config enables —
+``query_pooling`` in {max, weight, attention, gated_attention}, ``pred_head='Identity'`` — share the streaming kernels
+through ``ops.pooled`` (O [B,P,512] with a gradient row per prototype on the way back); only their P x 512 tail (the
+pooling modules below, state-dict compatible with model/layers.py:85-155) is torch ops on the GPU.
+``use_feat_proj=True`` puts the reference's Linear + LayerNorm over all N rows (a plain library GEMM) in front and gets
+its gradient from ``vlsa_agg_pooled_bwd_dx``.
 """
 from __future__ import annotations
 
@@ -56,6 +58,20 @@ class FeatMIL(nn.Module):
         return self.network(X.squeeze(0))
 
 
+class Feat_Projecter(nn.Module):
+    """model/layers.py:65-82: Linear + LayerNorm over every patch row ([B, N, C] or [N, C])."""
+
+    def __init__(self, in_dim=1024, out_dim=1024):
+        super().__init__()
+        self.projecter = nn.Sequential(nn.Linear(in_dim, out_dim), nn.LayerNorm(out_dim))
+
+    def forward(self, x):
+        if x.dim() == 3:
+            L1, L2, L3 = x.shape
+            return self.projecter(x.reshape(-1, L3)).view(L1, L2, -1)
+        return self.projecter(x)
+
+
 class Gated_Attention_Pooling(nn.Module):
     """model/layers.py:85-123 (Ilse et al. 2018) over the P per-prototype features: [B, P, d] -> [B, d]."""
 
@@ -97,15 +113,12 @@ class VLFAN(nn.Module):
         super().__init__()
         if dim_in != ops.D_FEAT:
             raise NotImplementedError(f"the B200 kernels are built for dim_in={ops.D_FEAT} (CONCH), got {dim_in}")
-        if use_feat_proj:
-            raise NotImplementedError("use_feat_proj=True (Feat_Projecter) is not on the accelerated path "
-                                      "(cfg_vlsa_conch.yaml:49 sets it False)")
         assert query in ["Parameter", "Text"]
         assert query_pooling in ["mean", "max", "weight", "attention", "gated_attention"]
         if not (1 <= num_query <= ops.MAX_P):
             raise NotImplementedError(f"num_query must be in 1..{ops.MAX_P}, got {num_query}")
         self._pos_gated_query = -1
-        self.feat_proj = None
+        self.feat_proj = Feat_Projecter(dim_in, dim_in) if use_feat_proj else None     # deepmil.py:81-84
         self.num_query = num_query
         self.query_type = query
         self.gated_query = gated_query
@@ -146,10 +159,15 @@ class VLFAN(nn.Module):
         return torch.matmul(weight, X).squeeze(1), None
 
     @property
-    def fused_tail(self) -> bool:
-        """True for the shipped configuration: mean over P and the Linear adapter run inside the CUDA path."""
-        return (not self.gated_query and isinstance(self.query_pooling, str) and self.query_pooling == "mean"
+    def mean_linear_tail(self) -> bool:
+        """Mean over P and the Linear adapter: the tail the CUDA path fuses (the shipped configuration)."""
+        return (isinstance(self.query_pooling, str) and self.query_pooling == "mean"
                 and isinstance(self.visual_adapter, nn.Linear))
+
+    @property
+    def fused_tail(self) -> bool:
+        """True when VLSA.forward can run as ONE fused call (ops.aggregate): fused tail and raw rows as input."""
+        return self.mean_linear_tail and self.feat_proj is None
 
     def query_directions(self):
         """(rows that enter the scores, prenorm flag).  Gated query (deepmil.py:192-195): A_[:, :-1] - A_[:, -1:] is
@@ -179,34 +197,32 @@ class VLFAN(nn.Module):
     # ---- fused path ----------------------------------------------------------------------------
     def encode_packed(self, X: torch.Tensor, plan: "ops.BagPlan"):
         """Packed bags [total_rows, D] -> visual features f [B, D] (differentiable w.r.t. Q, W, b)."""
-        if self.fused_tail:
-            f, ml = ops.encode(X, plan, self.get_query(), self.visual_adapter.weight, self.visual_adapter.bias,
-                               float(self.get_coattn_logit_scale()))
-            return f, ml
-        f, ml, _ = self.encode_packed_ext(X, plan)
+        f, ml, _, _ = self.encode_packed_ext(X, plan)
         return f, ml
 
     def encode_packed_ext(self, X: torch.Tensor, plan: "ops.BagPlan"):
-        """Variant tail: streaming kernels -> O [B, P, D] -> pooling over P -> adapter.  Returns (f, ml, pooling
-        scores or None)."""
+        """-> (f [B, D], ml, pooling scores or None, the rows the aggregation saw).  Mean + Linear tails run fused
+        (ops.encode); the others go streaming kernels -> O [B, P, D] -> pooling over P -> adapter."""
+        if self.feat_proj is not None:
+            X = self.feat_proj(X.float())                                  # deepmil.py:176-179, [sum N_i, D]
         Qd, prenorm = self.query_directions()
-        O, ml = ops.pooled(X, plan, Qd, prenorm, float(self.get_coattn_logit_scale()))
+        scale = float(self.get_coattn_logit_scale())
+        if self.mean_linear_tail:
+            f, ml = ops.encode(X, plan, Qd, self.visual_adapter.weight, self.visual_adapter.bias, scale, prenorm)
+            return f, ml, None, X
+        O, ml = ops.pooled(X, plan, Qd, prenorm, scale)
         pooled_out, pooled_ext = self.forward_query_pooling(O)
-        return self.visual_adapter(pooled_out), ml, pooled_ext
+        return self.visual_adapter(pooled_out), ml, pooled_ext, X
 
     def forward(self, X, ret_with_attn=False):
         """X [1, N, C] -> visual_features [1, C] (and A [1, P, N] detached), deepmil.py:170-215."""
         assert X.shape[0] == 1
         Xp = X[0].contiguous()
         plan = ops.make_plan([Xp.shape[0]], Xp.device)
-        if self.fused_tail:
-            f, ml = self.encode_packed(Xp, plan)
-            pooled_ext = None
-        else:
-            f, ml, pooled_ext = self.encode_packed_ext(Xp, plan)
+        f, ml, pooled_ext, Xs = self.encode_packed_ext(Xp, plan)
         if ret_with_attn:
             Qd, prenorm = self.query_directions()
-            A = ops.attention_scores(Xp, Qd.detach().contiguous(), ml[0], float(self.get_coattn_logit_scale()),
+            A = ops.attention_scores(Xs.detach(), Qd.detach().contiguous(), ml[0], float(self.get_coattn_logit_scale()),
                                      q_prenorm=prenorm).unsqueeze(0)
             if pooled_ext is not None:
                 return f, (A, pooled_ext.detach())                  # deepmil.py:208-209

@@ -112,8 +112,9 @@ class VLSA(nn.Module):
             g = torch.nn.functional.normalize(f, dim=-1)
             logits = self.logit_scale.exp() * g @ Tn.t()
             return logits, g, Tn, torch.softmax(logits.detach(), dim=-1), ml
-        return ops.aggregate(Xp, plan, enc.get_query(), enc.visual_adapter.weight, enc.visual_adapter.bias,
-                             text_features, self.logit_scale, float(enc.get_coattn_logit_scale()))
+        Qd, prenorm = enc.query_directions()
+        return ops.aggregate(Xp, plan, Qd, enc.visual_adapter.weight, enc.visual_adapter.bias,
+                             text_features, self.logit_scale, float(enc.get_coattn_logit_scale()), prenorm)
 
     def forward_packed(self, X_packed: torch.Tensor, plan: "ops.BagPlan", text_features: torch.Tensor | None = None):
         """All bags of one step in one launch: X_packed [sum N_i, 512] + plan -> (logits [B,R], g [B,512], Tn,

@@ -123,7 +123,7 @@ def _workspace(plan: BagPlan, P: int, device) -> torch.Tensor:
 
 
 def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd: bool = True, scale: float | None = None,
-                          workspace: torch.Tensor | None = None, want_if: bool = True):
+                          workspace: torch.Tensor | None = None, want_if: bool = True, q_prenorm: bool = False):
     """Launch vlsa_agg_fwd.  Returns a dict of fresh output tensors (no autograd)."""
     L = _lib.lib()
     B, P, R = plan.num_bags, Q.shape[0], T.shape[0]
@@ -150,7 +150,7 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
     }
     ws = workspace if workspace is not None else _workspace(plan, P, dev)
     rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
-                        plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P,
+                        plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, int(bool(q_prenorm)),
                         coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
                         T.data_ptr(), R, logit_scale.data_ptr(), ws.data_ptr(), ws.numel(),
                         out["v"].data_ptr(), out["f"].data_ptr(), out["g"].data_ptr(), out["logits"].data_ptr(),
@@ -174,11 +174,11 @@ class _AggregateFn(torch.autograd.Function):
     """Differentiable w.r.t. (Q, W, bias, T, logit_scale).  X is data (the reference never asks for dX)."""
 
     @staticmethod
-    def forward(ctx, X, plan, Q, W, bias, T, logit_scale, scale):
+    def forward(ctx, X, plan, Q, W, bias, T, logit_scale, scale, q_prenorm=False):
         Qc, Wc, bc, Tc, lsc = (t.detach().contiguous() for t in (Q, W, bias, T, logit_scale))
         need_bwd = any(t.requires_grad for t in (Q, W, bias, T, logit_scale))
-        out = aggregate_forward_raw(X, plan, Qc, Wc, bc, Tc, lsc, need_bwd=need_bwd, scale=scale)
-        ctx.plan, ctx.scale, ctx.need_bwd = plan, scale, need_bwd
+        out = aggregate_forward_raw(X, plan, Qc, Wc, bc, Tc, lsc, need_bwd=need_bwd, scale=scale, q_prenorm=q_prenorm)
+        ctx.plan, ctx.scale, ctx.need_bwd, ctx.prenorm = plan, scale, need_bwd, int(bool(q_prenorm))
         ctx.set_materialize_grads(False)
         ctx.ws = out["_workspace"]
         if need_bwd:
@@ -202,20 +202,21 @@ class _AggregateFn(torch.autograd.Function):
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
         dT, dls = torch.empty(R, D_FEAT, **f32), torch.empty((), **f32)
         rc = L.vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
-                            plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P,
+                            plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, ctx.prenorm,
                             coattn_scale() if ctx.scale is None else float(ctx.scale), W.data_ptr(), T.data_ptr(), R,
                             ls.data_ptr(), v.data_ptr(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), ml.data_ptr(),
                             O.data_ptr(), d_logits.data_ptr(), _ptr(d_g), None, ctx.ws.data_ptr(), ctx.ws.numel(),
                             dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), dT.data_ptr(), dls.data_ptr(), _stream())
         _lib.check(rc, "vlsa_agg_bwd")
-        return None, None, dQ, dW, db, dT, dls, None
+        return None, None, dQ, dW, db, dT, dls, None, None
 
 
 class _EncodeFn(torch.autograd.Function):
-    """VLFAN.forward alone (deepmil.py:170-215): packed bags -> f [B, D]; differentiable w.r.t. (Q, W, bias)."""
+    """VLFAN.forward alone (deepmil.py:170-215): packed bags -> f [B, D]; differentiable w.r.t. (Q, W, bias) and,
+    when the rows come out of a trainable feat_proj (X.requires_grad), w.r.t. X."""
 
     @staticmethod
-    def forward(ctx, X, plan, Q, W, bias, scale):
+    def forward(ctx, X, plan, Q, W, bias, scale, q_prenorm=False):
         L = _lib.lib()
         Qc, Wc, bc = (t.detach().contiguous() for t in (Q, W, bias))
         B, P = plan.num_bags, Qc.shape[0]
@@ -232,20 +233,22 @@ class _EncodeFn(torch.autograd.Function):
         ws = _workspace(plan, P, X.device)
         sc = coattn_scale() if scale is None else float(scale)
         rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
-                            plan.chunk_rows, plan.total_chunks, Qc.data_ptr(), P, sc, Wc.data_ptr(), bc.data_ptr(),
-                            None, 0, None, ws.data_ptr(), ws.numel(), v.data_ptr(), f.data_ptr(), None, None, None,
-                            ml.data_ptr(), O.data_ptr(), None, _stream())
+                            plan.chunk_rows, plan.total_chunks, Qc.data_ptr(), P, int(bool(q_prenorm)), sc, Wc.data_ptr(),
+                            bc.data_ptr(), None, 0, None, ws.data_ptr(), ws.numel(), v.data_ptr(), f.data_ptr(), None,
+                            None, None, ml.data_ptr(), O.data_ptr(), None, _stream())
         _lib.check(rc, "vlsa_agg_fwd")
-        ctx.plan, ctx.scale, ctx.ws = plan, sc, ws
+        ctx.plan, ctx.scale, ctx.ws, ctx.prenorm = plan, sc, ws, int(bool(q_prenorm))
+        if ctx.needs_input_grad[0] and X.dtype != torch.float32:
+            raise ValueError("a gradient w.r.t. the patch rows needs fp32 rows")
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(X, Qc, Wc, v, ml, O)
+        ctx.save_for_backward(X.detach(), Qc, Wc, v, ml, O)
         ctx.mark_non_differentiable(ml)
         return f, ml
 
     @staticmethod
     def backward(ctx, d_f, _d_ml):
         if d_f is None:
-            return (None,) * 6
+            return (None,) * 7
         X, Q, W, v, ml, O = ctx.saved_tensors
         plan = ctx.plan
         P = Q.shape[0]
@@ -254,16 +257,23 @@ class _EncodeFn(torch.autograd.Function):
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
         rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
                                      plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows, plan.total_chunks,
-                                     Q.data_ptr(), P, ctx.scale, W.data_ptr(), None, 0, None, v.data_ptr(), None, None,
-                                     None, ml.data_ptr(), O.data_ptr(), None, None, d_f.data_ptr(), ctx.ws.data_ptr(),
-                                     ctx.ws.numel(), dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), None, None, _stream())
+                                     Q.data_ptr(), P, ctx.prenorm, ctx.scale, W.data_ptr(), None, 0, None, v.data_ptr(),
+                                     None, None, None, ml.data_ptr(), O.data_ptr(), None, None, d_f.data_ptr(),
+                                     ctx.ws.data_ptr(), ctx.ws.numel(), dQ.data_ptr(), dW.data_ptr(), db.data_ptr(), None,
+                                     None, _stream())
         _lib.check(rc, "vlsa_agg_bwd")
-        return None, None, dQ, dW, db, None
+        dX = None
+        if ctx.needs_input_grad[0]:
+            # mean over P: every prototype sees the same gradient row dv / P, dv = W^T d_f ([B,512] x [512,512])
+            dO = ((d_f @ W) / P).unsqueeze(1).expand(-1, P, -1).contiguous()
+            dX = _pooled_dx(X, plan, Q, ctx.prenorm, ctx.scale, ml, O, dO)
+        return dX, None, dQ, dW, db, None, None
 
 
 class _PooledFn(torch.autograd.Function):
     """Per-prototype pooled features O [B, P, D] (deepmil.py:187-200) for the VLFAN variants whose tail is not
-    "mean over P -> Linear".  Differentiable w.r.t. the query directions; the gradient d_O may be anything."""
+    "mean over P -> Linear".  Differentiable w.r.t. the query directions — and w.r.t. X when X itself requires a
+    gradient (rows produced by a trainable feat_proj); the gradient d_O may be anything."""
 
     @staticmethod
     def forward(ctx, X, plan, Q, q_prenorm, scale):
@@ -287,8 +297,10 @@ class _PooledFn(torch.autograd.Function):
                                             ml.data_ptr(), O.data_ptr(), _stream())
         _lib.check(rc, "vlsa_agg_pooled_fwd")
         ctx.plan, ctx.scale, ctx.ws, ctx.prenorm = plan, sc, ws, int(bool(q_prenorm))
+        if ctx.needs_input_grad[0] and X.dtype != torch.float32:
+            raise ValueError("a gradient w.r.t. the patch rows needs fp32 rows")
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(X, Qc, ml, O)
+        ctx.save_for_backward(X.detach(), Qc, ml, O)
         ctx.mark_non_differentiable(ml)
         return O, ml
 
@@ -307,7 +319,20 @@ class _PooledFn(torch.autograd.Function):
                                             O.data_ptr(), d_O.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
                                             dQ.data_ptr(), _stream())
         _lib.check(rc, "vlsa_agg_pooled_bwd")
-        return None, None, dQ, None, None
+        dX = _pooled_dx(X, plan, Q, ctx.prenorm, ctx.scale, ml, O, d_O) if ctx.needs_input_grad[0] else None
+        return dX, None, dQ, None, None
+
+
+def _pooled_dx(X, plan: BagPlan, Q, prenorm: int, scale: float, ml, O, d_O):
+    """vlsa_agg_pooled_bwd_dx: gradient of the pooled aggregation w.r.t. the (fp32) patch rows."""
+    dX = torch.empty_like(X)
+    sizes = np.diff(plan.cu_rows_host)
+    rc = _lib.lib().vlsa_agg_pooled_bwd_dx(X.data_ptr(), plan.cu_rows.data_ptr(), plan.num_bags,
+                                           int(sizes.max()) if len(sizes) else 0, Q.data_ptr(), Q.shape[0], int(prenorm),
+                                           float(scale), ml.data_ptr(), O.data_ptr(), d_O.data_ptr(), dX.data_ptr(),
+                                           _stream())
+    _lib.check(rc, "vlsa_agg_pooled_bwd_dx")
+    return dX
 
 
 def pooled(X, plan: BagPlan, Q, q_prenorm: bool = False, scale: float | None = None):
@@ -316,14 +341,15 @@ def pooled(X, plan: BagPlan, Q, q_prenorm: bool = False, scale: float | None = N
     return _PooledFn.apply(X, plan, Q, q_prenorm, scale)
 
 
-def encode(X, plan: BagPlan, Q, W, bias, scale: float | None = None):
+def encode(X, plan: BagPlan, Q, W, bias, scale: float | None = None, q_prenorm: bool = False):
     """Fused VLFAN forward on a packed batch: returns (f [B,D], ml [B,P,2])."""
-    return _EncodeFn.apply(X, plan, Q, W, bias, scale)
+    return _EncodeFn.apply(X, plan, Q, W, bias, scale, q_prenorm)
 
 
-def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None):
-    """Fused VLSA forward on a packed batch.  Returns (logits [B,R], g [B,D], Tn [R,D], incidence [B,R], ml)."""
-    return _AggregateFn.apply(X, plan, Q, W, bias, T, logit_scale, scale)
+def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None, q_prenorm: bool = False):
+    """Fused VLSA forward on a packed batch.  Returns (logits [B,R], g [B,D], Tn [R,D], incidence [B,R], ml).
+    ``q_prenorm``: the rows of Q are the gated query's difference rows, used without normalisation."""
+    return _AggregateFn.apply(X, plan, Q, W, bias, T, logit_scale, scale, q_prenorm)
 
 
 def attention_scores(X, Q, ml, scale: float | None = None, q_prenorm: bool = False):
