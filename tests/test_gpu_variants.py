@@ -149,7 +149,7 @@ def test_vlsa_module_with_variant_encoder_trains(dev):
              pool["attention.0.weight"].grad, pool["attention.2.weight"].grad]
     for gr in grads:
         assert gr is not None and torch.isfinite(gr).all() and gr.abs().max() > 0
-    assert pool["attention.2.bias"].grad.abs().max() == 0          # a softmax ignores a common shift of its logits
+    assert pool["attention.2.bias"].grad.abs().max() <= 1e-6       # a softmax ignores a common shift of its logits
     assert net.mil_encoder.Q.grad.shape == (P + 1, 512) and net.mil_encoder.Q.grad[-1].abs().max() > 0
 
 
