@@ -30,7 +30,7 @@ def timed(fn, iters=10):
     return a.elapsed_time(b) / iters
 
 
-for P in (4, 12):
+for P in (4, 8, 12):
     g = torch.Generator().manual_seed(P)
     Q = torch.randn(P, 512, generator=g).to(dev).requires_grad_(True)
     W = (torch.randn(512, 512, generator=g) / 22).to(dev).requires_grad_(True)
@@ -49,9 +49,18 @@ for P in (4, 12):
         f, _ = ops.encode(X, plan, Q, W, bias)
         f.backward(df)
 
+    def step_pooled_dx():                       # the rows themselves need a gradient (feat_proj in front)
+        O, _ = ops.pooled(X, plan, Q, False)
+        torch.autograd.grad(O, (X, Q), dO)      # no accumulation into .grad: the kernels alone
+
     tf, ts, tm = timed(fwd_pooled), timed(step_pooled), timed(step_mean)
+    X.requires_grad_(True)
+    tx = timed(step_pooled_dx, iters=4)
+    X.requires_grad_(False)
     out[f"P{P}"] = {"pooled_fwd_ms": tf, "pooled_fwd_bwd_ms": ts, "pooled_bwd_ms": ts - tf,
-                    "pooled_bwd_GBps": gbytes / ((ts - tf) * 1e-3), "mean_fwd_bwd_ms": tm}
+                    "pooled_bwd_GBps": gbytes / ((ts - tf) * 1e-3), "mean_fwd_bwd_ms": tm,
+                    "dx_ms": tx - ts, "dx_GBps_read_plus_write": 2 * gbytes / ((tx - ts) * 1e-3)}
     print(P, out[f"P{P}"])
+group = os.environ.get("VLSA_GEN_GROUP", "default")
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/variant_time.json", "w"), indent=1)
+json.dump(out, open(f"gpurun_out/variant_time_group_{group}.json", "w"), indent=1)

@@ -31,6 +31,8 @@ struct AggParams {
                                 // MODE 2: [B, P, D] d loss / d O_p, one gradient row per prototype
     const float* ml;            // [B, P, 2] (max, sum) from forward
     const float* delta;         // [B, P]   dO_p . O_p
+    int p_stride;               // MODE 2: prototypes per bag in dv / ml / delta (>= P: a launch may serve a sub-range of
+                                //         the prototypes, the pointers then start at its first one)
 };
 
 #ifndef VLSA_AGG_WARPS
@@ -215,16 +217,17 @@ __global__ void __launch_bounds__(AggCfg<P, MODE, XT>::THREADS) agg_simt_kernel(
         if (BWD) {
             // per-bag operands: extra query row(s) dv_b / P | dO_b, saved (m, 1/l), delta_p = (dv . O_p) / P | dO_p . O_p
             __syncthreads();
+            const size_t bp = size_t(bag) * (GEN ? prm.p_stride : P);       // first prototype of the bag
             if (GEN) {
-                for (int i = tid; i < P * D; i += C::THREADS) qs[P * D + i] = __ldg(prm.dv + size_t(bag) * P * D + i);
+                for (int i = tid; i < P * D; i += C::THREADS) qs[P * D + i] = __ldg(prm.dv + bp * D + i);
             } else {
                 const float invP = 1.f / float(P);
                 for (int d = tid; d < D; d += C::THREADS) qs[P * D + d] = __ldg(prm.dv + size_t(bag) * D + d) * invP;
             }
             if (tid < P) {
-                s_m[tid] = __ldg(prm.ml + (size_t(bag) * P + tid) * 2);
-                s_l[tid] = 1.f / __ldg(prm.ml + (size_t(bag) * P + tid) * 2 + 1);
-                s_alpha[tid] = __ldg(prm.delta + size_t(bag) * P + tid);
+                s_m[tid] = __ldg(prm.ml + (bp + tid) * 2);
+                s_l[tid] = 1.f / __ldg(prm.ml + (bp + tid) * 2 + 1);
+                s_alpha[tid] = __ldg(prm.delta + bp + tid);
             }
             __syncthreads();
             if (QREG_J > 0) {                   // the bag's extra query row dv / P joins the register-resident Qn

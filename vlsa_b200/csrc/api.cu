@@ -164,6 +164,16 @@ static bool agg_use_tc(int P, int x_dtype) {
     return P > 5;
 }
 
+// prototypes per launch of the per-prototype-gradient backward (development override: VLSA_GEN_GROUP=1..16)
+static int gen_group_size() {
+    static const int g = [] {
+        const char* e = getenv("VLSA_GEN_GROUP");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= VLSA_MAX_P) ? v : 8;
+    }();
+    return g;
+}
+
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {
     if (agg_use_tc(P, x_dtype)) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
@@ -415,22 +425,36 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
     prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
-    prm.dv = d_O; prm.ml = ml; prm.delta = ws.delta;
-    int rc = 0;
-    VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 2, float>(prm, st);
-        else rc = launch_agg<kP, 2, __nv_bfloat16>(prm, st);
-        if (rc) return rc;
-    });
-    const int Sb = merge_bwd_splits(total_chunks, P);
-    if (Sb > 0) {
-        merge_bwd_split_kernel<<<dim3(Sb, P), 128, 0, st>>>(ws.part_O, total_chunks, P, Sb, ws.l2_O);
+    prm.p_stride = P;
+    // 2 P + 1 dots per row and 2 P resident rows outgrow registers and shared memory beyond P = 8 (one launch at
+    // P = 12: 4.0 ms for 32 x 50k rows, against 1.3 ms at P = 8), and prototypes are independent in this pass: serve
+    // them in balanced groups of <= 8, one launch and one read of X per group, each with its own slice of the partials.
+    const int group = gen_group_size();
+    const int ngroups = (P + group - 1) / group;
+    for (int gi = 0, p0 = 0; gi < ngroups; ++gi) {
+        const int pg = (P - p0 + (ngroups - gi) - 1) / (ngroups - gi);       // balanced: 12 -> 6+6, 9 -> 5+4
+        float* part = ws.part_O + size_t(total_chunks) * p0 * VLSA_D;
+        float* l2 = ws.l2_O + size_t(merge_bwd_splits(total_chunks, P)) * p0 * VLSA_D;
+        prm.Q = Q + size_t(p0) * VLSA_D; prm.dv = d_O + size_t(p0) * VLSA_D; prm.ml = ml + size_t(p0) * 2;
+        prm.delta = ws.delta + p0; prm.part_O = part;
+        int rc = 0;
+        VLSA_DISPATCH_P(pg, {
+            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 2, float>(prm, st);
+            else rc = launch_agg<kP, 2, __nv_bfloat16>(prm, st);
+            if (rc) return rc;
+        });
+        // the split count is the one the workspace was carved for (P prototypes); any split is a valid fixed order
+        const int Sb = merge_bwd_splits(total_chunks, P);
+        if (Sb > 0) {
+            merge_bwd_split_kernel<<<dim3(Sb, pg), 128, 0, st>>>(part, total_chunks, pg, Sb, l2);
+            VLSA_CUDA(cudaGetLastError());
+            merge_bwd_kernel<<<pg, 512, 0, st>>>(l2, Sb, pg, prm.Q, dQ + size_t(p0) * VLSA_D, q_prenorm);
+        } else {
+            merge_bwd_kernel<<<pg, 512, 0, st>>>(part, total_chunks, pg, prm.Q, dQ + size_t(p0) * VLSA_D, q_prenorm);
+        }
         VLSA_CUDA(cudaGetLastError());
-        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.l2_O, Sb, P, Q, dQ, q_prenorm);
-    } else {
-        merge_bwd_kernel<<<P, 512, 0, st>>>(ws.part_O, total_chunks, P, Q, dQ, q_prenorm);
+        p0 += pg;
     }
-    VLSA_CUDA(cudaGetLastError());
     return 0;
 }
 
