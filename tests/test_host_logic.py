@@ -124,6 +124,19 @@ def test_vlfan_variants_keep_reference_parameters_and_fail_loudly_on_cpu():
     with pytest.raises(RuntimeError):
         PromptAdapter(None, method="TaskRes", num_prompts=6, pretrained_prompt_features=torch.randn(6, 512),
                       load_negative_prompts=True)
+    # the other query_text methods of the reference (prompt_adapter.py:86-105,118-149)
+    feats = torch.randn(6, 512)
+    ad = PromptAdapter(None, method="Adapter", num_prompts=6, pretrained_prompt_features=feats, dim_reduction=4,
+                       keep_ratio=0.8)
+    assert {k: tuple(v.shape) for k, v in ad.state_dict().items()} == {"adapter.fc.0.weight": (128, 512),
+                                                                        "adapter.fc.2.weight": (512, 128)}
+    want = 0.2 * torch.relu(torch.relu(feats @ ad.adapter.fc[0].weight.T) @ ad.adapter.fc[2].weight.T) + 0.8 * feats
+    torch.testing.assert_close(ad(), want)
+    fc = PromptAdapter(None, method="FC", num_prompts=6, pretrained_prompt_features=feats).eval()
+    assert set(fc.state_dict()) == {"fc.0.weight"}
+    torch.testing.assert_close(fc(), feats @ fc.fc[0].weight.T)
+    torch.testing.assert_close(PromptAdapter(None, method="default", num_prompts=6, pretrained_prompt_features=feats)(),
+                               feats)
 
 
 def test_no_cpu_fallback():
