@@ -10,6 +10,7 @@ tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_p4.json 2> gpurun_out/bench_p4.err; tail -c 3500 gpurun_out/bench_p4.json; tail -5 gpurun_out/bench_p4.err
 timeout 600 python bench.py --steps 20 --warmup 5 --P 12 --R 12 --no-e2e --no-cpu-baseline > gpurun_out/bench_p12.json 2> gpurun_out/bench_p12.err; tail -c 2500 gpurun_out/bench_p12.json; tail -5 gpurun_out/bench_p12.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref.json 2>&1; tail -c 600 gpurun_out/bench_ref.json
+timeout 300 python scripts/dev_variant_time.py > gpurun_out/variant_time.log 2>&1; tail -3 gpurun_out/variant_time.log
 # launch lists of the same bench commands (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_p4.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/ncu_bench_p4.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_p12_train.csv python bench.py --steps 3 --warmup 3 --P 12 --R 12 --no-e2e --no-cpu-baseline > gpurun_out/ncu_bench_p12.log 2>&1

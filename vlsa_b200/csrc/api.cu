@@ -469,7 +469,7 @@ int vlsa_agg_pooled_bwd_dx(const float* X, const int64_t* cu_rows, int B, int64_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem = (size_t(2 * P) * VLSA_D + 3 * P) * sizeof(float);
     VLSA_CUDA(cudaFuncSetAttribute(agg_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    agg_dx_kernel<<<dim3(unsigned(tiles), unsigned(B)), 256, smem, st>>>(X, reinterpret_cast<const long long*>(cu_rows), Q, P,
+    agg_dx_kernel<<<dim3(unsigned(tiles), unsigned(B)), 128, smem, st>>>(X, reinterpret_cast<const long long*>(cu_rows), Q, P,
                                                                          q_prenorm, coattn_scale, ml, O, d_O, out_dX);
     VLSA_CUDA(cudaGetLastError());
     return 0;

@@ -242,13 +242,16 @@ __global__ void __launch_bounds__(1024) logit_pool_kernel(const float* __restric
 // over all patch rows, model/layers.py:65-82 + model/deepmil.py:176-179).  With O_p = sum_n A_pn x_n and
 // s_pn = scale qdir_p . x_n / |x_n|:
 //   dx_n = sum_p ( A_pn dO_p + (scale dS_pn / |x_n|) qdir_p ) - (sum_p dS_pn s_pn) x_n / |x_n|^2,   dS_pn = A_pn (dO_p . x_n - dO_p . O_p)
-// (no projection term for rows whose norm is clamped at eps, as F.normalize's backward).  One warp per row, lane = 16
-// columns; the 2 P rows (qdir, dO_b) of the bag sit in shared memory.  grid (ceil(max_rows / 128), B), 256 threads.
-__global__ void __launch_bounds__(256) agg_dx_kernel(const float* __restrict__ X, const long long* __restrict__ cu_rows,
+// (no projection term for rows whose norm is clamped at eps, as F.normalize's backward).  The 2 P rows (qdir, dO_b) of
+// the bag sit in shared memory; a warp works on FOUR rows at a time (lane = 16 columns of each) so that every 16-byte
+// read of a qdir / dO row serves four patch rows in both of its uses (dot product, then accumulation) — with one row
+// per warp the kernel re-read 2 x 2 P x 2 KB of shared memory per 2 KB row and was bound by that.  Packed fp32x2 FMAs.
+// grid (ceil(max_rows / 128), B), 128 threads.
+__global__ void __launch_bounds__(128) agg_dx_kernel(const float* __restrict__ X, const long long* __restrict__ cu_rows,
                                                      const float* __restrict__ Q, int P, int q_prenorm, float scale,
                                                      const float* __restrict__ ml, const float* __restrict__ O,
                                                      const float* __restrict__ dO, float* __restrict__ dX) {
-    constexpr int D = VLSA_D, ROWS = 128;
+    constexpr int D = VLSA_D, ROWS = 128, RW = 4;
     extern __shared__ __align__(16) float s_dx[];            // [P][D] qdir | [P][D] dO_b | [P] m | [P] 1/l | [P] delta
     float* s_qd = s_dx;
     float* s_g = s_dx + size_t(P) * D;
@@ -259,12 +262,12 @@ __global__ void __launch_bounds__(256) agg_dx_kernel(const float* __restrict__ X
     const long long r0 = cu_rows[b] + (long long)blockIdx.x * ROWS, rend = cu_rows[b + 1];
     if (r0 >= rend) return;                                    // block-uniform
     load_normalized_rows(Q, P, s_qd, q_prenorm != 0);
-    for (int i = tid; i < P * D; i += 256) s_g[i] = __ldg(dO + size_t(b) * P * D + i);
+    for (int i = tid; i < P * D; i += 128) s_g[i] = __ldg(dO + size_t(b) * P * D + i);
     if (tid < P) {
         s_mm[tid] = ml[(size_t(b) * P + tid) * 2];
         s_il[tid] = 1.f / ml[(size_t(b) * P + tid) * 2 + 1];
     }
-    for (int p = warp; p < P; p += 8) {                        // delta_p = dO_p . O_p
+    for (int p = warp; p < P; p += 4) {                        // delta_p = dO_p . O_p
         const size_t at = (size_t(b) * P + p) * D;
         float a = 0.f;
         for (int k = lane; k < D; k += 32) a += __ldg(dO + at + k) * __ldg(O + at + k);
@@ -273,49 +276,82 @@ __global__ void __launch_bounds__(256) agg_dx_kernel(const float* __restrict__ X
     }
     __syncthreads();
     const long long r1 = r0 + ROWS < rend ? r0 + ROWS : rend;
-    for (long long n = r0 + warp; n < r1; n += 8) {
-        float x[16], dx[16];
-        load_row16<float>(X + n * D, lane, x);
-        float ss = 0.f;
+    for (long long n0 = r0 + warp * RW; n0 < r1; n0 += 4 * RW) {
+        float2 x[RW][8], dx[RW][8];
+        float inv[RW], tsum[RW];
+        bool clamped[RW];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { ss += x[i] * x[i]; dx[i] = 0.f; }
-        ss = warp_sum(ss);
-        const float nr = sqrtf(ss);
-        const bool clamped = nr < VLSA_NORM_EPS;
-        const float inv = 1.f / fmaxf(nr, VLSA_NORM_EPS);
-        float t = 0.f;
-        for (int p = 0; p < P; ++p) {
-            float qa = 0.f, ga = 0.f;
+        for (int r = 0; r < RW; ++r) {
+            const bool live = n0 + r < r1;                     // warp-uniform
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 q4 = *reinterpret_cast<const float4*>(s_qd + p * D + j * 128 + lane * 4);
-                const float4 g4 = *reinterpret_cast<const float4*>(s_g + p * D + j * 128 + lane * 4);
-                qa += q4.x * x[4 * j] + q4.y * x[4 * j + 1] + q4.z * x[4 * j + 2] + q4.w * x[4 * j + 3];
-                ga += g4.x * x[4 * j] + g4.y * x[4 * j + 1] + g4.z * x[4 * j + 2] + g4.w * x[4 * j + 3];
-            }
-            qa = warp_sum(qa);
-            ga = warp_sum(ga);
-            const float sv = scale * (qa * inv);
-            const float a = expf(sv - s_mm[p]) * s_il[p];                  // A_pn (deepmil.py:198)
-            const float ds = a * (ga - s_dl[p]);
-            const float c = scale * ds * inv;
-            t += ds * sv;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 q4 = *reinterpret_cast<const float4*>(s_qd + p * D + j * 128 + lane * 4);
-                const float4 g4 = *reinterpret_cast<const float4*>(s_g + p * D + j * 128 + lane * 4);
-                dx[4 * j + 0] += a * g4.x + c * q4.x; dx[4 * j + 1] += a * g4.y + c * q4.y;
-                dx[4 * j + 2] += a * g4.z + c * q4.z; dx[4 * j + 3] += a * g4.w + c * q4.w;
+                const float4 v = live ? __ldg(reinterpret_cast<const float4*>(X + (n0 + r) * D + j * 128 + lane * 4))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                x[r][2 * j] = make_float2(v.x, v.y);
+                x[r][2 * j + 1] = make_float2(v.z, v.w);
             }
         }
-        const float k = clamped ? 0.f : t * inv * inv;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(dX + n * D + j * 128 + lane * 4) =
-                make_float4(dx[4 * j] - k * x[4 * j], dx[4 * j + 1] - k * x[4 * j + 1], dx[4 * j + 2] - k * x[4 * j + 2],
-                            dx[4 * j + 3] - k * x[4 * j + 3]);
+        for (int r = 0; r < RW; ++r) {
+            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s2 = __ffma2_rn(x[r][i], x[r][i], s2); dx[r][i] = make_float2(0.f, 0.f); }
+            const float nr = sqrtf(warp_sum(s2.x + s2.y));
+            clamped[r] = nr < VLSA_NORM_EPS;
+            inv[r] = 1.f / fmaxf(nr, VLSA_NORM_EPS);
+            tsum[r] = 0.f;
+        }
+        for (int p = 0; p < P; ++p) {
+            float2 q2[8], g2[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 q4 = *reinterpret_cast<const float4*>(s_qd + p * D + j * 128 + lane * 4);
+                const float4 g4 = *reinterpret_cast<const float4*>(s_g + p * D + j * 128 + lane * 4);
+                q2[2 * j] = make_float2(q4.x, q4.y); q2[2 * j + 1] = make_float2(q4.z, q4.w);
+                g2[2 * j] = make_float2(g4.x, g4.y); g2[2 * j + 1] = make_float2(g4.z, g4.w);
+            }
+            float qa[RW], ga[RW];
+#pragma unroll
+            for (int r = 0; r < RW; ++r) {
+                float2 aq = make_float2(0.f, 0.f), ag = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { aq = __ffma2_rn(q2[i], x[r][i], aq); ag = __ffma2_rn(g2[i], x[r][i], ag); }
+                qa[r] = aq.x + aq.y;
+                ga[r] = ag.x + ag.y;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {                 // eight interleaved warp reductions
+#pragma unroll
+                for (int r = 0; r < RW; ++r) {
+                    qa[r] += __shfl_xor_sync(0xffffffffu, qa[r], o);
+                    ga[r] += __shfl_xor_sync(0xffffffffu, ga[r], o);
+                }
+            }
+            const float mp = s_mm[p], ilp = s_il[p], dlp = s_dl[p];
+#pragma unroll
+            for (int r = 0; r < RW; ++r) {
+                const float sv = scale * (qa[r] * inv[r]);
+                const float a = expf(sv - mp) * ilp;                           // A_pn (deepmil.py:198)
+                const float ds = a * (ga[r] - dlp);
+                const float c = scale * ds * inv[r];
+                tsum[r] += ds * sv;
+                const float2 a2 = make_float2(a, a), c2 = make_float2(c, c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dx[r][i] = __ffma2_rn(c2, q2[i], __ffma2_rn(a2, g2[i], dx[r][i]));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+            if (n0 + r >= r1) break;                           // warp-uniform
+            const float k = clamped[r] ? 0.f : -tsum[r] * inv[r] * inv[r];
+            const float2 k2 = make_float2(k, k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 lo = __ffma2_rn(k2, x[r][2 * j], dx[r][2 * j]), hi = __ffma2_rn(k2, x[r][2 * j + 1], dx[r][2 * j + 1]);
+                *reinterpret_cast<float4*>(dX + (n0 + r) * D + j * 128 + lane * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+        }
     }
 }
-
 
 }  // namespace vlsa
