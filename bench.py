@@ -250,7 +250,7 @@ def main():
     ws = ops._workspace(plan, P, dev)
     use_tc = args.dtype == "fp32" and P > 5 and os.environ.get("VLSA_AGG_VARIANT", "")[:1] != "s" \
         or os.environ.get("VLSA_AGG_VARIANT", "")[:1] == "t" and args.dtype == "fp32"
-    kernel_name = "agg_tc_kernel<false> (tcgen05)" if use_tc else "agg_simt_kernel<P,false,XT>"
+    kernel_name = "agg_tc_kernel<false> (tcgen05)" if use_tc else "agg_simt_kernel<P,0,XT>"
     two_level = plan.total_chunks >= 8 * nb
     # streaming kernel, [merge level 1,] merge, adapter, head
     launches_per_step = 4 + (1 if two_level else 0)
