@@ -21,4 +21,20 @@ for variant in (os.environ.get("DEV_VARIANTS", "tc,simt").split(",")):
         total.backward()
         torch.cuda.synchronize()
         print(variant, P, sizes, float(total), float(res.grad.abs().sum()), flush=True)
+# variant path: pooled forward, per-prototype-gradient backward (one launch and grouped), dX kernel
+ops.set_agg_variant(None)
+for P, sizes, prenorm in ((3, [513, 64, 1], False), (12, [700, 37], True), (16, [300, 0, 129], False)):
+    g = torch.Generator().manual_seed(P)
+    bags = [synth.make_bag("g1", n, 300 + i) for i, n in enumerate(sizes)]
+    X = torch.cat(bags, 0).to(dev).requires_grad_(True)
+    plan = ops.make_plan(sizes, dev)
+    Q = torch.randn(P, 512, generator=g).to(dev).requires_grad_(True)
+    dO = torch.randn(len(sizes), P, 512, generator=g).to(dev)
+    O, ml = ops.pooled(X, plan, Q, prenorm)
+    dX, dQ = torch.autograd.grad(O, (X, Q), dO)
+    W = (torch.randn(512, 512, generator=g) / 22).to(dev).requires_grad_(True)
+    f, _ = ops.encode(X, plan, Q, W, torch.zeros(512, device=dev), None, prenorm)
+    dX2, = torch.autograd.grad(f.sum(), X)
+    torch.cuda.synchronize()
+    print("variant", P, sizes, float(O.abs().sum()), float(dX.abs().sum()), float(dQ.abs().sum()), float(dX2.abs().sum()), flush=True)
 print("done")
