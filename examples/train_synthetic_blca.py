@@ -49,6 +49,10 @@ def main():
     ap.add_argument("--P", type=int, default=12)
     ap.add_argument("--R", type=int, default=12)
     ap.add_argument("--seed", type=int, default=0)
+    # VLFAN switches no shipped config enables; all of them run on the same streaming kernels
+    ap.add_argument("--gated-query", action="store_true")
+    ap.add_argument("--query-pooling", default="mean", choices=["mean", "max", "weight", "attention", "gated_attention"])
+    ap.add_argument("--feat-proj", action="store_true")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -105,11 +109,13 @@ def main():
     cfg = {"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4,
            "opt_weight_decay": 1e-5, "bp_every_batch": 32, "net_output_converter": "softmax"}
     net = VLSA(text_encoder_cfg={"name": "mahmoodlab/conch"},
-               image_encoder_cfg=dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, query="Text", num_query=P,
-                                      gated_query=False, query_pooling="mean", pred_head="default",
-                                      query_text_method="TaskRes", query_text_res_ratio=0.5),
+               image_encoder_cfg=dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=args.feat_proj, query="Text",
+                                      num_query=P, gated_query=args.gated_query, query_pooling=args.query_pooling,
+                                      pred_head="default", query_text_method="TaskRes", query_text_res_ratio=0.5),
                prompt_learner_cfg={"name": "CoOp"}, text_features=pr["text_features"],
-               query_prompt_features=pr["prompt_features"], vlsa_api="CONCH", path_clip_model=None)
+               query_prompt_features=pr["prompt_features"], vlsa_api="CONCH", path_clip_model=None,
+               query_neg_prompt_features=torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1)
+               if args.gated_query else None)
     handler = VLSAHandler(cfg, net=net, device=dev)
     loader = OneBagLoader()
     bs = cfg["bp_every_batch"]
