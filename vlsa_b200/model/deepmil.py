@@ -143,6 +143,15 @@ class VLFAN(nn.Module):
     def get_coattn_logit_scale(self):
         return self.coattn_logit_scale.exp()
 
+    def coattn_scale_float(self) -> float:
+        """exp(coattn_logit_scale) as the Python float the kernels take; re-evaluated when the tensor is replaced or
+        modified in place."""
+        t = self.coattn_logit_scale
+        key = (id(t), t._version)
+        if getattr(self, "_scale_key", None) != key:
+            self._scale_key, self._scale_val = key, float(t.exp())
+        return self._scale_val
+
     def reset_query(self, query_network):
         assert self.query_type != "Parameter", f"Cannot override Q (query) for query_type ({self.query_type})."
         self.Q = query_network
@@ -206,7 +215,7 @@ class VLFAN(nn.Module):
         if self.feat_proj is not None:
             X = self.feat_proj(X.float())                                  # deepmil.py:176-179, [sum N_i, D]
         Qd, prenorm = self.query_directions()
-        scale = float(self.get_coattn_logit_scale())
+        scale = self.coattn_scale_float()
         if self.mean_linear_tail:
             f, ml = ops.encode(X, plan, Qd, self.visual_adapter.weight, self.visual_adapter.bias, scale, prenorm)
             return f, ml, None, X
@@ -222,7 +231,7 @@ class VLFAN(nn.Module):
         f, ml, pooled_ext, Xs = self.encode_packed_ext(Xp, plan)
         if ret_with_attn:
             Qd, prenorm = self.query_directions()
-            A = ops.attention_scores(Xs.detach(), Qd.detach().contiguous(), ml[0], float(self.get_coattn_logit_scale()),
+            A = ops.attention_scores(Xs.detach(), Qd.detach().contiguous(), ml[0], self.coattn_scale_float(),
                                      q_prenorm=prenorm).unsqueeze(0)
             if pooled_ext is not None:
                 return f, (A, pooled_ext.detach())                  # deepmil.py:208-209

@@ -65,7 +65,8 @@ class PromptAdapter(nn.Module):
         return raw
 
     def forward(self):
-        prompt_features = self.prompt_features.clone()
+        # (the reference clones the buffer first; every branch below builds a new tensor anyway, except 'default')
+        prompt_features = self.prompt_features
         if self.method == "TaskRes":
             text_features = self.res_ratio * self.residual_features + prompt_features      # prompt_adapter.py:125-126
             if hasattr(self, "neg_prompt_features"):                                       # prompt_adapter.py:127-134
@@ -78,4 +79,4 @@ class PromptAdapter(nn.Module):
             if hasattr(self, "neg_prompt_features"):
                 prompt_features = torch.cat([prompt_features, self.neg_prompt_features.clone()], dim=0)
             return self.fc(prompt_features)
-        return prompt_features
+        return prompt_features.clone()

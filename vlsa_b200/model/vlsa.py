@@ -77,6 +77,12 @@ class VLSA(nn.Module):
             return self._text_fn()
         raise RuntimeError("no source of ordinal prompt embeddings: pass text_features= to VLSA(...)")
 
+    def _text_features_for_kernels(self):
+        """forward_text_only() without the defensive clone of the frozen buffer (the kernels only read it)."""
+        if hasattr(self, "pretrained_text_features"):
+            return self.pretrained_text_features
+        return self.forward_text_only()
+
     def encode_instances(self, X):
         return self.mil_encoder(X)
 
@@ -88,7 +94,7 @@ class VLSA(nn.Module):
         if X.dim() != 3 or X.shape[0] != 1:
             raise AssertionError("X must be [1, N, feat_dim]")       # deepmil.py:175
         Xp = X[0].contiguous()
-        text_features = self.forward_text_only()
+        text_features = self._text_features_for_kernels()
         if isinstance(self.mil_encoder, deepmil.FeatMIL):
             if Xp.shape[0] > 1 and self.mil_encoder.pooling not in ("mean", "max"):
                 _, pooled = ops.logit_pool(Xp, text_features.detach().contiguous(), self.logit_scale,
@@ -114,12 +120,12 @@ class VLSA(nn.Module):
             return logits, g, Tn, torch.softmax(logits.detach(), dim=-1), ml
         Qd, prenorm = enc.query_directions()
         return ops.aggregate(Xp, plan, Qd, enc.visual_adapter.weight, enc.visual_adapter.bias,
-                             text_features, self.logit_scale, float(enc.get_coattn_logit_scale()), prenorm)
+                             text_features, self.logit_scale, enc.coattn_scale_float(), prenorm)
 
     def forward_packed(self, X_packed: torch.Tensor, plan: "ops.BagPlan", text_features: torch.Tensor | None = None):
         """All bags of one step in one launch: X_packed [sum N_i, 512] + plan -> (logits [B,R], g [B,512], Tn,
         incidence [B,R]).  Numerically identical to looping ``forward`` over the bags."""
         if text_features is None:
-            text_features = self.forward_text_only()
+            text_features = self._text_features_for_kernels()
         logits, g, Tn, inc, _ = self._fused(X_packed, plan, text_features)
         return logits, g, Tn, inc

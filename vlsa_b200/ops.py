@@ -7,7 +7,9 @@ in libvlsa_b200.so; there is no PyTorch fallback.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
+from collections import OrderedDict
 from dataclasses import dataclass
 
 import numpy as np
@@ -20,6 +22,7 @@ MAX_P = 16
 MAX_R = 32
 
 
+@functools.lru_cache(maxsize=1)
 def coattn_scale() -> float:
     """exp(fp32(log 100)) as the reference computes it (model/deepmil.py:122,125)."""
     return float((torch.ones([]) * np.log(100)).exp())
@@ -85,8 +88,38 @@ class BagPlan:
         return int(self.chunk_start_host[-1])
 
 
+_PLAN_CACHE: "OrderedDict[tuple, tuple[BagPlan, torch.cuda.Event | None]]" = OrderedDict()
+_PLAN_CACHE_MAX = 4096          # an entry is two small host arrays + one 512-byte device block
+
+
 def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
-    """Host-side schedule for a batch of bags with the given row counts (vlsa_agg_plan)."""
+    """Host-side schedule for a batch of bags with the given row counts (vlsa_agg_plan).
+
+    Plans are immutable and cached by (sizes, device, sms): the per-bag loops of the reference call ``VLSA.forward``
+    once per slide and epoch, and at a few thousand rows the schedule (numpy + ctypes + one H2D copy, ~45 us) costs more
+    than the kernels.  A hit from another stream than the one that uploaded the plan waits on the upload's event."""
+    dev = torch.device(device)
+    sizes_t = tuple(int(n) for n in bag_sizes)
+    key = (sizes_t, dev.type, dev.index if dev.index is not None else (torch.cuda.current_device() if dev.type == "cuda" else -1), sms)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None:
+        _PLAN_CACHE.move_to_end(key)
+        plan, uploaded = hit
+        if uploaded is not None and not uploaded.query():
+            torch.cuda.current_stream(dev).wait_event(uploaded)
+        return plan
+    plan = _build_plan(sizes_t, dev, sms)
+    uploaded = None
+    if dev.type == "cuda":
+        uploaded = torch.cuda.Event()
+        uploaded.record(torch.cuda.current_stream(dev))
+    _PLAN_CACHE[key] = (plan, uploaded)
+    if len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def _build_plan(bag_sizes, device, sms: int | None) -> BagPlan:
     sizes = np.asarray(list(bag_sizes), dtype=np.int64)
     if (sizes < 0).any():
         raise ValueError("negative bag size")
@@ -99,12 +132,15 @@ def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
     rc = _lib.lib().vlsa_agg_plan(cu.ctypes.data_as(C.POINTER(C.c_int64)), len(sizes), int(sms), C.byref(chunk_rows),
                                   cs.ctypes.data_as(C.POINTER(C.c_int32)))
     _lib.check(rc, "vlsa_agg_plan")
-    # one small pinned staging buffer -> async H2D on the current stream
+    # one small staging array -> one H2D copy on the current stream.  Batched steps keep a pinned staging buffer (a
+    # truly asynchronous copy next to the big X copy of the loader); the per-bag calls of the reference's loops use
+    # pageable memory, which the runtime stages itself and which is cheaper than a pinned allocation per plan.
     stage = torch.empty(len(cu) * 2, dtype=torch.int64)
-    if torch.device(device).type == "cuda":
+    if torch.device(device).type == "cuda" and len(sizes) > 4:
         stage = stage.pin_memory()
-    stage[: len(cu)] = torch.from_numpy(cu)
-    stage[len(cu):].view(torch.int32)[: len(cs)] = torch.from_numpy(cs)
+    stage_np = stage.numpy()
+    stage_np[: len(cu)] = cu
+    stage_np[len(cu):].view(np.int32)[: len(cs)] = cs
     dev = stage.to(device, non_blocking=True)
     return BagPlan(cu, cs, int(chunk_rows.value), dev[: len(cu)], dev[len(cu):].view(torch.int32)[: len(cs)])
 
@@ -346,9 +382,18 @@ def encode(X, plan: BagPlan, Q, W, bias, scale: float | None = None, q_prenorm: 
     return _EncodeFn.apply(X, plan, Q, W, bias, scale, q_prenorm)
 
 
+def _needs_graph(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 def aggregate(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None, q_prenorm: bool = False):
     """Fused VLSA forward on a packed batch.  Returns (logits [B,R], g [B,D], Tn [R,D], incidence [B,R], ml).
     ``q_prenorm``: the rows of Q are the gated query's difference rows, used without normalisation."""
+    if not _needs_graph(Q, W, bias, T, logit_scale):
+        # inference: same launches, no autograd node, nothing kept for a backward
+        out = aggregate_forward_raw(X, plan, *(t.detach().contiguous() for t in (Q, W, bias, T, logit_scale)),
+                                    need_bwd=False, scale=scale, q_prenorm=q_prenorm)
+        return out["logits"], out["g"], out["Tn"], out["incidence"], out["ml"]
     return _AggregateFn.apply(X, plan, Q, W, bias, T, logit_scale, scale, q_prenorm)
 
 
