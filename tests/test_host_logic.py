@@ -306,3 +306,27 @@ def test_flat_bucket_attached_gradients_alias_the_bucket():
     loss(b, 1.0).backward()
     att.pack(None)
     assert torch.allclose(att.flat[:12], b[0].grad.reshape(-1))
+
+
+def test_plan_cache_returns_the_same_immutable_schedule():
+    """ops.make_plan caches by (sizes, device, sms): the per-bag loops of the reference ask for the same schedule once
+    per slide and epoch.  CPU device = planning only (no upload event)."""
+    import numpy as np
+    from vlsa_b200 import ops
+    a = ops.make_plan([1000, 37, 2798], "cpu", sms=148)
+    b = ops.make_plan(np.array([1000, 37, 2798]), "cpu", sms=148)          # numpy ints hash like Python ints
+    c = ops.make_plan([1000, 37, 2798], "cpu", sms=8)
+    d = ops.make_plan([1000, 37, 2799], "cpu", sms=148)
+    assert a is b and a is not c and a is not d
+    assert a.total_rows == 3835 and d.total_rows == 3836 and a.num_bags == 3
+    assert a.chunk_start_host[0] == 0 and a.total_chunks == int(a.chunk_start_host[-1])
+    before = len(ops._PLAN_CACHE)
+    old_max, ops._PLAN_CACHE_MAX = ops._PLAN_CACHE_MAX, before + 2
+    try:
+        for n in range(5):
+            ops.make_plan([5000 + n], "cpu", sms=148)
+        assert len(ops._PLAN_CACHE) <= before + 2                          # least recently used entries are dropped
+    finally:
+        ops._PLAN_CACHE_MAX = old_max
+    with pytest.raises(ValueError):
+        ops.make_plan([10, -1], "cpu")
