@@ -43,11 +43,45 @@ def parse():
     return ap.parse_args()
 
 
+def _find_hbm_peak(obj, path=""):
+    """All (key path, GB/s) candidates for an HBM bandwidth figure in a (possibly nested) MEASURED_PEAKS.json."""
+    found = []
+    if isinstance(obj, dict):
+        for k, v in obj.items():
+            kp = f"{path}.{k}" if path else str(k)
+            if isinstance(v, (int, float)) and not isinstance(v, bool):
+                name = kp.lower()
+                if "hbm" in name or "copy" in name or "dram" in name or "bandwidth" in name:
+                    val = float(v)
+                    if "tb" in name and val < 100:          # a TB/s figure
+                        val *= 1000.0
+                    if 1000.0 < val < 20000.0:              # plausible GB/s for one B200
+                        found.append((kp, val))
+            else:
+                found += _find_hbm_peak(v, kp)
+    elif isinstance(obj, list):
+        for i, v in enumerate(obj):
+            found += _find_hbm_peak(v, f"{path}[{i}]")
+    return found
+
+
 def measured_peaks():
+    """HBM peak for the roofline: the driver-written MEASURED_PEAKS.json when present (the streaming kernel is timed
+    alone, so the burst figure is preferred over a sustained one), else the profiling guide's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as fh:
-            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    try:
+        if os.path.exists(path):
+            with open(path) as fh:
+                data = json.load(fh)
+            if isinstance(data, dict) and isinstance(data.get("hbm_gbs"), (int, float)):
+                return float(data["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            cands = _find_hbm_peak(data)
+            if cands:
+                burst = [c for c in cands if "burst" in c[0].lower()]
+                key, val = (burst or cands)[0]
+                return val, f"measured (MEASURED_PEAKS.json {key})"
+    except (OSError, ValueError, TypeError):
+        pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
