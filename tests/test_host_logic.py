@@ -330,3 +330,21 @@ def test_plan_cache_returns_the_same_immutable_schedule():
         ops._PLAN_CACHE_MAX = old_max
     with pytest.raises(ValueError):
         ops.make_plan([10, -1], "cpu")
+
+
+def test_bench_reads_measured_peaks_in_any_layout(tmp_path, monkeypatch):
+    """bench.py's roofline denominator: the driver-written MEASURED_PEAKS.json when it is there (flat `hbm_gbs`, nested,
+    burst preferred for a kernel timed alone, TB/s keys), the profiling guide's fallback otherwise — never a crash."""
+    import json
+    import bench
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.measured_peaks()[0] == 6650.0
+    cases = (({"hbm_gbs": 6538.9, "bf16_tflops": 1500.0}, 6538.9),
+             ({"hbm": {"sustained_gbs": 6500.0, "burst_gbs": 7100.0}, "bf16": {"tflops": 1600.0}}, 7100.0),
+             ({"hbm_copy_tb_s": 6.6}, 6600.0), ({"unrelated": 1}, 6650.0), ("garbage", 6650.0))
+    for data, want in cases:
+        (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps(data))
+        got, source = bench.measured_peaks()
+        assert abs(got - want) < 1e-6, (data, got, source)
+    (tmp_path / "MEASURED_PEAKS.json").write_text("{not json")
+    assert bench.measured_peaks()[0] == 6650.0
