@@ -142,6 +142,8 @@ def _build_plan(bag_sizes, device, sms: int | None) -> BagPlan:
     stage_np[: len(cu)] = cu
     stage_np[len(cu):].view(np.int32)[: len(cs)] = cs
     dev = stage.to(device, non_blocking=True)
+    cu.flags.writeable = False          # plans are shared through the cache: nobody may edit one in place
+    cs.flags.writeable = False
     return BagPlan(cu, cs, int(chunk_rows.value), dev[: len(cu)], dev[len(cu):].view(torch.int32)[: len(cs)])
 
 
