@@ -348,3 +348,41 @@ def test_bench_reads_measured_peaks_in_any_layout(tmp_path, monkeypatch):
         assert abs(got - want) < 1e-6, (data, got, source)
     (tmp_path / "MEASURED_PEAKS.json").write_text("{not json")
     assert bench.measured_peaks()[0] == 6650.0
+
+
+def test_interpretation_utility_rejects_variant_encoders():
+    """The decoupled similarities assume mean pooling + Linear adapter; other VLFAN switches must fail loudly."""
+    from vlsa_b200 import synth
+    from vlsa_b200.model import VLSA
+    from vlsa_b200.utils import calc_text_img_similarity
+    pr = synth.make_params(4, 4, 5)
+    for extra in (dict(gated_query=True), dict(query_pooling="max"), dict(pred_head="Identity"), dict(use_feat_proj=True)):
+        img = dict(name="VLFAN", dim_in=512, use_feat_proj=False, query="Parameter", num_query=4)
+        img.update(extra)
+        net = VLSA({"name": "mahmoodlab/conch"}, img, {"name": "CoOp"}, text_features=pr["text_features"])
+        with pytest.raises(NotImplementedError):
+            calc_text_img_similarity(net, torch.randn(10, 512))
+
+
+def test_gated_query_directions_reproduce_the_reference_scores():
+    """What the kernels rely on for gated_query: A_[:, :-1] - A_[:, -1:] (model/deepmil.py:192-195) equals the scores of
+    the P difference rows Qn_p - Qn_gate used WITHOUT normalisation, and the gradient reaches all P + 1 raw rows."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200.model import VLFAN
+    torch.manual_seed(3)
+    enc = VLFAN(dim_in=512, use_feat_proj=False, num_query=5, gated_query=True).double()
+    X = torch.randn(1, 40, 512, dtype=torch.float64) + 0.5
+    Qd, prenorm = enc.query_directions()
+    assert prenorm and Qd.shape == (5, 512)
+    scale = torch.tensor(O.coattn_scale(), dtype=torch.float64)
+    S = scale * Qd @ torch.nn.functional.normalize(X[0], dim=-1).t()          # what the kernels compute from Qd
+    A = torch.softmax(S, dim=-1)
+    f_kernel_math = (A @ X[0]).mean(0, keepdim=True) @ enc.visual_adapter.weight.t() + enc.visual_adapter.bias
+    f_ref, A_ref, _, _ = O.vlfan_forward_variant(X, enc.Q, enc.visual_adapter.weight, enc.visual_adapter.bias,
+                                                 gated_query=True, scale=scale)
+    torch.testing.assert_close(A, A_ref[0], rtol=1e-10, atol=1e-14)
+    torch.testing.assert_close(f_kernel_math, f_ref, rtol=1e-10, atol=1e-12)
+    g1, = torch.autograd.grad(f_kernel_math.sum(), enc.Q, retain_graph=True)
+    g2, = torch.autograd.grad(f_ref.sum(), enc.Q)
+    torch.testing.assert_close(g1, g2, rtol=1e-8, atol=1e-12)
+    assert g1[-1].abs().max() > 0

@@ -60,8 +60,14 @@ def calc_text_img_similarity(model, X_feats, axis_softmax: str = "V", verbose: b
         X_feats = X_feats[0]
     dev = next(model.parameters()).device
     X = X_feats.to(dev).contiguous()
+    enc = model.mil_encoder
+    if not getattr(enc, "fused_tail", False) or enc.gated_query:
+        # the decoupling (utils/model_inference.py:115-131) rests on the mean over the prototypes and the Linear adapter:
+        # with another pooling, a gate row or a projection in front the per-prototype similarities no longer add up to
+        # the model's prediction, and the reference's own routine is undefined for them (P + 1 query rows)
+        raise NotImplementedError("calc_text_img_similarity needs the shipped VLFAN configuration "
+                                  "(query_pooling='mean', pred_head='default', no gated_query / feat_proj)")
     with torch.no_grad():
-        enc = model.mil_encoder
         T = model.forward_text_only().detach().contiguous()
         Q = enc.get_query().detach().contiguous()
         W, b = enc.visual_adapter.weight.detach(), enc.visual_adapter.bias.detach()
