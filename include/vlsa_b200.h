@@ -16,7 +16,8 @@
  *   - the library never allocates device memory: scratch comes in through `workspace`
  *     (size from the matching *_workspace_bytes query) and must stay alive until the stream reaches
  *     the end of the call;
- *   - no global mutable state: calls on different streams are independent;
+ *   - no global mutable state: calls on different streams are independent (the only process-wide data are
+ *     once-initialised caches of per-device launch attributes);
  *   - return value: 0 on success, a negative VLSA_E* code for argument errors, a positive
  *     cudaError_t for CUDA failures (vlsa_error_string decodes both).
  *   - feature dim D is fixed at 512 (vlsa_img_encoder_dim_in, config/IFMLE/tcga_blca/cfg_vlsa_conch.yaml:47);
@@ -38,6 +39,13 @@ extern "C" {
 
 #define VLSA_DTYPE_F32 0
 #define VLSA_DTYPE_BF16 1
+#define VLSA_DTYPE_MASK 0xff
+/* Optional bits OR-ed into x_dtype of the vlsa_agg_* calls: force the streaming kernel of an fp32 pass for THIS call
+ * (cross-checks in the parity tests; default = automatic: TMA-fed tcgen05 kernel for P > 5, CUDA-core kernel otherwise).
+ * All kernels compute the same function (model/deepmil.py:187-203). */
+#define VLSA_KERNEL_SIMT 0x100   /* CUDA-core kernel (agg_simt_kernel) */
+#define VLSA_KERNEL_TC 0x200     /* TMA-fed tcgen05 kernel (agg_tma_kernel) */
+#define VLSA_KERNEL_TC_REG 0x400 /* register-staged tcgen05 kernel of round 1 (agg_tc_kernel) */
 
 #define VLSA_EINVAL (-1)      /* bad argument (null pointer, P/R/D out of range, ...) */
 #define VLSA_EWORKSPACE (-2)  /* workspace too small */
@@ -45,15 +53,10 @@ extern "C" {
 
 #define VLSA_POOL_MEAN 0 /* 'logit_mean'  (deepmil.py:29-30) */
 #define VLSA_POOL_TOPK 1 /* 'logit_topK' / 'logit_max' = top-1 (deepmil.py:24-28) */
+#define VLSA_POOL_MAX 2  /* FeatMIL pooling 'max' over the patch FEATURES (deepmil.py:59-60); vlsa_feat_pool_fwd only */
 
 int vlsa_version(void);
 const char* vlsa_error_string(int code);
-/* Development / cross-check hook (process-wide, the only piece of global state in the library): which streaming
- * kernel serves fp32 passes.  -1 = automatic (tcgen05 kernel for P > 5, CUDA-core kernel otherwise), 0 = CUDA-core
- * kernel, 1 = tcgen05 kernel.  Both compute the same function (reference: model/deepmil.py:187-203); the parity
- * tests run every case through both. */
-int vlsa_debug_set_agg_variant(int variant);
-
 /* Host-only helper: split the bags of one call into row chunks for the streaming kernels.
  * cu_rows_host[B+1] are the row offsets of the bags inside the packed X.  Writes chunk_start_host[B+1]
  * (first chunk id of every bag; chunk_start_host[B] = total chunks) and *chunk_rows_out (rows per
@@ -69,13 +72,14 @@ size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P);
  *   v = mean_P(O); f = W v + b                                         (deepmil.py:136,204)
  *   g = f/|f|; Tn = T/|T|; logits = (exp(logit_scale) g) @ Tn^T        (vlsa.py:185-192)
  *   IF = softmax(logits)                                               (utils/func.py:44)
- * X is read exactly once.  out_ml / out_O / out_v / out_f are what vlsa_agg_bwd needs later
+ * X [total_rows, 512] holds the bags back to back (total_rows = cu_rows[B], passed by value because the TMA tensor map
+ * of the tcgen05 kernel is built on the host) and is read exactly once.  out_ml / out_O / out_v / out_f are what vlsa_agg_bwd needs later
  * (out_O may be NULL when no backward follows).  out_if and out_Tn may be NULL.
  * Encoder-only use (VLFAN.forward alone, deepmil.py:170-215): T = NULL stops after f; out_g, out_logits,
  * out_if, out_Tn are then ignored.
  * q_prenorm = 0 everywhere except the gated query (deepmil.py:192-195), which passes the P difference rows
  * Qn_p - Qn_gate with q_prenorm = 1: they enter the scores as they are (see vlsa_agg_pooled_fwd). */
-int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
@@ -84,7 +88,7 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
 /* Only the streaming kernel of vlsa_agg_fwd (the one launch that reads X): writes the per-chunk
  * online-softmax partials into `workspace` and nothing else.  Exists so that the dominant kernel can be
  * timed in isolation (bench.py roofline) and so that callers can overlap the epilogue themselves. */
-int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_partial_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                          int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale,
                          void* workspace, size_t workspace_bytes, void* stream);
 
@@ -98,7 +102,7 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, con
  * f, g, logits, d_logits, dT, dlogit_scale are ignored.
  * Outputs are overwritten (not accumulated): dQ [P,D], dW [D,D], db [D], dT [R,D], dlogit_scale [1].
  * With q_prenorm = 1, dQ is the gradient w.r.t. the rows as passed (no normalisation Jacobian). */
-int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
@@ -112,7 +116,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
  * q_prenorm = 0: qdir_p = Q_p / |Q_p| as in vlsa_agg_fwd.  q_prenorm = 1: qdir_p = Q_p as given — the gated query
  * passes Qn_p - Qn_gate, the difference of two unit rows (A_[:, :-1] - A_[:, -1:] is linear in the query).
  * Same plan and workspace as vlsa_agg_fwd.  out_ml [B,P,2], out_O [B,P,D]. */
-int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_pooled_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                         int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
                         void* workspace, size_t workspace_bytes, float* out_ml, float* out_O, void* stream);
 
@@ -120,7 +124,7 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
  *   dS_pn = A_pn (d_O_p . x_n - d_O_p . O_p),  dqdir_p = scale * sum_n dS_pn x_n / |x_n|,
  * dQ [P,D] = dqdir pushed through the row normalisation (q_prenorm = 0) or dqdir itself (q_prenorm = 1), summed
  * over the B bags.  One pass over X with 2 P + 1 dot products per row (CUDA-core kernel for every P and dtype). */
-int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_pooled_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                         int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
                         const float* ml, const float* O, const float* d_O, void* workspace, size_t workspace_bytes,
                         float* dQ, void* stream);
@@ -173,17 +177,32 @@ int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, i
                         int mode, int k, void* workspace, size_t workspace_bytes, float* out_logits,
                         int64_t* out_pred, void* stream);
 
+/* Zero-shot arm, FeatMIL pooling 'mean' | 'max' (model/deepmil.py:57-60 + model/vlsa.py:188-192), ONE bag:
+ *   f = mean | max over the N rows of X (column-wise); g = f/|f|; logits = (exp(logit_scale) g) @ (T/|T|)^T.
+ * A one-row bag under any pooling is the same computation (mean of one row).  mode = VLSA_POOL_MEAN | VLSA_POOL_MAX.
+ * out_f [512], out_g [512] (the returned image_features), out_logits [R], out_Tn [R,512] (may be NULL). */
+size_t vlsa_feat_pool_workspace_bytes(void);
+int vlsa_feat_pool_fwd(const void* X, int x_dtype, int64_t N, int mode, const float* T, int R, const float* logit_scale,
+                       void* workspace, size_t workspace_bytes, float* out_f, float* out_g, float* out_logits,
+                       float* out_Tn, void* stream);
+
+/* image_features of the logit-pooling zero-shot modes: the N patches L2-normalised (F.normalize, model/vlsa.py:188-189).
+ * out [N,512] fp32. */
+int vlsa_row_normalize(const void* X, int x_dtype, int64_t N, float* out, void* stream);
+
 /* Whole path with HOST buffers (what a caller holding CPU tensors — the reference's DataLoader output,
  * dataset/PatchWSI.py:197-215 + runner/vlsa_handler.py:205,322-330 — would call): stage the packed bags
  * X_host [total_rows, D] (pinned memory for a truly asynchronous copy) to the device on `stream_copy`,
  * run vlsa_agg_fwd on `stream_compute` once the copy has landed, and copy the incidence [B,R] (and raw
  * logits if out_logits_host != NULL) back to the host on `stream_compute`.  Parameters (Q, W, bias, T,
  * logit_scale) are DEVICE pointers (they live on the GPU between calls).  Returns after enqueueing;
- * synchronise `stream_compute` before reading the outputs.  `workspace` is device memory of at least
+ * synchronise `stream_compute` before reading the outputs.  With two streams the call orders them both ways (the
+ * copies wait for whatever `stream_compute` still does with `workspace`, the kernels wait for the copies), so a
+ * workspace may be reused by the next call without a host synchronisation.  `workspace` is device memory of at least
  * vlsa_forward_host_workspace_bytes(total_rows, B, P, x_dtype) bytes. */
 size_t vlsa_forward_host_workspace_bytes(int64_t total_rows, int B, int P, int x_dtype);
 int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_host, int B, const float* Q, int P,
-                      float coattn_scale, const float* W, const float* bias, const float* T, int R,
+                      int q_prenorm, float coattn_scale, const float* W, const float* bias, const float* T, int R,
                       const float* logit_scale, void* workspace, size_t workspace_bytes, float* out_if_host,
                       float* out_logits_host, void* stream_compute, void* stream_copy);
 

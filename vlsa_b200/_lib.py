@@ -20,23 +20,22 @@ c_i32p = C.c_void_p
 _SIGNATURES = {
     "vlsa_version": (C.c_int, []),
     "vlsa_error_string": (C.c_char_p, [C.c_int]),
-    "vlsa_debug_set_agg_variant": (C.c_int, [C.c_int]),
     "vlsa_agg_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32)]),
     "vlsa_agg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+    "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
-    "vlsa_agg_partial_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+    "vlsa_agg_partial_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                        C.c_float, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "vlsa_agg_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+    "vlsa_agg_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                C.c_int, C.c_float, c_f32p, c_f32p, C.c_int, c_f32p,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
                                c_f32p, c_f32p, c_f32p,
                                C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
-    "vlsa_agg_pooled_fwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+    "vlsa_agg_pooled_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                       C.c_int, C.c_float, C.c_void_p, C.c_size_t, c_f32p, c_f32p, C.c_void_p]),
-    "vlsa_agg_pooled_bwd": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
+    "vlsa_agg_pooled_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                       C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_void_p, C.c_size_t, c_f32p,
                                       C.c_void_p]),
     "vlsa_agg_pooled_bwd_dx": (C.c_int, [c_f32p, c_i64p, C.c_int, C.c_int64, c_f32p, C.c_int, C.c_int, C.c_float, c_f32p,
@@ -52,7 +51,11 @@ _SIGNATURES = {
     "vlsa_logit_pool_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_size_t, c_f32p, c_i64p, C.c_void_p]),
     "vlsa_forward_host_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
-    "vlsa_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, c_f32p, C.c_int, C.c_float,
+    "vlsa_feat_pool_workspace_bytes": (C.c_size_t, []),
+    "vlsa_feat_pool_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_f32p, C.c_int, c_f32p, C.c_void_p,
+                                     C.c_size_t, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),
+    "vlsa_row_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_void_p]),
+    "vlsa_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_int, c_f32p, C.c_int, C.c_int, C.c_float,
                                     c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

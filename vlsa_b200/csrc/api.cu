@@ -6,8 +6,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "agg_simt.cuh"
 #include "agg_tc.cuh"
+#include "agg_tma.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
@@ -119,26 +122,45 @@ static AggWorkspace carve(void* base, int total_chunks, int B, int P) {
     return w;
 }
 
+// Per-(kernel, device) launch attributes, set / queried once: cudaFuncSetAttribute and the occupancy query cost more
+// host time than the launch itself on the one-bag-per-call path.  Once-initialised caches of device facts, not state:
+// a value is written once and is the same for every caller.
+static constexpr int kMaxDevices = 64;
+template <typename K>
+static int kernel_slots(K kern, int threads, int smem, std::atomic<int>* cache) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    int v = cache[dev].load(std::memory_order_acquire);
+    if (v > 0) return v;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return -1;
+    if (occ < 1) occ = 1;
+    v = device_sm_count() * occ;
+    cache[dev].store(v, std::memory_order_release);
+    return v;
+}
+
 template <int P, int MODE, typename XT>
 static int launch_agg(const AggParams& prm, cudaStream_t st) {
     using C = AggCfg<P, MODE, XT>;
     auto kern = agg_simt_kernel<P, MODE, XT>;
-    VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
-    int occ = 1;
-    VLSA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::THREADS, C::SMEM));
-    if (occ < 1) occ = 1;
-    const int slots = device_sm_count() * occ;          // persistent CTAs: every resident slot, no second wave
+    static std::atomic<int> cache[kMaxDevices];
+    const int slots = kernel_slots(kern, C::THREADS, int(C::SMEM), cache);   // persistent CTAs: every resident slot, no second wave
+    if (slots <= 0) return static_cast<int>(cudaGetLastError());
     const int grid = prm.total_chunks < slots ? prm.total_chunks : slots;
     if (grid <= 0) return 0;
     kern<<<grid, C::THREADS, C::SMEM, st>>>(prm);
     return static_cast<int>(cudaGetLastError());
 }
 
+// register-staged tcgen05 kernel of round 1 (kept for cross-checks: VLSA_KERNEL_TC_REG)
 template <bool BWD>
 static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
     using C = TcCfg;
     auto kern = agg_tc_kernel<BWD>;
-    VLSA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+    static std::atomic<int> cache[kMaxDevices];
+    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
     const int sms = device_sm_count();
     const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
     if (grid <= 0) return 0;
@@ -146,39 +168,77 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
-// Which streaming kernel serves an fp32 pass (forward or backward): the tcgen05 variant or the CUDA-core one.
-// Default: tensor cores for P > 5 (the CUDA-core kernel is faster at P <= 5).  Cross-checking hooks:
-// the environment variable VLSA_AGG_VARIANT=simt|tc and vlsa_debug_set_agg_variant() force one of them.
-#include <atomic>
-static std::atomic<int> g_agg_variant{[] {
-    const char* e = getenv("VLSA_AGG_VARIANT");
-    if (!e) return -1;
-    if (e[0] == 't') return 1;
-    if (e[0] == 's') return 0;
-    return -1;
-}()};
-static bool agg_use_tc(int P, int x_dtype) {
-    if (x_dtype != VLSA_DTYPE_F32) return false;
-    const int forced = g_agg_variant.load(std::memory_order_relaxed);
-    if (forced >= 0) return forced == 1;
-    return P > 5;
-}
-
-// prototypes per launch of the per-prototype-gradient backward (development override: VLSA_GEN_GROUP=1..16)
-static int gen_group_size() {
-    static const int g = [] {
-        const char* e = getenv("VLSA_GEN_GROUP");
-        const int v = e ? atoi(e) : 0;
-        return (v >= 1 && v <= VLSA_MAX_P) ? v : 8;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
     }();
-    return g;
+    return fn;
 }
 
-static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t st) {
-    if (agg_use_tc(P, x_dtype)) return launch_agg_tc<false>(prm, P, st);
+// TMA-fed tcgen05 kernel: X [total_rows, 512] fp32 as a 2-D tensor, box = 16 rows x 64 columns (one slot of a tile)
+template <bool BWD>
+static int launch_agg_tma(const AggParams& prm, int P, long long total_rows, cudaStream_t st) {
+    using C = TmaCfg;
+    if (total_rows <= 0 || total_rows > 0x7fffffffLL) return VLSA_EINVAL;
+    if (reinterpret_cast<uintptr_t>(prm.X) & 15u) return VLSA_EINVAL;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return VLSA_EUNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {cuuint64_t(VLSA_D), cuuint64_t(total_rows)};
+    const cuuint64_t gstr[1] = {cuuint64_t(VLSA_D) * sizeof(float)};
+    const cuuint32_t box[2] = {64u, cuuint32_t(C::TR)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(prm.X), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return VLSA_EINVAL;
+    auto kern = agg_tma_kernel<BWD>;
+    static std::atomic<int> cache[kMaxDevices];
+    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
+    const int sms = device_sm_count();
+    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    if (grid <= 0) return 0;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P, tmap);
+    return static_cast<int>(cudaGetLastError());
+}
+
+// Which streaming kernel serves a pass.  Default: the TMA-fed tcgen05 kernel for fp32 rows and P > 5 (the CUDA-core
+// kernel is at the HBM roofline for P <= 5); bf16 rows run on CUDA cores.  The caller can force a
+// kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
+enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTcReg = 2 };
+static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
+    const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
+    if (dtype != VLSA_DTYPE_F32) return kAggSimt;
+    if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
+    if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTma;
+    if (x_dtype_flags & VLSA_KERNEL_TC_REG) return kAggTcReg;
+    return P > 5 ? kAggTma : kAggSimt;
+}
+static bool dtype_ok(int x_dtype_flags) {
+    const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
+    return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
+           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_KERNEL_TC_REG)) == 0;
+}
+
+// prototypes per launch of the per-prototype-gradient backward (measured best, profiles/variant_time_r01.json)
+static constexpr int kGenGroup = 8;
+
+static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long total_rows, cudaStream_t st) {
+    const AggKernel k = agg_kernel_choice(P, x_dtype);
+    if (k == kAggTma) return launch_agg_tma<false>(prm, P, total_rows, st);
+    if (k == kAggTcReg) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
-        if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
+        if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
         else rc = launch_agg<kP, 0, __nv_bfloat16>(prm, st);
     });
     return rc;
@@ -186,13 +246,13 @@ static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, cudaStream_t
 
 extern "C" {
 
-int vlsa_version(void) { return 102; }
+int vlsa_version(void) { return 200; }
 
-int vlsa_debug_set_agg_variant(int variant) {
-    if (variant < -1 || variant > 1) return VLSA_EINVAL;
-    g_agg_variant.store(variant, std::memory_order_relaxed);
-    return 0;
+#ifdef VLSA_TMA_PROF
+int vlsa_debug_read_prof(long long* out_host) {          // development builds only
+    return static_cast<int>(cudaMemcpyFromSymbol(out_host, vlsa::g_tma_prof, sizeof(long long) * 32));
 }
+#endif
 
 const char* vlsa_error_string(int code) {
     if (code == 0) return "success";
@@ -239,7 +299,7 @@ size_t vlsa_agg_workspace_bytes(int total_chunks, int B, int P) {
     return carve(nullptr, total_chunks, B, P).bytes + 256;
 }
 
-int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* bias, const float* T, int R, const float* logit_scale, void* workspace,
                  size_t workspace_bytes, float* out_v, float* out_f, float* out_g, float* out_logits,
@@ -249,9 +309,9 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if (T && (!logit_scale || !out_g || !out_logits || R < 1 || R > VLSA_MAX_R)) return VLSA_EINVAL;
     if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
-    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (!dtype_ok(x_dtype)) return VLSA_EUNSUPPORTED;
     if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
-    if (total_chunks > 0 && (!X || !workspace)) return VLSA_EINVAL;
+    if (total_chunks > 0 && (!X || !workspace || total_rows <= 0)) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
     if (total_chunks > 0 && (base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes)
@@ -264,7 +324,7 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     prm.q_prenorm = q_prenorm;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
 
-    int rc = launch_agg_fwd(prm, P, x_dtype, st);
+    int rc = launch_agg_fwd(prm, P, x_dtype, total_rows, st);
     if (rc) return rc;
     const int S = merge_fwd_splits(total_chunks, B, P);
     if (S > 0) {
@@ -287,14 +347,14 @@ int vlsa_agg_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     return 0;
 }
 
-int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_partial_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                          int chunk_rows, int total_chunks, const float* Q, int P, float coattn_scale,
                          void* workspace, size_t workspace_bytes, void* stream) {
     if (B == 0 || total_chunks == 0) return 0;
     if (!X || !cu_rows || !chunk_start || !Q || !workspace) return VLSA_EINVAL;
     if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
-    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (!dtype_ok(x_dtype) || total_rows <= 0) return VLSA_EUNSUPPORTED;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
     if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
@@ -303,10 +363,10 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, const int64_t* cu_rows, con
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return launch_agg_fwd(prm, P, x_dtype, st);
+    return launch_agg_fwd(prm, P, x_dtype, total_rows, st);
 }
 
-int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                  int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale, const float* W,
                  const float* T, int R, const float* logit_scale, const float* v, const float* f, const float* g,
                  const float* logits, const float* ml, const float* O, const float* d_logits, const float* d_g,
@@ -318,9 +378,9 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     if (!T && !d_f) return VLSA_EINVAL;
     if (B < 1 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
-    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (!dtype_ok(x_dtype)) return VLSA_EUNSUPPORTED;
     if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
-    if (total_chunks > 0 && !X) return VLSA_EINVAL;
+    if (total_chunks > 0 && (!X || total_rows <= 0)) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
     if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
@@ -347,12 +407,16 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta; prm.q_prenorm = q_prenorm;
     int rc = 0;
-    if (agg_use_tc(P, x_dtype)) {
+    const AggKernel kern = total_chunks > 0 ? agg_kernel_choice(P, x_dtype) : kAggSimt;
+    if (kern == kAggTma) {
+        rc = launch_agg_tma<true>(prm, P, total_rows, st);
+        if (rc) return rc;
+    } else if (kern == kAggTcReg) {
         rc = launch_agg_tc<true>(prm, P, st);
         if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {
-            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 1, float>(prm, st);
+            if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 1, float>(prm, st);
             else rc = launch_agg<kP, 1, __nv_bfloat16>(prm, st);
             if (rc) return rc;
         });
@@ -369,7 +433,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32
     return 0;
 }
 
-int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_pooled_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                         int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
                         void* workspace, size_t workspace_bytes, float* out_ml, float* out_O, void* stream) {
     if (B == 0) return 0;
@@ -377,8 +441,8 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     if (B < 0 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
-    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
-    if (total_chunks > 0 && (!X || !workspace)) return VLSA_EINVAL;
+    if (!dtype_ok(x_dtype)) return VLSA_EUNSUPPORTED;
+    if (total_chunks > 0 && (!X || !workspace || total_rows <= 0)) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
     if (total_chunks > 0 && (base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes)
@@ -388,7 +452,7 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
     prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
-    int rc = launch_agg_fwd(prm, P, x_dtype, st);
+    int rc = launch_agg_fwd(prm, P, x_dtype, total_rows, st);
     if (rc) return rc;
     const int S = merge_fwd_splits(total_chunks, B, P);
     if (S > 0) {
@@ -405,7 +469,7 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     return 0;
 }
 
-int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, const int32_t* chunk_start, int B,
+int vlsa_agg_pooled_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* cu_rows, const int32_t* chunk_start, int B,
                         int chunk_rows, int total_chunks, const float* Q, int P, int q_prenorm, float coattn_scale,
                         const float* ml, const float* O, const float* d_O, void* workspace, size_t workspace_bytes,
                         float* dQ, void* stream) {
@@ -413,7 +477,8 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     if (B < 1 || P < 1 || P > VLSA_MAX_P || chunk_rows <= 0 || chunk_rows % kRowTile || total_chunks < 0)
         return VLSA_EINVAL;
     if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
-    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    if (!dtype_ok(x_dtype)) return VLSA_EUNSUPPORTED;
+    (void)total_rows;                                          // this pass runs on the CUDA-core kernel for every P
     if (total_chunks > 0 && !X) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);
@@ -429,7 +494,7 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
     // 2 P + 1 dots per row and 2 P resident rows outgrow registers and shared memory beyond P = 8 (one launch at
     // P = 12: 4.0 ms for 32 x 50k rows, against 1.3 ms at P = 8), and prototypes are independent in this pass: serve
     // them in balanced groups of <= 8, one launch and one read of X per group, each with its own slice of the partials.
-    const int group = gen_group_size();
+    const int group = kGenGroup;
     const int ngroups = (P + group - 1) / group;
     for (int gi = 0, p0 = 0; gi < ngroups; ++gi) {
         const int pg = (P - p0 + (ngroups - gi) - 1) / (ngroups - gi);       // balanced: 12 -> 6+6, 9 -> 5+4
@@ -439,7 +504,7 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, const int64_t* cu_rows, cons
         prm.delta = ws.delta + p0; prm.part_O = part;
         int rc = 0;
         VLSA_DISPATCH_P(pg, {
-            if (x_dtype == VLSA_DTYPE_F32) rc = launch_agg<kP, 2, float>(prm, st);
+            if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 2, float>(prm, st);
             else rc = launch_agg<kP, 2, __nv_bfloat16>(prm, st);
             if (rc) return rc;
         });
@@ -566,6 +631,49 @@ int vlsa_logit_pool_fwd(const void* X, int x_dtype, int64_t N, const float* T, i
     return 0;
 }
 
+size_t vlsa_feat_pool_workspace_bytes(void) { return size_t(296) * VLSA_D * sizeof(float) + 512; }
+
+int vlsa_feat_pool_fwd(const void* X, int x_dtype, int64_t N, int mode, const float* T, int R, const float* logit_scale,
+                       void* workspace, size_t workspace_bytes, float* out_f, float* out_g, float* out_logits,
+                       float* out_Tn, void* stream) {
+    if (!X || !T || !logit_scale || !workspace || !out_f || !out_g || !out_logits) return VLSA_EINVAL;
+    if (N < 1 || R < 1 || R > VLSA_MAX_R || (mode != VLSA_POOL_MEAN && mode != VLSA_POOL_MAX)) return VLSA_EINVAL;
+    if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
+    uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+    const int G = int(N < 296 ? N : 296);                      // two CTAs per SM; fixed by N alone (bit-stable)
+    if ((base - reinterpret_cast<uintptr_t>(workspace)) + size_t(G) * VLSA_D * sizeof(float) > workspace_bytes)
+        return VLSA_EWORKSPACE;
+    float* part = reinterpret_cast<float*>(base);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x_dtype == VLSA_DTYPE_F32) {
+        if (mode == VLSA_POOL_MEAN) feat_pool_partial_kernel<float, 0><<<G, 128, 0, st>>>(static_cast<const float*>(X), N, part);
+        else feat_pool_partial_kernel<float, 1><<<G, 128, 0, st>>>(static_cast<const float*>(X), N, part);
+    } else {
+        if (mode == VLSA_POOL_MEAN) feat_pool_partial_kernel<__nv_bfloat16, 0><<<G, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, part);
+        else feat_pool_partial_kernel<__nv_bfloat16, 1><<<G, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, part);
+    }
+    VLSA_CUDA(cudaGetLastError());
+    if (mode == VLSA_POOL_MEAN) feat_pool_final_kernel<0><<<1, 128, 0, st>>>(part, G, N, out_f);
+    else feat_pool_final_kernel<1><<<1, 128, 0, st>>>(part, G, N, out_f);
+    VLSA_CUDA(cudaGetLastError());
+    head_fwd_kernel<<<1, 256, 0, st>>>(out_f, T, R, logit_scale, out_g, out_logits, nullptr, out_Tn);
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int vlsa_row_normalize(const void* X, int x_dtype, int64_t N, float* out, void* stream) {
+    if (N == 0) return 0;
+    if (!X || !out || N < 0) return VLSA_EINVAL;
+    const long long blocks = (N + 7) / 8;
+    if (blocks > 0x7fffffffLL) return VLSA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (x_dtype == VLSA_DTYPE_F32) row_normalize_kernel<float><<<unsigned(blocks), 256, 0, st>>>(static_cast<const float*>(X), N, out);
+    else if (x_dtype == VLSA_DTYPE_BF16) row_normalize_kernel<__nv_bfloat16><<<unsigned(blocks), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(X), N, out);
+    else return VLSA_EUNSUPPORTED;
+    VLSA_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---- host-buffer entry ---------------------------------------------------------------------------
 struct HostWs {
     void* X; long long* cu_rows; int* chunk_start; void* agg; size_t agg_bytes;
@@ -601,12 +709,12 @@ size_t vlsa_forward_host_workspace_bytes(int64_t total_rows, int B, int P, int x
 }
 
 int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_host, int B, const float* Q, int P,
-                      float coattn_scale, const float* W, const float* bias, const float* T, int R,
+                      int q_prenorm, float coattn_scale, const float* W, const float* bias, const float* T, int R,
                       const float* logit_scale, void* workspace, size_t workspace_bytes, float* out_if_host,
                       float* out_logits_host, void* stream_compute, void* stream_copy) {
     if (B == 0) return 0;
     if (!cu_rows_host || !Q || !W || !bias || !T || !logit_scale || !workspace || !out_if_host) return VLSA_EINVAL;
-    if (B < 0 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R) return VLSA_EINVAL;
+    if (B < 0 || P < 1 || P > VLSA_MAX_P || R < 1 || R > VLSA_MAX_R || (q_prenorm != 0 && q_prenorm != 1)) return VLSA_EINVAL;
     if (x_dtype != VLSA_DTYPE_F32 && x_dtype != VLSA_DTYPE_BF16) return VLSA_EUNSUPPORTED;
     const int esize = x_dtype == VLSA_DTYPE_F32 ? 4 : 2;
     const int64_t total_rows = cu_rows_host[B];
@@ -616,30 +724,39 @@ int vlsa_forward_host(const void* X_host, int x_dtype, const int64_t* cu_rows_ho
     if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
 
     int chunk_rows = 0;
-    int32_t* cs_host = static_cast<int32_t*>(malloc(size_t(B + 1) * sizeof(int32_t)));
+    int32_t cs_stack[1025];                      // a step is 32 bags; larger batches take the heap
+    int32_t* cs_host = B + 1 <= 1025 ? cs_stack : static_cast<int32_t*>(malloc(size_t(B + 1) * sizeof(int32_t)));
     if (!cs_host) return VLSA_EINVAL;
     int rc = vlsa_agg_plan(cu_rows_host, B, 0, &chunk_rows, cs_host);
     const int total_chunks = rc == 0 ? cs_host[B] : 0;
     if (rc == 0 && total_chunks > max_chunks_bound(B)) rc = VLSA_EWORKSPACE;
     cudaStream_t sc = static_cast<cudaStream_t>(stream_compute), sx = static_cast<cudaStream_t>(stream_copy);
-    cudaEvent_t landed = nullptr;
-    if (rc == 0) rc = static_cast<int>(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+    // Two streams: the copies must not overwrite a workspace the previous call's kernels are still reading
+    // (compute -> copy), and the kernels must wait for the copies (copy -> compute).  One stream needs neither.
+    cudaEvent_t ev = nullptr;
+    if (rc == 0 && sx != sc) {
+        rc = static_cast<int>(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (rc == 0) rc = static_cast<int>(cudaEventRecord(ev, sc));
+        if (rc == 0) rc = static_cast<int>(cudaStreamWaitEvent(sx, ev, 0));
+    }
     if (rc == 0 && total_rows > 0)
         rc = static_cast<int>(cudaMemcpyAsync(ws.X, X_host, size_t(total_rows) * VLSA_D * esize, cudaMemcpyHostToDevice, sx));
-    // small pageable arrays: the runtime stages them before returning, so cs_host can be freed below
+    // small pageable arrays: the runtime stages them before returning, so cs_host may go out of scope below
     if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(ws.cu_rows, cu_rows_host, size_t(B + 1) * 8, cudaMemcpyHostToDevice, sx));
     if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(ws.chunk_start, cs_host, size_t(B + 1) * 4, cudaMemcpyHostToDevice, sx));
-    if (rc == 0) rc = static_cast<int>(cudaEventRecord(landed, sx));
-    if (rc == 0) rc = static_cast<int>(cudaStreamWaitEvent(sc, landed, 0));
+    if (rc == 0 && ev) {
+        rc = static_cast<int>(cudaEventRecord(ev, sx));
+        if (rc == 0) rc = static_cast<int>(cudaStreamWaitEvent(sc, ev, 0));
+    }
     if (rc == 0)
-        rc = vlsa_agg_fwd(ws.X, x_dtype, reinterpret_cast<const int64_t*>(ws.cu_rows), ws.chunk_start, B, chunk_rows,
-                          total_chunks, Q, P, 0, coattn_scale, W, bias, T, R, logit_scale, ws.agg, ws.agg_bytes, ws.v,
-                          ws.f, ws.g, ws.logits, ws.inc, ws.ml, nullptr, nullptr, sc);
+        rc = vlsa_agg_fwd(ws.X, x_dtype, total_rows, reinterpret_cast<const int64_t*>(ws.cu_rows), ws.chunk_start, B,
+                          chunk_rows, total_chunks, Q, P, q_prenorm, coattn_scale, W, bias, T, R, logit_scale, ws.agg,
+                          ws.agg_bytes, ws.v, ws.f, ws.g, ws.logits, ws.inc, ws.ml, nullptr, nullptr, sc);
     if (rc == 0) rc = static_cast<int>(cudaMemcpyAsync(out_if_host, ws.inc, size_t(B) * R * 4, cudaMemcpyDeviceToHost, sc));
     if (rc == 0 && out_logits_host)
         rc = static_cast<int>(cudaMemcpyAsync(out_logits_host, ws.logits, size_t(B) * R * 4, cudaMemcpyDeviceToHost, sc));
-    if (landed) cudaEventDestroy(landed);      // deferred until the event has completed
-    free(cs_host);
+    if (ev) cudaEventDestroy(ev);               // deferred by the runtime until the event has completed
+    if (cs_host != cs_stack) free(cs_host);
     return rc;
 }
 

@@ -238,6 +238,63 @@ __global__ void __launch_bounds__(1024) logit_pool_kernel(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Zero-shot arm, the remaining branches of FeatMIL.forward + VLSA.forward (model/deepmil.py:51-67, model/vlsa.py:188-198):
+//  * pooling 'mean' | 'max': column-wise mean / max over the N rows -> one [512] vector that then goes through the cosine
+//    head (head_fwd_kernel).  Two fixed-order levels: `G` CTAs each fold rows blockIdx.x, blockIdx.x + G, ... (thread =
+//    4 columns, sequential over rows), then one CTA folds the G partials in index order.  Bit-stable.
+//  * image_features of the logit-pooling modes: the N normalised patches (F.normalize, model/vlsa.py:189).
+template <typename XT>
+__device__ __forceinline__ float4 load_x4(const XT* p);
+template <> __device__ __forceinline__ float4 load_x4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 load_x4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+}
+
+template <typename XT, int MODE /* 0 mean (sum), 1 max */>
+__global__ void __launch_bounds__(128) feat_pool_partial_kernel(const XT* __restrict__ X, long long N, float* __restrict__ part) {
+    constexpr int D = VLSA_D;
+    const int c = threadIdx.x * 4;
+    float4 a = MODE == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (long long n = blockIdx.x; n < N; n += gridDim.x) {
+        const float4 v = load_x4<XT>(X + n * D + c);
+        if (MODE == 0) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        else { a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w); }
+    }
+    *reinterpret_cast<float4*>(part + size_t(blockIdx.x) * D + c) = a;
+}
+template <int MODE>
+__global__ void __launch_bounds__(128) feat_pool_final_kernel(const float* __restrict__ part, int G, long long N, float* __restrict__ out) {
+    constexpr int D = VLSA_D;
+    const int c = threadIdx.x * 4;
+    float4 a = *reinterpret_cast<const float4*>(part + c);
+    for (int g = 1; g < G; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(part + size_t(g) * D + c);
+        if (MODE == 0) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+        else { a.x = fmaxf(a.x, v.x); a.y = fmaxf(a.y, v.y); a.z = fmaxf(a.z, v.z); a.w = fmaxf(a.w, v.w); }
+    }
+    if (MODE == 0) { const float inv = 1.f / float(N); a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv; }
+    *reinterpret_cast<float4*>(out + c) = a;
+}
+// out[n] = x_n / max(|x_n|, eps) in fp32; one warp per row, 8 rows per CTA
+template <typename XT>
+__global__ void __launch_bounds__(256) row_normalize_kernel(const XT* __restrict__ X, long long N, float* __restrict__ out) {
+    constexpr int D = VLSA_D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n = (long long)blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    float x[16];
+    load_row16<XT>(X + n * D, lane, x);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ss += x[i] * x[i];
+    ss = warp_sum(ss);
+    const float nrm = fmaxf(sqrtf(ss), VLSA_NORM_EPS);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[n * D + slot_col<XT>(lane, i)] = x[i] / nrm;
+}
+
 // dX of the pooled aggregation for callers that train something IN FRONT of it (VLFAN's feat_proj, a Linear + LayerNorm
 // over all patch rows, model/layers.py:65-82 + model/deepmil.py:176-179).  With O_p = sum_n A_pn x_n and
 // s_pn = scale qdir_p . x_n / |x_n|:

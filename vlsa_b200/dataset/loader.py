@@ -68,6 +68,8 @@ class AsyncBagLoader:
         self._dev = [None] * self.depth          # device ring slots
         self._pin = [None] * self.depth          # pinned staging per slot
         self._free = [None] * self.depth         # event: consumer finished with the slot
+        self._copied = [None] * self.depth       # event: the H2D copy out of the slot's pinned staging buffer is done
+        self._busy = [False] * self.depth        # slot handed to the consumer and not released yet
         self._max_rows = max_rows
         self.h2d_bytes = 0
 
@@ -75,13 +77,19 @@ class AsyncBagLoader:
         cap = max(rows, self._max_rows or 0, 1)
         if self._dev[slot] is None or self._dev[slot].shape[0] < rows:
             self._dev[slot] = torch.empty(cap, ops.D_FEAT, dtype=self.dtype, device=self.device)
+            # the block comes from the allocator pool of the CURRENT stream and may still be in use there by whoever
+            # freed it; its first writer is the copy stream
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         return self._dev[slot]
 
     def release(self, batch: PackedBatch, stream: torch.cuda.Stream | None = None) -> None:
-        """Mark the batch's ring slot reusable once ``stream`` (default: current) has consumed it."""
+        """Mark the batch's ring slot reusable once ``stream`` (default: current) has consumed it.  Called
+        automatically (on the current stream) when the iterator is asked for the batch after this one; call it
+        yourself only when the batch was consumed on another stream."""
         ev = torch.cuda.Event()
         ev.record(stream or torch.cuda.current_stream(self.device))
         self._free[batch.slot] = ev
+        self._busy[batch.slot] = False
 
     def __iter__(self) -> Iterator[PackedBatch]:
         pending: list[PackedBatch] = []
@@ -99,7 +107,13 @@ class AsyncBagLoader:
                 slot = (slot + 1) % self.depth
             if not pending:
                 return
-            yield pending.pop(0)
+            batch = pending.pop(0)
+            self._busy[batch.slot] = True
+            yield batch
+            # the consumer asked for the next batch: everything it enqueued on the current stream so far is what used
+            # this one (an explicit release() on another stream has already cleared the flag)
+            if self._busy[batch.slot]:
+                self.release(batch)
 
     def _stage(self, item, slot: int) -> PackedBatch:
         if len(item) == 4 and isinstance(item[1], (list, tuple, np.ndarray)) and isinstance(item[0], torch.Tensor) \
@@ -108,8 +122,13 @@ class AsyncBagLoader:
             sizes = [int(s) for s in sizes]
         else:
             bags, labels, index = item
+            if self._copied[slot] is not None:
+                self._copied[slot].synchronize()                     # the previous H2D copy still reads this staging buffer
             host, sizes = pack_bags(bags, self._pin[slot])
             self._pin[slot] = host
+        if self._busy[slot]:
+            raise RuntimeError("AsyncBagLoader: ring slot reused while its batch is still held by the consumer "
+                               "(raise depth= or release() the batch)")
         rows = sum(sizes)
         dst = self._slot_buffers(slot, rows)
         with torch.cuda.stream(self.copy_stream):
@@ -117,6 +136,8 @@ class AsyncBagLoader:
                 self.copy_stream.wait_event(self._free[slot])        # consumer done with this slot
             if rows:
                 dst[:rows].copy_(host[:rows], non_blocking=True)
+                self._copied[slot] = torch.cuda.Event()
+                self._copied[slot].record(self.copy_stream)
             plan = ops.make_plan(sizes, self.device)
             lab = labels.to(self.device, non_blocking=True) if labels is not None else None
             ready = torch.cuda.Event()

@@ -28,13 +28,17 @@ def coattn_scale() -> float:
     return float((torch.ones([]) * np.log(100)).exp())
 
 
+_KERNEL_FLAG = {None: 0, "auto": 0, "simt": 0x100, "tc": 0x200, "tc_reg": 0x400}
+_agg_variant_flag = 0
+
+
 def set_agg_variant(variant: str | None) -> None:
-    """Cross-check hook: force the streaming kernel of fp32 passes ('simt' = CUDA cores, 'tc' = tcgen05) or
-    None for the automatic choice (tensor cores for P > 5)."""
-    code = {None: -1, "auto": -1, "simt": 0, "tc": 1}[variant]
-    rc = _lib.lib().vlsa_debug_set_agg_variant(code)
-    if rc:
-        raise RuntimeError(_lib.lib().vlsa_error_string(rc).decode())
+    """Cross-check hook of the parity tests: force the streaming kernel of fp32 passes — 'simt' = CUDA cores, 'tc' = the
+    TMA-fed tcgen05 kernel, 'tc_reg' = the register-staged tcgen05 kernel of round 1 — or None for the automatic choice
+    (tcgen05 for P > 5).  The choice travels with every call as a VLSA_KERNEL_* bit of x_dtype (include/vlsa_b200.h);
+    the library itself keeps no switch."""
+    global _agg_variant_flag
+    _agg_variant_flag = _KERNEL_FLAG[variant]
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -155,6 +159,11 @@ def _x_dtype_code(x: torch.Tensor) -> int:
     raise ValueError(f"X must be float32 or bfloat16, got {x.dtype}")
 
 
+def _agg_dtype_code(x: torch.Tensor) -> int:
+    """x_dtype of the vlsa_agg_* calls: storage type + the kernel the cross-check hook asks for (if any)."""
+    return _x_dtype_code(x) | _agg_variant_flag
+
+
 def _workspace(plan: BagPlan, P: int, device) -> torch.Tensor:
     nbytes = _lib.lib().vlsa_agg_workspace_bytes(plan.total_chunks, plan.num_bags, P)
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -187,7 +196,7 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
         "Tn": torch.empty(R, D_FEAT, **f32),
     }
     ws = workspace if workspace is not None else _workspace(plan, P, dev)
-    rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+    rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                         plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, int(bool(q_prenorm)),
                         coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
                         T.data_ptr(), R, logit_scale.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -200,7 +209,7 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
 
 def aggregate_partial_only(X, plan: BagPlan, Q, workspace: torch.Tensor, scale: float | None = None) -> None:
     """Launch only the streaming kernel (vlsa_agg_partial_fwd); used to time the dominant kernel alone."""
-    rc = _lib.lib().vlsa_agg_partial_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+    rc = _lib.lib().vlsa_agg_partial_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
                                          plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
                                          plan.total_chunks, Q.data_ptr(), Q.shape[0],
                                          coattn_scale() if scale is None else float(scale), workspace.data_ptr(),
@@ -239,7 +248,7 @@ class _AggregateFn(torch.autograd.Function):
         d_g = None if d_g is None else d_g.contiguous().float()
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
         dT, dls = torch.empty(R, D_FEAT, **f32), torch.empty((), **f32)
-        rc = L.vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+        rc = L.vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                             plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, ctx.prenorm,
                             coattn_scale() if ctx.scale is None else float(ctx.scale), W.data_ptr(), T.data_ptr(), R,
                             ls.data_ptr(), v.data_ptr(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), ml.data_ptr(),
@@ -270,7 +279,7 @@ class _EncodeFn(torch.autograd.Function):
         ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
         ws = _workspace(plan, P, X.device)
         sc = coattn_scale() if scale is None else float(scale)
-        rc = L.vlsa_agg_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+        rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                             plan.chunk_rows, plan.total_chunks, Qc.data_ptr(), P, int(bool(q_prenorm)), sc, Wc.data_ptr(),
                             bc.data_ptr(), None, 0, None, ws.data_ptr(), ws.numel(), v.data_ptr(), f.data_ptr(), None,
                             None, None, ml.data_ptr(), O.data_ptr(), None, _stream())
@@ -293,7 +302,7 @@ class _EncodeFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=X.device)
         d_f = d_f.contiguous().float()
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
-        rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
                                      plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows, plan.total_chunks,
                                      Q.data_ptr(), P, ctx.prenorm, ctx.scale, W.data_ptr(), None, 0, None, v.data_ptr(),
                                      None, None, None, ml.data_ptr(), O.data_ptr(), None, None, d_f.data_ptr(),
@@ -329,7 +338,7 @@ class _PooledFn(torch.autograd.Function):
         ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
         ws = _workspace(plan, P, X.device)
         sc = coattn_scale() if scale is None else float(scale)
-        rc = _lib.lib().vlsa_agg_pooled_fwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_pooled_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
                                             plan.chunk_start.data_ptr(), B, plan.chunk_rows, plan.total_chunks,
                                             Qc.data_ptr(), P, int(bool(q_prenorm)), sc, ws.data_ptr(), ws.numel(),
                                             ml.data_ptr(), O.data_ptr(), _stream())
@@ -351,7 +360,7 @@ class _PooledFn(torch.autograd.Function):
         P = Q.shape[0]
         d_O = d_O.contiguous().float()
         dQ = torch.empty(P, D_FEAT, dtype=torch.float32, device=X.device)
-        rc = _lib.lib().vlsa_agg_pooled_bwd(X.data_ptr(), _x_dtype_code(X), plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_pooled_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
                                             plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
                                             plan.total_chunks, Q.data_ptr(), P, ctx.prenorm, ctx.scale, ml.data_ptr(),
                                             O.data_ptr(), d_O.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
@@ -503,12 +512,42 @@ def logit_pool(X, T, logit_scale, pooling: str):
     return pred, pooled
 
 
+def feat_pool(X, T, logit_scale, pooling: str):
+    """Zero-shot arm with FeatMIL pooling 'mean' | 'max' (model/deepmil.py:57-60 + model/vlsa.py:188-192), one bag:
+    returns (logits [1,R], image_features g [1,512], Tn [R,512]).  A one-row bag under ANY pooling is the 'mean' case."""
+    L = _lib.lib()
+    _check_cuda(X, "X", None)
+    _check_cuda(T, "T")
+    mode = {"mean": 0, "max": 2}[pooling]
+    N, R = X.shape[0], T.shape[0]
+    if N < 1:
+        raise ValueError("empty bag")
+    f32 = dict(dtype=torch.float32, device=X.device)
+    ws = torch.empty(int(L.vlsa_feat_pool_workspace_bytes()), dtype=torch.uint8, device=X.device)
+    f, g, logits, Tn = torch.empty(1, D_FEAT, **f32), torch.empty(1, D_FEAT, **f32), torch.empty(1, R, **f32), torch.empty(R, D_FEAT, **f32)
+    ls = logit_scale.detach().reshape(()).float().contiguous()
+    rc = L.vlsa_feat_pool_fwd(X.data_ptr(), _x_dtype_code(X), N, mode, T.data_ptr(), R, ls.data_ptr(), ws.data_ptr(),
+                              ws.numel(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), Tn.data_ptr(), _stream())
+    _lib.check(rc, "vlsa_feat_pool_fwd")
+    return logits, g, Tn
+
+
+def row_normalize(X):
+    """F.normalize(X, dim=-1) in fp32 for packed rows [N, 512] (image_features of the logit-pooling zero-shot modes)."""
+    _check_cuda(X, "X", None)
+    out = torch.empty(X.shape[0], D_FEAT, dtype=torch.float32, device=X.device)
+    rc = _lib.lib().vlsa_row_normalize(X.data_ptr(), _x_dtype_code(X), X.shape[0], out.data_ptr(), _stream())
+    _lib.check(rc, "vlsa_row_normalize")
+    return out
+
+
 def forward_host(X_host: torch.Tensor, bag_sizes, Q, W, bias, T, logit_scale, out_if_host: torch.Tensor | None = None,
                  workspace: torch.Tensor | None = None, copy_stream: torch.cuda.Stream | None = None,
-                 scale: float | None = None, device=None):
+                 scale: float | None = None, device=None, q_prenorm: bool = False):
     """vlsa_forward_host: packed HOST bags (pinned for async copies) -> incidence on the HOST.  Enqueues the
     H2D copy on `copy_stream`, the kernels and the D2H copy on the current stream; returns
-    (out_if_host [B,R], workspace) without synchronising."""
+    (out_if_host [B,R], workspace) without synchronising.  The returned workspace may be passed to the next call
+    straight away: the library orders the copy stream behind the kernels that still read it."""
     L = _lib.lib()
     device = Q.device if device is None else torch.device(device)
     sizes = np.asarray(list(bag_sizes), dtype=np.int64)
@@ -525,7 +564,7 @@ def forward_host(X_host: torch.Tensor, bag_sizes, Q, W, bias, T, logit_scale, ou
         out_if_host = torch.empty(B, R, dtype=torch.float32).pin_memory()
     cs = copy_stream.cuda_stream if copy_stream is not None else _stream()
     rc = L.vlsa_forward_host(X_host.data_ptr(), code, cu.ctypes.data_as(C.POINTER(C.c_int64)), B, Q.data_ptr(), P,
-                             coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
+                             int(bool(q_prenorm)), coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
                              T.data_ptr(), R, logit_scale.data_ptr(), workspace.data_ptr(), workspace.numel(),
                              out_if_host.data_ptr(), None, _stream(), cs)
     _lib.check(rc, "vlsa_forward_host")
