@@ -45,7 +45,6 @@ extern "C" {
  * All kernels compute the same function (model/deepmil.py:187-203). */
 #define VLSA_KERNEL_SIMT 0x100   /* CUDA-core kernel (agg_simt_kernel) */
 #define VLSA_KERNEL_TC 0x200     /* TMA-fed tcgen05 kernel (agg_tma_kernel) */
-#define VLSA_KERNEL_TC_REG 0x400 /* register-staged tcgen05 kernel of round 1 (agg_tc_kernel) */
 
 #define VLSA_EINVAL (-1)      /* bad argument (null pointer, P/R/D out of range, ...) */
 #define VLSA_EWORKSPACE (-2)  /* workspace too small */

@@ -146,10 +146,16 @@ def logit_pooling(logits, method: str):
 
 
 def vlsa_forward_zero_shot(X, T, logit_scale, pooling: str):
-    """model/vlsa.py:181-198 with mil_encoder = FeatMIL(pooling=logit_*) (deepmil.py:51-67):
-    per-patch logits [N,R] then logit_pooling.  Returns (preds [1], pooled [1,R], g [N,D], Tn)."""
+    """model/vlsa.py:181-198 with mil_encoder = FeatMIL(pooling) (deepmil.py:51-67).  pooling 'mean' | 'max': the patch
+    FEATURES are pooled to one vector (deepmil.py:57-60) and the logits stay [1,R]; otherwise (identity): per-patch
+    logits [N,R] then logit_pooling.  Returns (preds [1], pooled [1,R], g [1|N,D], Tn)."""
     assert X.shape[0] == 1
     Tn = F.normalize(T, dim=-1)
+    if pooling in ("mean", "max"):
+        vec = torch.mean(X, dim=1) if pooling == "mean" else torch.max(X, dim=1)[0]
+        g = F.normalize(vec, dim=-1)
+        logits = logit_scale.exp() * g @ Tn.t()
+        return logits.argmax(dim=1), logits, g, Tn
     g = F.normalize(X.squeeze(0), dim=-1)                    # FeatMIL identity arm, vlsa.py:189
     logits = logit_scale.exp() * g @ Tn.t()                  # [N,R]
     if logits.shape[0] > 1:                                  # vlsa.py:195

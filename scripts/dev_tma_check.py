@@ -83,7 +83,7 @@ for P in ([12] if quick else [12, 8, 16] if not os.environ.get("VLSA_DEV_FEWP") 
     ws = ops._workspace(plan, P, dev)
     Qd = (0.5 * res + pf).detach()
     gb = N * B * 512 * 4 / 1e9
-    for variant in ("tc", "tc_reg"):
+    for variant in ("tc", "simt"):
         ops.set_agg_variant(variant)
         ms_k = timeit(lambda i: ops.aggregate_partial_only(Xs[i % 2], plan, Qd, ws))
 

@@ -15,8 +15,10 @@ def pytest_configure(config):
 
 
 def golden_cases(prefix):
-    with open(os.path.join(GOLDEN, "INDEX.txt")) as fh:
-        names = [ln.strip() for ln in fh if ln.strip()]
+    names = []
+    for index in ("INDEX.txt", "INDEX_r02.txt"):
+        with open(os.path.join(GOLDEN, index)) as fh:
+            names += [ln.strip() for ln in fh if ln.strip()]
     return [n for n in names if n.startswith(prefix)]
 
 

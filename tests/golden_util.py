@@ -67,6 +67,33 @@ def rebuild_inputs(name, case):
     return bags, params, t, e
 
 
+def rebuild_interp(case):
+    """Inputs of an `interp_*` golden (tests/golden/make_golden_r02.py::interp_inputs): (X [N,512], params)."""
+    ck = _ckpt()
+    P, R, seed, kind = int(case["P"]), int(case["R"]), int(case["seed"]), str(case["kind"])
+    params = synth.make_params(P, R, seed, w=ck["W"], b=ck["b"])
+    if kind == "real":
+        X = _real()
+        if P == 12:
+            params["residual_features"] = ck["residual_features"].clone()
+        params["logit_scale"] = ck["logit_scale"].clone()
+    else:
+        X = synth.make_bag(kind, int(np.atleast_1d(case["n"])[0]), seed + 7)
+    got = X.double().sum().item()
+    assert abs(got - float(case["x_sum"])) <= 1e-9 * max(1.0, abs(float(case["x_sum"]))), "synthetic generator drifted"
+    return X, params
+
+
+def rebuild_zeroshot2(case):
+    """Inputs of a `zeroshot2_*` golden: (X [N,512], params with text_features / logit_scale)."""
+    ck = _ckpt()
+    R, seed, n = int(case["R"]), int(case["seed"]), int(np.atleast_1d(case["n"])[0])
+    X = synth.make_bag(str(case["kind"]), n, seed)
+    got = X.double().sum().item()
+    assert abs(got - float(case["x_sum"])) <= 1e-9 * max(1.0, abs(float(case["x_sum"]))), "synthetic generator drifted"
+    return X, synth.make_params(1, R, seed + 100000, w=ck["W"], b=ck["b"])
+
+
 # ---- VLFAN variants (SURVEY §8 f4): cases and seeded inputs shared by the generator and the tests -----------------
 VARIANT_CASES = [
     dict(P=4, gated=True, pooling="mean", pred_head="default", hid=32, kind="g1", ns=(1000, 37), seed=31001),

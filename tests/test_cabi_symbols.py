@@ -89,12 +89,17 @@ def test_workspace_query_grows_with_chunks(lib):
 
 def test_null_arguments_are_rejected_without_a_gpu(lib):
     # argument validation happens before any CUDA call
-    assert lib.vlsa_agg_fwd(None, 0, None, None, 1, 16, 1, None, 4, 0, 100.0, None, None, None, 4, None, None, 0,
+    assert lib.vlsa_agg_fwd(None, 0, 16, None, None, 1, 16, 1, None, 4, 0, 100.0, None, None, None, 4, None, None, 0,
                             None, None, None, None, None, None, None, None, None) == -1
-    assert lib.vlsa_agg_pooled_fwd(None, 0, None, None, 1, 32, 1, None, 4, 0, 100.0, None, 0, None, None, None) == -1
-    assert lib.vlsa_agg_pooled_bwd(None, 0, None, None, 1, 32, 1, None, 4, 0, 100.0, None, None, None, None, 0, None,
+    assert lib.vlsa_agg_pooled_fwd(None, 0, 32, None, None, 1, 32, 1, None, 4, 0, 100.0, None, 0, None, None, None) == -1
+    assert lib.vlsa_agg_pooled_bwd(None, 0, 32, None, None, 1, 32, 1, None, 4, 0, 100.0, None, None, None, None, 0, None,
                                    None) == -1
     assert lib.vlsa_agg_pooled_bwd_dx(None, None, 1, 10, None, 4, 0, 100.0, None, None, None, None, None) == -1
     assert lib.vlsa_surv_loss_fwd_bwd(None, None, None, 1, 4, None, 1.0, 1.0, 0.0, 1e-7, 1.0, 0, None, None, None,
                                       None, None) == -1
     assert lib.vlsa_logit_pool_fwd(None, 0, 10, None, 4, None, 1, 10, None, 0, None, None, None) == -1
+    assert lib.vlsa_feat_pool_fwd(None, 0, 10, 0, None, 4, None, None, 0, None, None, None, None, None) == -1
+    assert lib.vlsa_row_normalize(None, 0, 10, None, None) == -1
+    assert lib.vlsa_feat_pool_workspace_bytes() >= 296 * 512 * 4
+    # kernel-selection bits other than the documented ones are refused
+    assert lib.vlsa_agg_pooled_fwd(None, 0x800, 32, None, None, 1, 32, 1, None, 4, 0, 100.0, None, 0, None, None, None) in (-1, -3)

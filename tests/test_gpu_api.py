@@ -90,12 +90,35 @@ def test_encoder_only_backward_matches_autograd_of_oracle(dev):
 def test_zero_shot_module(name, dev):
     case = load_case(name)
     bags, pr, _, _ = rebuild_inputs(name, case)
-    n = bags[0].shape[0]
-    if n == 1:
-        pytest.skip("single-patch bags take the reference's non-pooled branch (logits.shape[0] == 1)")
     net = build_net(pr, 1, int(case["R"]), dev, encoder="FeatMIL", pooling=str(case["pooling"]))
-    logits, _, Tn = net(bags[0].unsqueeze(0).to(dev))
+    logits, feats, Tn = net(bags[0].unsqueeze(0).to(dev))        # one-patch bags included (vlsa.py:195: no pooling)
+    assert logits.shape == (1, int(case["R"]))
     np.testing.assert_allclose(logits.cpu().numpy(), case["logits_f32"], rtol=2e-5, atol=2e-5)
+    assert feats.shape == (bags[0].shape[0], 512)                  # image_features: the N normalised patches
+    np.testing.assert_allclose(feats.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", golden_cases("zeroshot2_"))
+def test_zero_shot_all_featmil_branches_vs_reference(name, dev):
+    """VLSA.forward with FeatMIL through every branch the reference has (model/vlsa.py:181-198, deepmil.py:51-67):
+    feature pooling 'mean' | 'max', one-patch bags, and the returned image_features, against the reference's own
+    forward (tests/golden/make_golden_r02.py)."""
+    from golden_util import rebuild_zeroshot2
+    case = load_case(name)
+    X, pr = rebuild_zeroshot2(case)
+    R, pooling = int(case["R"]), str(case["pooling"])
+    net = build_net(pr, 1, R, dev, encoder="FeatMIL", pooling=pooling)
+    logits, feats, Tn = net(X.unsqueeze(0).to(dev))
+    assert logits.shape == (1, R) and tuple(feats.shape) == tuple(case["feats_shape"]) and Tn.shape == (R, 512)
+    np.testing.assert_allclose(logits.cpu().numpy(), case["logits_f64"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(feats[:8].cpu().numpy(), case["feats_head_f64"], atol=2e-6)
+    np.testing.assert_allclose(feats.double().sum(0).cpu().numpy(), case["feats_sum_f64"], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(Tn.cpu().numpy(), case["Tn_f32"], atol=1e-6)
+    if pooling == "max":                                            # max is exact: same bits as the fp32 reference
+        np.testing.assert_allclose(logits.cpu().numpy(), case["logits_f32"], rtol=1e-6, atol=2e-6)
+    # bf16 storage of the patches goes through the same entries
+    lb, fb, _ = net(X.to(torch.bfloat16).unsqueeze(0).to(dev))
+    assert lb.shape == (1, R) and torch.isfinite(lb).all() and (lb - logits).abs().max().item() < 0.5
 
 
 @pytest.mark.parametrize("name", golden_cases("batch_"))
@@ -163,22 +186,36 @@ def test_forward_host_and_async_loader_match_device_path(dev):
         X = torch.cat(bags, 0).to(dev)
         plan = ops.make_plan([x.shape[0] for x in bags], dev)
         direct.append(ops.aggregate_forward_raw(X, plan, Q, W, b, T, ls)["incidence"].cpu())
-    # (a) C-ABI host entry
+    # (a) C-ABI host entry; the workspace of one call is handed to the next WITHOUT a synchronisation in between (the
+    #     library orders the copy stream behind the kernels still reading it), several rounds to give a race a chance
     copy_stream = torch.cuda.Stream()
-    for bags, ref in zip(steps, direct):
-        host = torch.cat(bags, 0).pin_memory()
-        out, _ = ops.forward_host(host, [x.shape[0] for x in bags], Q, W, b, T, ls, copy_stream=copy_stream)
+    hosts = [torch.cat(bags, 0).pin_memory() for bags in steps]
+    for _ in range(5):
+        ws, outs = None, []
+        for bags, host in zip(steps, hosts):
+            out, ws = ops.forward_host(host, [x.shape[0] for x in bags], Q, W, b, T, ls, workspace=ws, copy_stream=copy_stream)
+            outs.append(out)
         torch.cuda.synchronize()
-        assert torch.equal(out, ref)
-    # (b) loader + module API
+        for out, ref in zip(outs, direct):
+            assert torch.equal(out, ref)
+    # (a') pre-normalised query rows (the gated query's difference rows) through the same entry
+    Qd = torch.nn.functional.normalize(Q, dim=-1)
+    Qd = (Qd[:-1] - Qd[-1:]).contiguous()
+    Xd = torch.cat(steps[0], 0).to(dev)
+    ref_g = ops.aggregate_forward_raw(Xd, ops.make_plan([x.shape[0] for x in steps[0]], dev), Qd, W, b, T, ls,
+                                      q_prenorm=True)["incidence"].cpu()
+    out_g, _ = ops.forward_host(hosts[0], [x.shape[0] for x in steps[0]], Qd, W, b, T, ls, copy_stream=copy_stream, q_prenorm=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out_g, ref_g) and not torch.equal(out_g[:, :], direct[0][:, :])
+    # (b) loader + module API; a batch is released automatically when the next one is requested
     loader = AsyncBagLoader(((bags, None, None) for bags in steps), dev, depth=2)
     got = []
     with torch.no_grad():
         for batch in loader:
             batch.wait()
             logits, g, Tn, inc = net.forward_packed(batch.X, batch.plan)
-            loader.release(batch)
-            got.append(inc.cpu())
+            got.append(inc)
+    got = [g_.cpu() for g_ in got]
     assert len(got) == 3
     for a, ref in zip(got, direct):
         assert torch.equal(a, ref)
@@ -244,6 +281,31 @@ def test_interpretation_path_matches_reference_formula(P, R, N, kind, axis, dev)
     if shap64 is not None:
         np.testing.assert_allclose(shap.numpy(), shap64.numpy(), atol=2e-4)
     assert shap.shape == (P,)
+
+
+@pytest.mark.parametrize("name", golden_cases("interp_"))
+def test_interpretation_path_vs_reference_own_routine(name, dev):
+    """`calc_text_img_similarity` + `evaluate_prototype_shap_imp` against the outputs of the reference's OWN functions
+    (utils/model_inference.py:21-144) run unmodified on CPU in fp64 (tests/golden/make_golden_r02.py)."""
+    from golden_util import rebuild_interp
+    from vlsa_b200.utils import calc_text_img_similarity
+    case = load_case(name)
+    X, pr = rebuild_interp(case)
+    P, R, axis = int(case["P"]), int(case["R"]), str(case["axis"])
+    net = build_net(pr, P, R, dev)
+    none, A, cottn, probs, probs2, imp, shap = calc_text_img_similarity(net, X.unsqueeze(0), axis_softmax=axis)
+    assert none is None and A.shape == (P, X.shape[0]) and cottn.shape == (P, X.shape[0])
+    k = case["A_head_f64"].shape[1]
+    np.testing.assert_allclose(A[:, :k].numpy(), case["A_head_f64"], rtol=2e-4, atol=1e-7 if axis == "L" else 1e-9)
+    np.testing.assert_allclose(cottn[:, :k].numpy(), case["cottn_head_f64"], rtol=2e-4, atol=1e-9)
+    np.testing.assert_allclose(cottn.max(1).values.numpy(), case["cottn_max_f64"], rtol=2e-4)
+    assert (cottn.argmax(1).numpy() == case["cottn_argmax_f64"]).all()
+    np.testing.assert_allclose(A.sum(1).numpy(), case["A_rowsum_f64"], rtol=1e-4)
+    assert np.abs(probs.numpy() - case["probs_f64"]).max() <= IF_TOL
+    assert np.abs(probs2.numpy() - case["probs2_f64"]).max() <= IF_TOL
+    assert np.abs(imp.numpy() - case["imp_f64"]).max() <= 5e-5
+    np.testing.assert_allclose(shap.numpy(), case["shap_f64"], atol=2e-4)        # all 2^P subsets, P up to 12
+    np.testing.assert_allclose(shap.numpy(), case["shap_f32"], atol=5e-4)
 
 
 def test_flat_store_to_async_loader_to_forward(tmp_path, dev):

@@ -143,13 +143,61 @@ def test_forward_vs_oracle_seeded(P, N, kind, dev):
     np.testing.assert_allclose(out["g"].cpu().numpy(), g64.numpy(), atol=2e-6)
 
 
-@pytest.mark.parametrize("P", [4, 12, 16])
-def test_bf16_storage_tolerance(P, dev):
-    """BASELINE config 5: bf16 storage of X, fp32 accumulate; incidence <= 1e-3 vs the oracle run on the
-    SAME bf16-rounded values (storage rounding is the caller's choice, the kernel must add < 1e-4)."""
+@pytest.mark.parametrize("P,N,kind", [(4, 50000, "g0"), (4, 50000, "g1"), (4, 100000, "g0"), (4, 100000, "g1"),
+                                      (12, 50000, "g1"), (12, 100000, "g0")])
+def test_headline_shapes_vs_oracle(P, N, kind, dev):
+    """The driver-benchmarked configurations against the fp64 oracle at FULL size: P = R = 4 (BASELINE 'K = 4', the
+    CUDA-core kernel) and the shipped P = R = 12 (tcgen05 kernel), N = 50k and 100k, both generators."""
     from oracle import vlsa_oracle as O
     from vlsa_b200 import ops, synth
-    N = 20000
+    X = synth.make_bag(kind, N, 90210 + N + P)
+    pr = synth.make_params(P, P, 17 + P)
+    _, plan, out = _fwd(ops, [X], pr, dev)
+    c = lambda z: z.double()
+    Q64 = O.task_res_query(c(pr["prompt_features"]), c(pr["residual_features"]), pr["res_ratio"])
+    logits64, g64, _ = O.vlsa_forward(c(X).unsqueeze(0), Q64, c(pr["W"]), c(pr["b"]), c(pr["text_features"]),
+                                      c(pr["logit_scale"]))
+    assert np.abs(out["incidence"].cpu().numpy() - O.softmax_converter(logits64).numpy()).max() <= IF_TOL
+    np.testing.assert_allclose(out["g"].cpu().numpy(), g64.numpy(), atol=2e-6)
+
+
+@pytest.mark.parametrize("P", [4, 12])
+def test_packed_step_of_32_bags_matches_per_bag_calls(P, dev):
+    """bench.py's workload (32 bags x 50k rows in ONE launch) against 32 one-bag calls and, for three of the bags, the
+    fp64 oracle.  The packed plan cuts chunks differently from a one-bag plan, so the comparison is to summation-order
+    tolerance; two copies of the same bag inside the batch must agree bit for bit."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import ops, synth
+    B, N = 32, 50000
+    pr = synth.make_params(P, P, 5 + P)
+    g = torch.Generator(device=dev).manual_seed(1234 + P)
+    X = torch.randn(B * N, 512, generator=g, device=dev) * 1.1
+    X[: 3 * N] += 0.7                                            # three bags with a common direction (peaky softmax)
+    X[31 * N:] = X[:N]                                           # bag 31 duplicates bag 0
+    args = tuple(z.to(dev) for z in (_query(pr), pr["W"], pr["b"], pr["text_features"], pr["logit_scale"]))
+    packed = ops.aggregate_forward_raw(X, ops.make_plan([N] * B, dev), *args)
+    torch.cuda.synchronize()
+    assert torch.equal(packed["incidence"][0], packed["incidence"][31]) and torch.equal(packed["f"][0], packed["f"][31])
+    one = ops.make_plan([N], dev)
+    for i in range(B):
+        single = ops.aggregate_forward_raw(X[i * N:(i + 1) * N], one, *args)
+        assert (single["incidence"][0] - packed["incidence"][i]).abs().max().item() <= 2e-6, i
+    c = lambda z: z.double()
+    Q64 = O.task_res_query(c(pr["prompt_features"]), c(pr["residual_features"]), pr["res_ratio"])
+    for i in (0, 7, 30):
+        Xi = X[i * N:(i + 1) * N].cpu()
+        logits64, _, _ = O.vlsa_forward(c(Xi).unsqueeze(0), Q64, c(pr["W"]), c(pr["b"]), c(pr["text_features"]), c(pr["logit_scale"]))
+        assert np.abs(packed["incidence"][i].cpu().numpy() - O.softmax_converter(logits64).numpy()[0]).max() <= IF_TOL, i
+
+
+@pytest.mark.parametrize("P", [4, 8, 12, 16])
+def test_bf16_storage_tolerance(P, dev):
+    """BASELINE config 5 (K in {4, 8, 16}, N = 50k, bf16 vs fp32): bf16 storage of X, fp32 accumulate; incidence <= 1e-3
+    vs the fp32-input oracle and <= 2e-5 vs the oracle run on the SAME bf16-rounded values (storage rounding is the
+    caller's choice, the kernel must add < 1e-4)."""
+    from oracle import vlsa_oracle as O
+    from vlsa_b200 import ops, synth
+    N = 50000
     X = synth.make_bag("g1", N, 777 + P)
     pr = synth.make_params(P, P, 55 + P)
     Xb = X.to(torch.bfloat16)
@@ -283,11 +331,17 @@ def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dev):
 
 
 def test_backward_accuracy_regression_case(dev):
-    """An ill-conditioned step (delta_p = dv . O_p / P cancels heavily, so the gradients amplify any error of the
-    forward's pooled features): the reference's own fp32 arithmetic is 5e-4 away from its fp64 run here.  The
-    tensor-core path (split accumulators, near-exact O) must stay at 2e-5 — this is the case that exposed a 700x loss
-    of gradient accuracy when the lo-plane products shared an accumulator with the hi-plane ones — and the CUDA-core
-    path must stay within a small multiple of what fp32 arithmetic in the reference's order gives."""
+    """An ill-conditioned optimizer step: a censored sample with almost no probability mass left after its time bin
+    makes d loss / d logits amplify a 1e-6 difference of a logit about a thousand times, so the reference's own fp32
+    arithmetic is 5e-4 away from its fp64 run here — and so is any fp32-grade forward, by the luck of its last bit
+    (round 1 bounded the tcgen05 path at 2e-5 on exactly this case; the same kernel is 7.5e-4 off on [2798, 37]).
+    What the kernels can be held to, and are:
+      (a) with the UPSTREAM gradient d loss / d logits fixed (taken from the fp64 reference), the gradients of both
+          streaming kernels are within 2e-5 of the fp64 reference — the backward itself loses nothing (this is the
+          check that exposed a 700x loss of accuracy when the lo-plane products shared a TMEM accumulator with the
+          hi-plane ones);
+      (b) through the real loss, both stay within a small multiple of what fp32 arithmetic in the reference's order
+          gives."""
     from oracle import vlsa_oracle as O
     from vlsa_b200 import ops, synth
     P = R = 12
@@ -302,6 +356,17 @@ def test_backward_accuracy_regression_case(dev):
     gref = ref["d_residual"].numpy()
     err_ref32 = np.abs(ref32["d_residual"].double().numpy() - gref).max() / np.abs(gref).max()
     assert err_ref32 > 1e-4                      # the case is ill-conditioned for fp32 arithmetic (measured 5e-4)
+    # fp64 reference of (a): d (sum logits * G) with G = d loss / d logits of the fp64 run
+    c = lambda z: z.double()
+    res64 = c(pr["residual_features"]).requires_grad_(True)
+    Q64 = O.task_res_query(c(pr["prompt_features"]), res64, pr["res_ratio"])
+    lg64 = torch.cat([O.vlsa_forward(c(X).unsqueeze(0), Q64, c(pr["W"]), c(pr["b"]), c(pr["text_features"]),
+                                     c(pr["logit_scale"]))[0] for X in bags], 0)
+    lg_leaf = lg64.detach().clone().requires_grad_(True)
+    O.objective_loss(lg_leaf, t, e, c(pr["logit_scale"]).exp()).backward()
+    G = lg_leaf.grad.clone()
+    (lg64 * G).sum().backward()
+    gfix = res64.grad.numpy()
     X = torch.cat(bags, 0).to(dev)
     plan = ops.make_plan(sizes, dev)
     try:
@@ -311,12 +376,17 @@ def test_backward_accuracy_regression_case(dev):
             res, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))
             Q = pr["res_ratio"] * res + pr["prompt_features"].to(dev)
             logits, g, Tn, inc, ml = ops.aggregate(X, plan, Q, W, b, T, ls)
+            (logits * G.float().to(dev)).sum().backward()
+            torch.cuda.synchronize()
+            err = np.abs(res.grad.cpu().numpy() - gfix).max() / np.abs(gfix).max()
+            assert err <= 2e-5, f"{variant}: fixed upstream gradient, d_residual relative error {err:.2e}"
+            res.grad = None
+            logits, g, Tn, inc, ml = ops.aggregate(X, plan, pr["res_ratio"] * res + pr["prompt_features"].to(dev), W, b, T, ls)
             total, *_ = ops.surv_loss(logits, t.to(dev), e.to(dev), ls)
             total.backward()
             torch.cuda.synchronize()
             err = np.abs(res.grad.cpu().numpy() - gref).max() / np.abs(gref).max()
-            bound = 2e-5 if variant == "tc" else 3 * err_ref32
-            assert err <= bound, f"{variant}: d_residual relative error {err:.2e} (fp32 reference ops: {err_ref32:.2e})"
-            assert abs(total.item() - ref["loss"].item()) <= (2e-6 if variant == "tc" else 1e-4) * abs(ref["loss"].item()), variant
+            assert err <= 3 * err_ref32, f"{variant}: d_residual relative error {err:.2e} (fp32 reference ops: {err_ref32:.2e})"
+            assert abs(total.item() - ref["loss"].item()) <= 1e-5 * abs(ref["loss"].item()), variant
     finally:
         ops.set_agg_variant(None)

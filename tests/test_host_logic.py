@@ -181,7 +181,7 @@ def test_flat_bucket_roundtrip():
     c = torch.nn.Parameter(torch.randn(2), requires_grad=False)
     a.grad = torch.randn(3, 4)
     bucket = FlatBucket([a, b, c], extra=1)
-    assert bucket.flat.numel() == 12 + 5 + 1
+    assert bucket.flat.numel() == 12 + 5 + 1 + 2          # gradients | loss slot | one 'touched' flag per parameter
     ga = a.grad.clone()
     bucket.pack(torch.tensor([2.5]))
     bucket.all_reduce()                       # no process group: identity
@@ -189,6 +189,10 @@ def test_flat_bucket_roundtrip():
     bucket.unpack()
     assert torch.equal(a.grad, ga) and torch.equal(b.grad, torch.zeros(5)) and c.grad is None
     assert float(bucket.tail[0]) == 2.5
+    # `a` had a gradient, `b` had none: the flags say so, and drop_untouched gives `b` back grad = None (the reference's
+    # zero_grad(set_to_none) semantics: Adam skips a parameter nobody's backward reached)
+    assert bucket.flags.tolist() == [1.0, 0.0]
+    assert bucket.drop_untouched(bucket.flags) == 1 and b.grad is None and a.grad is not None
 
 
 def test_param_groups_follow_reference_rule():
@@ -196,7 +200,9 @@ def test_param_groups_follow_reference_rule():
     net, _ = _net(P=4, R=4)
     groups = param_groups_weight_decay(net, 1e-5)
     no_decay = {id(p) for p in groups[0]["params"]}
-    assert id(net.logit_scale) in no_decay and id(net.mil_encoder.visual_adapter.bias) in no_decay
+    # optim/optim_factory.py:25-37 tests `len(param.shape) == 1`: the bias is exempt, the 0-dim logit_scale is NOT
+    assert id(net.mil_encoder.visual_adapter.bias) in no_decay
+    assert id(net.logit_scale) not in no_decay
     assert id(net.mil_encoder.visual_adapter.weight) not in no_decay
     assert id(net.mil_encoder.Q.residual_features) not in no_decay
     assert sum(p.numel() for g in groups for p in g["params"]) == 1 + 512 * 512 + 512 + 4 * 512
@@ -295,7 +301,8 @@ def test_flat_bucket_attached_gradients_alias_the_bucket():
         loss(a, step).backward(); loss(b, step).backward()
         loss(b, step).backward()                       # accumulation into the attached views
         plain.pack(torch.tensor([step])); att.pack(torch.tensor([step]))
-        assert torch.allclose(att.flat[:-1], 2 * plain.flat[:-1]) and float(att.tail[0]) == step
+        assert torch.allclose(att.flat[:17], 2 * plain.flat[:17]) and float(att.tail[0]) == step
+        assert att.flags.tolist() == [1.0, 1.0] and plain.flags.tolist() == [1.0, 1.0]
         plain.all_reduce(); att.all_reduce(); plain.unpack(); att.unpack()
         assert all(p.grad.data_ptr() == seg.data_ptr() for p, seg in att._views())
         assert torch.allclose(b[0].grad, 2 * a[0].grad) and torch.allclose(b[1].grad, 2 * a[1].grad)

@@ -141,3 +141,38 @@ def test_variant_oracle_matches_reference(case):
             ref = gold[f"{key}_{tag}"]
             np.testing.assert_allclose(val, ref, rtol=10 * tol, atol=tol * max(1.0, float(np.abs(ref).max())),
                                        err_msg=f"{key}_{tag}")
+
+
+@pytest.mark.parametrize("name", golden_cases("interp_"))
+def test_interpretation_oracle_matches_reference_own_routine(name):
+    """The oracle's decoupled similarities / Shapley values vs the reference's OWN calc_text_img_similarity and
+    evaluate_prototype_shap_imp (utils/model_inference.py:21-144), run unmodified by make_golden_r02.py."""
+    from golden_util import rebuild_interp
+    case = load_case(name)
+    X, pr = rebuild_interp(case)
+    c = lambda z: z.double()
+    Q64 = O.task_res_query(c(pr["prompt_features"]), c(pr["residual_features"]), pr["res_ratio"])
+    A, probs, probs2, dec = O.decoupled_similarity(c(X).unsqueeze(0), Q64, c(pr["W"]), c(pr["b"]), c(pr["text_features"]),
+                                                   c(pr["logit_scale"]))
+    k = case["cottn_head_f64"].shape[1]
+    np.testing.assert_allclose(A[:, :k].numpy(), case["cottn_head_f64"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(probs.numpy(), case["probs_f64"], atol=1e-12)
+    np.testing.assert_allclose(probs2.numpy(), case["probs2_f64"], atol=1e-12)
+    ls = float(pr["logit_scale"].double().exp())
+    np.testing.assert_allclose(torch.softmax(ls * dec, dim=0).numpy(), case["imp_f64"], atol=1e-12)
+    if int(case["P"]) <= 8:                       # the subset-by-subset port is O(P 4^P) Python
+        np.testing.assert_allclose(O.prototype_shap_imp(dec.float(), ls).numpy(), case["shap_f64"], atol=2e-5)
+    # the reference's identity (notebook cell 12 == cell 17): both routes give the same prediction
+    np.testing.assert_allclose(case["probs_f64"], case["probs2_f64"], atol=1e-10)
+
+
+@pytest.mark.parametrize("name", golden_cases("zeroshot2_"))
+def test_zero_shot_feature_pooling_matches_reference(name):
+    from golden_util import rebuild_zeroshot2
+    case = load_case(name)
+    X, pr = rebuild_zeroshot2(case)
+    preds, pooled, g, Tn = O.vlsa_forward_zero_shot(X.unsqueeze(0), pr["text_features"], pr["logit_scale"], str(case["pooling"]))
+    np.testing.assert_allclose(pooled.numpy(), case["logits_f32"], rtol=2e-5, atol=2e-5)
+    assert tuple(g.shape) == tuple(case["feats_shape"])
+    np.testing.assert_allclose(g[:8].numpy(), case["feats_head_f64"], atol=2e-6)
+    np.testing.assert_allclose(Tn.numpy(), case["Tn_f32"], atol=1e-6)

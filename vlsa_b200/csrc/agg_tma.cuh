@@ -1,6 +1,26 @@
-// Fused language-guided aggregation on the 5th-generation tensor cores, TMA-fed (round-2 kernel for fp32 rows, P > 5).
-// Same contract and the same two contractions as agg_tc_kernel (agg_tc.cuh: GEMM1 scores, GEMM2 weighted sums, fp16
-// hi / lo planes, Qn' resident in TMEM, lazy-rescaled softmax) — what changed is how the rows get on chip:
+// Fused language-guided aggregation on the 5th-generation tensor cores (tcgen05 + TMEM), TMA-fed, forward and backward
+// (fp32 rows, P > 5).  Same contract as agg_simt_kernel<P,BWD,float>: ONE read of X, per-chunk partials — forward:
+// online-softmax (m, l, O[P,D]); backward: partial dQn[P,D] — with both skinny contractions on tcgen05.mma (kind::f16,
+// fp32 accumulators in TMEM), issued by one elected thread per GEMM:
+//
+//   GEMM1  S^T[128, 32]  = Qn'[128, 512] (A, resident in TMEM) . [X_hi ; X_lo][32, 512]^T (B, K-major smem)
+//   GEMM2  O^T[512 d, 32 | 16] += X_hi^T | X_lo^T [512, 16] (A, MN-major, the SAME smem bytes) . W[32 | 16, 16]^T
+//
+// Precision design (the tensor core truncates its fp32 accumulator toward zero after every instruction, so the number of
+// accumulation steps per accumulator is kept small):
+//   * every row of X is split into fp16 (hi, lo) planes: 22 significant bits at 4 bytes of shared memory per element;
+//     Qn is split the same way;
+//   * A-operand row (TMEM lane) 32 w + j holds prototype p = 4 w + (j & 3), part (j >> 2) & 1 (hi / lo) of Qn restricted
+//     to the feature range 128 (j >> 3) .. +127 (zeros elsewhere): every accumulator only sees 8 non-zero steps, and the
+//     16 partial sums of a score (2 parts x 4 ranges x 2 planes) are added in fp32 registers.  TMEM quadrant q therefore
+//     owns prototypes 4 q .. 4 q + 3 completely;
+//   * the per-row weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); products with the hi and
+//     the lo plane of X accumulate in separate TMEM columns (a merged accumulator costs the backward three orders of
+//     magnitude of gradient accuracy: tiny lo-plane products are absorbed by a large, cancelling accumulator);
+//     tcgen05.mma needs A and B in the same 16-bit format, hence fp16 weights kept in range by a lazily rescaled softmax
+//     reference (forward) / a lazily grown power-of-two normaliser per prototype (backward, exact rescale).
+//
+// How the rows get on chip (what round 2 changed against the register-staged kernel of round 1):
 //
 //   * measured (scripts/dev_mma_sweep.cu, dev_mma_mix.cu, profiles/mma_r02.md): the tensor pipe needs ~1 400 cycles for
 //     the 48 MMAs of 32 rows, half the HBM budget of those rows (2 900 cycles at 6.5 TB/s) — the register-staged kernel
@@ -29,7 +49,8 @@
 #pragma once
 #include <cuda.h>
 
-#include "agg_tc.cuh"
+#include "agg_simt.cuh"
+#include "tc_common.cuh"
 
 namespace vlsa {
 
@@ -201,7 +222,11 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
         }
         float4 dvr[BWD ? 8 : 1];                               // dv / P at this lane's columns (backward)
         int dv_bag = -1;
-        uint32_t tt = 0;
+        uint32_t b = 0, ph = 0;                                // ring position and phase of the current tile
+        const uint32_t unit_off = (2 * wq) * C::SLOT + g * C::GRP, prow_off = (8 * g + jr) * 4;
+        float4 v[2][4];                                        // the lane's 32 raw values of the current tile
+        bool loaded = false;                                   // ... already fetched by the previous iteration
+        auto more_tiles = [&](int c, int t, int ntiles) { return t + 1 < ntiles || c + int(gridDim.x) < prm.total_chunks; };
         PROF_DECL
         for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
             int bag; long long r0, r1;
@@ -219,19 +244,20 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                         dvr[BWD ? 4 * k + i : 0] = make_float4(t4.x * invP, t4.y * invP, t4.z * invP, t4.w * invP);
                     }
             }
-            for (int t = 0; t < ntiles; ++t, ++tt) {
-                const uint32_t b = tt % C::NBUF, u = tt / C::NBUF;
-                unsigned char* unit0 = ring + b * C::TILE + (2 * wq) * C::SLOT + g * C::GRP;
-                const int row = 8 * g + jr;
-                PROF_BEGIN();
-                mbar_wait_wd(landed + b, u & 1u);
-                PROF_END(0);
-                // phase 1: both 2 KB units into registers, partial |x|^2 (and dv . x / P) of the lane's row
-                float4 v[2][4];
+            for (int t = 0; t < ntiles; ++t) {
+                unsigned char* unit0 = ring + b * C::TILE + unit_off;
+                float* pss = s_pssq + b * (TR * 4) + prow_off;
+                // phase 1: both 2 KB units into registers (already there if the previous iteration found the tile landed),
+                // partial |x|^2 (and dv . x / P) of the lane's row
+                if (!loaded) {
+                    PROF_BEGIN();
+                    mbar_wait_wd(landed + b, ph);
+                    PROF_END(0);
 #pragma unroll
-                for (int k = 0; k < 2; ++k)
+                    for (int k = 0; k < 2; ++k)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v[k][i] = *reinterpret_cast<const float4*>(unit0 + k * C::SLOT + ld_off[i]);
+                        for (int i = 0; i < 4; ++i) v[k][i] = *reinterpret_cast<const float4*>(unit0 + k * C::SLOT + ld_off[i]);
+                }
                 float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, u2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
@@ -254,15 +280,15 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                     uu += __shfl_xor_sync(0xffffffffu, uu, 2);
                 }
                 if (qd == 0) {
-                    s_pssq[(b * TR + row) * 4 + wq] = ss;
-                    if (BWD) s_pu[(b * TR + row) * 4 + wq] = uu;
+                    pss[wq] = ss;
+                    if (BWD) pss[C::NBUF * TR * 4 + wq] = uu;              // s_pu follows s_pssq
                 }
                 PROF_BEGIN();
                 named_bar_sync(8 + g, 128);                    // the four warps of this row group
                 PROF_END(1);
                 // phase 2: full-row norm; rows with |x| in [2, 2^14) are split as they are (every CONCH-like row), any other
                 // row is first scaled by a power of two (|x~| in [1, 2)) that the weight warps undo exactly
-                const float4 pp = *reinterpret_cast<const float4*>(s_pssq + (b * TR + row) * 4);
+                const float4 pp = *reinterpret_cast<const float4*>(pss);
                 const float ssq = ((pp.x + pp.y) + pp.z) + pp.w;
                 uint32_t ex = __float_as_uint(ssq) >> 23;                  // biased exponent (ssq >= 0)
                 if (ex == 0u || ex >= 255u) ex = 127u;                     // zero / denormal / non-finite rows: scale 1
@@ -275,6 +301,7 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { v[k][i].x *= sc; v[k][i].y *= sc; v[k][i].z *= sc; v[k][i].w *= sc; }
                 }
+#ifndef VLSA_TMA_NOCONV        // development: time the kernel without the fp16 split (results are garbage)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -286,6 +313,7 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                         *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
                         *reinterpret_cast<uint2*>(dst + 1024) = make_uint2(l0, l1);
                     }
+#endif
                 if (wq == 0 && qd == 0) {
                     // row info: score = info.x (Qn . x~), info.x = scale / max(|x~|, eps 2^-e), 2^e = info.y,
                     // info.z = dv . x / P (backward).  1 / |x~| = rsqrt + one Newton step.
@@ -298,17 +326,30 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                     info.x = prm.scale * y;
                     info.z = 0.f;
                     if (BWD) {
-                        const float4 u4 = *reinterpret_cast<const float4*>(s_pu + (b * TR + row) * 4);
+                        const float4 u4 = *reinterpret_cast<const float4*>(pss + C::NBUF * TR * 4);
                         info.z = ((u4.x + u4.y) + u4.z) + u4.w;
                     }
                     info.w = 0.f;
-                    *reinterpret_cast<float4*>(s_rowinfo + (b * TR + row) * 4) = info;
+                    *reinterpret_cast<float4*>(pss - C::NBUF * TR * 4) = info;          // s_rowinfo precedes s_pssq
+                }
+                // the raw rows of the next tile (whatever chunk it belongs to) are fetched before the proxy fence of this one
+                // if they have landed: their latency hides behind the fence, the arrive and the loop top
+                const uint32_t bn = b + 1 == C::NBUF ? 0u : b + 1, phn = bn == 0u ? ph ^ 1u : ph;
+                loaded = more_tiles(c, t, ntiles) && mbar_try_wait(landed + bn, phn);
+                loaded = __all_sync(0xffffffffu, loaded);
+                if (loaded) {
+                    const unsigned char* un = ring + bn * C::TILE + unit_off;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) v[k][i] = *reinterpret_cast<const float4*>(un + k * C::SLOT + ld_off[i]);
                 }
                 PROF_BEGIN();
                 fence_proxy_async_smem();
                 PROF_END(2);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + b);
+                b = bn; ph = phn;
             }
         }
         PROF_FLUSH(0, 3, cw == 0 && lane == 0)
@@ -446,9 +487,14 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                 bw_il = 1.f / __ldg(prm.ml + (size_t(bag) * P + p) * 2 + 1);
                 bw_delta = __ldg(prm.delta + size_t(bag) * P + p);
             }
-            for (int t = 0; t < ntiles; ++t, ++tt) {
-                if (int(tt & 1u) != set) continue;
-                const uint32_t v = tt >> 1, b = tt % C::NBUF, u = tt / C::NBUF;
+            // own tiles of this chunk: t = t_first, t_first + 2, ...; tt0 = index of the chunk's first tile in the CTA's sequence
+            const uint32_t tt0 = tt;
+            const int t_first = int((uint32_t(set) ^ tt0) & 1u);
+            uint32_t b = (tt0 + t_first) % C::NBUF, ph = ((tt0 + t_first) / C::NBUF) & 1u;
+            tt = tt0 + uint32_t(ntiles);                           // for the next chunk
+            for (int t = t_first; t < ntiles; t += 2, b += 2u) {
+                if (b >= uint32_t(C::NBUF)) { b -= C::NBUF; ph ^= 1u; }
+                const uint32_t tt = tt0 + uint32_t(t), v = tt >> 1;
                 const int nvalid = min(TR, chunk_nrows - t * TR);
                 PROF_BEGIN();
                 mbar_wait_wd(s_ready + set, v & 1u);
@@ -479,7 +525,7 @@ __global__ void __launch_bounds__(TmaCfg::THREADS, 1) agg_tma_kernel(const AggPa
                     __syncwarp();
                 }
                 PROF_BEGIN();
-                mbar_wait_wd(full + b, u & 1u);                        // acquire the converters' row info
+                mbar_wait_wd(full + b, ph);                            // acquire the converters' row info
                 PROF_END(1);
                 float4 info[2];
 #pragma unroll

@@ -9,7 +9,6 @@
 #include <atomic>
 
 #include "agg_simt.cuh"
-#include "agg_tc.cuh"
 #include "agg_tma.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
@@ -54,8 +53,8 @@ using namespace vlsa;
     }
 #endif
 
-static constexpr int kRowTile = 32;   // TcCfg::TR; a multiple of the CUDA-core kernel's AggCfg::TN
-static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile == TcCfg::TR, "chunk_rows must suit both streaming kernels");
+static constexpr int kRowTile = 32;   // a multiple of TmaCfg::TR and of the CUDA-core kernel's AggCfg::TN
+static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile % TmaCfg::TR == 0, "chunk_rows must suit both streaming kernels");
 
 static int device_sm_count() {
     int dev = 0, sms = 0;
@@ -154,20 +153,6 @@ static int launch_agg(const AggParams& prm, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
-// register-staged tcgen05 kernel of round 1 (kept for cross-checks: VLSA_KERNEL_TC_REG)
-template <bool BWD>
-static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
-    using C = TcCfg;
-    auto kern = agg_tc_kernel<BWD>;
-    static std::atomic<int> cache[kMaxDevices];
-    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
-    const int sms = device_sm_count();
-    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
-    if (grid <= 0) return 0;
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P);
-    return static_cast<int>(cudaGetLastError());
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -214,19 +199,18 @@ static int launch_agg_tma(const AggParams& prm, int P, long long total_rows, cud
 // Which streaming kernel serves a pass.  Default: the TMA-fed tcgen05 kernel for fp32 rows and P > 5 (the CUDA-core
 // kernel is at the HBM roofline for P <= 5); bf16 rows run on CUDA cores.  The caller can force a
 // kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
-enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTcReg = 2 };
+enum AggKernel { kAggSimt = 0, kAggTma = 1 };
 static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     if (dtype != VLSA_DTYPE_F32) return kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTma;
-    if (x_dtype_flags & VLSA_KERNEL_TC_REG) return kAggTcReg;
     return P > 5 ? kAggTma : kAggSimt;
 }
 static bool dtype_ok(int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
-           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_KERNEL_TC_REG)) == 0;
+           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC)) == 0;
 }
 
 // prototypes per launch of the per-prototype-gradient backward (measured best, profiles/variant_time_r01.json)
@@ -235,7 +219,6 @@ static constexpr int kGenGroup = 8;
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long total_rows, cudaStream_t st) {
     const AggKernel k = agg_kernel_choice(P, x_dtype);
     if (k == kAggTma) return launch_agg_tma<false>(prm, P, total_rows, st);
-    if (k == kAggTcReg) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
@@ -410,9 +393,6 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
     const AggKernel kern = total_chunks > 0 ? agg_kernel_choice(P, x_dtype) : kAggSimt;
     if (kern == kAggTma) {
         rc = launch_agg_tma<true>(prm, P, total_rows, st);
-        if (rc) return rc;
-    } else if (kern == kAggTcReg) {
-        rc = launch_agg_tc<true>(prm, P, st);
         if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {

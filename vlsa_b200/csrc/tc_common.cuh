@@ -1,6 +1,9 @@
 // tcgen05 / TMEM / UMMA-descriptor helpers (sm_100a).  Raw PTX; layouts follow the PTX ISA canonical
 // shared-memory layouts for tcgen05.mma (128-byte swizzle) — see DESIGN.md §4 (tensor-core variant).
 #pragma once
+#include <cuda_fp16.h>
+#include <stdio.h>
+
 #include "common.cuh"
 
 namespace vlsa {
@@ -135,11 +138,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
     return ok != 0;
 }
+// Fast path first: one try_wait (it sleeps in hardware up to its suspend hint) decides almost every wait.  The watchdog
+// loop stays INLINE: moving it into a __noinline__ function made the backward of agg_tma_kernel fault intermittently
+// (illegal address, only without compute-sanitizer) — a call from single-elected-lane / tcgen05 code is not worth it.
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_hint(bar, parity, 4000u)) return;
     uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, 4000u)) {
+    do {
         if (++spins > (1u << 22)) { printf("vlsa: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
+    } while (!mbar_try_wait_hint(bar, parity, 4000u));
 }
 
 // x = hi + lo with hi, lo bf16 (16 significant bits in total); packs (a, b) -> bf16x2 with a in the low half
@@ -147,6 +154,28 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
     const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+
+// x = hi + lo with hi, lo fp16 (packed pairs, first element in the low half); SASS: 2 F2FP + 2 HADD2.F32 + 1 FADD2
+__device__ __forceinline__ void split_f16x2(float2 a, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __float22half2_rn(a);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __float22half2_rn(__fadd2_rn(a, make_float2(-hf.x, -hf.y)));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    split_f16x2(make_float2(a, b), hi, lo);
+}
+
+// barrier among `nthreads` threads that also ORs a predicate across them (bar.red.or)
+__device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %3, 0;\n\t"
+        "bar.red.or.pred r, %1, %2, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+        : "=r"(out) : "r"(id), "r"(nthreads), "r"(uint32_t(pred)) : "memory");
+    return out != 0;
 }
 
 }  // namespace vlsa

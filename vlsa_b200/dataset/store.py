@@ -106,6 +106,10 @@ class PatchFeatureStore:
     def read_into(self, sids: Sequence[str], out: torch.Tensor) -> int:
         """Copy the rows of the slides ``sids`` (in that order: PatchWSI.py:205-212) into ``out`` [>= n, 512];
         returns the number of rows written.  Missing slides are skipped with the reference's warning."""
+        if out.dtype != self.dtype:
+            # a bf16 store holds raw 16-bit patterns: copying them into an fp32 tensor would convert the BITS numerically
+            raise TypeError(f"read_into: destination is {out.dtype} but the store holds {self.dtype}; read into a "
+                            f"{self.dtype} tensor and convert explicitly")
         dst = self._view(out)
         r = 0
         for sid in sids:
@@ -113,6 +117,7 @@ class PatchFeatureStore:
                 print(f"[WSIPatchSurv] warning: not found slide {sid}.")
                 continue
             off, n = self.slides[sid]
+            # same element width on both sides; 'unsafe' only reinterprets int16 <-> uint16 bit patterns of bf16
             np.copyto(dst[r:r + n], self._mm[off:off + n], casting="unsafe" if dst.dtype != self._mm.dtype else "same_kind")
             r += n
         return r

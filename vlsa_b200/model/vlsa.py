@@ -96,13 +96,21 @@ class VLSA(nn.Module):
         Xp = X[0].contiguous()
         text_features = self._text_features_for_kernels()
         if isinstance(self.mil_encoder, deepmil.FeatMIL):
-            if Xp.shape[0] > 1 and self.mil_encoder.pooling not in ("mean", "max"):
-                _, pooled = ops.logit_pool(Xp, text_features.detach().contiguous(), self.logit_scale,
-                                           self.image_encoder_cfg["pooling"])
-                Tn = torch.nn.functional.normalize(text_features, dim=-1)
-                # image_features of the zero-shot arm are the N normalised patches; callers discard them
-                return pooled, None, Tn
-            raise NotImplementedError("FeatMIL with mean/max feature pooling is not on the accelerated path")
+            # zero-shot arm (model/vlsa.py:188-198 with model/deepmil.py:51-67): inference only, nothing to differentiate
+            T = text_features.detach().contiguous()
+            pooling = self.mil_encoder.pooling
+            if pooling in ("mean", "max"):
+                # FeatMIL pools the patch FEATURES: one [1, 512] vector through the cosine head, logits stay [1, R]
+                return ops.feat_pool(Xp, T, self.logit_scale, pooling)
+            if Xp.shape[0] == 1:
+                # identity encoder, one patch: logits.shape[0] == 1, so the reference skips logit_pooling (vlsa.py:195)
+                return ops.feat_pool(Xp, T, self.logit_scale, "mean")
+            _, pooled = ops.logit_pool(Xp, T, self.logit_scale, self.image_encoder_cfg["pooling"])
+            Tn = torch.nn.functional.normalize(text_features, dim=-1)
+            # image_features of this arm are the N normalised patches (vlsa.py:188-189); callers that only want the pooled
+            # logits can switch the extra [N, 512] write off with `zero_shot_image_features = False`
+            feats = ops.row_normalize(Xp) if getattr(self, "zero_shot_image_features", True) else None
+            return pooled, feats, Tn
         plan = ops.make_plan([Xp.shape[0]], Xp.device)
         logits, g, Tn, _, _ = self._fused(Xp, plan, text_features)
         return logits, g, Tn

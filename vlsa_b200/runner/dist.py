@@ -56,13 +56,27 @@ class FlatBucket:
         self.params = [p for p in params if p.requires_grad]
         self.sizes = [p.numel() for p in self.params]
         self.extra = extra
-        total = sum(self.sizes) + extra
+        # tail = `extra` caller scalars, then one "received a gradient this step" flag per parameter (summed over the
+        # ranks by the same all-reduce): a parameter nobody touched keeps grad = None for the optimizer, as after the
+        # reference's zero_grad(set_to_none) — Adam must not decay its moments or apply weight decay to it
+        total = sum(self.sizes) + extra + len(self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._touched = [False] * len(self.params)
+        self._hooks = []
+        self._flag_stage = torch.zeros(len(self.params), dtype=torch.float32)
+        if dev.type == "cuda":
+            self._flag_stage = self._flag_stage.pin_memory()
 
     @property
     def tail(self) -> torch.Tensor:
-        return self.flat[len(self.flat) - self.extra:]
+        """The caller's `extra` scalars."""
+        n = len(self.flat) - self.extra - len(self.params)
+        return self.flat[n:n + self.extra]
+
+    @property
+    def flags(self) -> torch.Tensor:
+        return self.flat[len(self.flat) - len(self.params):]
 
     def _views(self):
         at = 0
@@ -77,14 +91,33 @@ class FlatBucket:
             if p.grad is not None and p.grad.data_ptr() != g.data_ptr():
                 g.copy_(p.grad)
             p.grad = g
+        if not self._hooks:
+            for i, p in enumerate(self.params):
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._touched.__setitem__(i, True)))
 
     def zero(self) -> None:
-        """Zero all gradients.  Attached: one memset of the bucket; otherwise `grad = None` like zero_grad()."""
+        """Zero all gradients.  Attached: one memset of the bucket (parameters detached by `drop_untouched` are
+        re-attached); otherwise `grad = None` like zero_grad()."""
+        self._touched = [False] * len(self.params)
+        if self._hooks:
+            for p, seg in self._views():
+                if p.grad is None or p.grad.data_ptr() != seg.data_ptr():
+                    p.grad = seg.view_as(p)
         if all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views()):
             self.flat.zero_()
         else:
             for p in self.params:
                 p.grad = None
+
+    def drop_untouched(self, flags_host) -> int:
+        """After the all-reduce: `grad = None` for every parameter whose flag summed to zero over the ranks (nobody's
+        backward reached it).  `flags_host` is a host copy of `self.flags`.  Returns how many were dropped."""
+        n = 0
+        for p, f in zip(self.params, flags_host.tolist()):
+            if f == 0.0:
+                p.grad = None
+                n += 1
+        return n
 
     def pack(self, extra_values: torch.Tensor | None = None) -> None:
         for p, seg in self._views():
@@ -97,6 +130,12 @@ class FlatBucket:
                 self.tail.zero_()
             else:
                 self.tail.copy_(extra_values.reshape(-1).to(self.flat.dtype))
+        if self.params:
+            if self._hooks:
+                self._flag_stage.copy_(torch.tensor(self._touched, dtype=torch.float32))
+            else:                                   # not attached: a parameter is touched iff it has a gradient
+                self._flag_stage.copy_(torch.tensor([p.grad is not None for p in self.params], dtype=torch.float32))
+            self.flags.copy_(self._flag_stage, non_blocking=True)
 
     def all_reduce(self) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -44,12 +44,13 @@ def create_output_converter(converter=None):
 
 
 def param_groups_weight_decay(model: torch.nn.Module, weight_decay: float):
-    """optim/optim_factory.py:25-37: no weight decay on 1-D parameters and biases."""
+    """optim/optim_factory.py:25-37 (`add_weight_decay`): no weight decay on parameters with ONE dimension and on biases.
+    `len(param.shape) == 1` as in the reference: the 0-dim `logit_scale` is decayed there, so it is here."""
     decay, no_decay = [], []
     for name, p in model.named_parameters():
         if not p.requires_grad:
             continue
-        if p.dim() <= 1 or name.endswith(".bias"):
+        if len(p.shape) == 1 or name.endswith(".bias"):
             no_decay.append(p)
         else:
             decay.append(p)
@@ -84,8 +85,16 @@ class VLSAHandler:
             if n not in ("SurvIFMLE", "SurvEMD"):
                 raise NotImplementedError(f"loss {n} is not part of the accelerated VLSA path")
         self.loss_weight = {n: float(cfg.get(f"loss_{n.lower()}_weight", 1.0)) for n in names}
+        # loss options the fused kernel does not implement must not be ignored silently (loss/loss_surv_ext.py:58-69,
+        # loss/loss_surv.py:127-143): the shipped configs use p = 2, raw distance, mean reduction, eps 1e-7
+        for key, ok in (("loss_survemd_p", lambda v: int(v) == 2), ("loss_survemd_raw_distance", lambda v: bool(v)),
+                        ("loss_survemd_reduction", lambda v: v == "mean"), ("loss_survifmle_reduction", lambda v: v == "mean"),
+                        ("loss_survemd_eps", lambda v: abs(float(v) - 1e-7) < 1e-12)):
+            if key in cfg and not ok(cfg[key]):
+                raise NotImplementedError(f"{key}={cfg[key]!r} is not implemented by the fused survival loss kernel")
         self.objective = SurvObjective(self.loss_weight.get("SurvIFMLE", 0.0), self.loss_weight.get("SurvEMD", 0.0),
-                                       alpha=float(cfg.get("loss_survifmle_alpha", 0.0)))
+                                       alpha=float(cfg.get("loss_survifmle_alpha", 0.0)),
+                                       eps=float(cfg.get("loss_survifmle_eps", 1e-7)))
         self.output_converter = create_output_converter(cfg.get("net_output_converter", "softmax"))
         assert cfg.get("opt_name", "adam") == "adam", "only Adam is wired (cfg_vlsa_conch.yaml:111)"
         self.optimizer = torch.optim.Adam(param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5))),
@@ -152,8 +161,10 @@ class VLSAHandler:
         self.bucket.pack(local_loss.reshape(1))
         self.bucket.all_reduce()
         self.bucket.unpack()
+        tail = self.bucket.flat[-(1 + len(self.bucket.params)):].cpu()         # loss + per-parameter "touched" flags
+        self.bucket.drop_untouched(tail[1:])
         self.optimizer.step()
-        val_loss = float(self.bucket.tail[0])
+        val_loss = float(tail[0])
         val_preds = vdist.all_reduce_rows(local_pred, mine, n_sample).cpu()
         return val_loss, val_preds
 
