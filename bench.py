@@ -4,9 +4,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-A step = one pass of the hot path (VLSA.forward for every bag) over one batch of 32 synthetic bags of
-N=50k CONCH-like rows (D=512, P=R=4, fp32) per GPU; bags shard across ranks with no data-path
-collective (weak scaling).  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement.
+A step = one pass of the hot path (VLSA.forward for every bag, through the public `VLSA.forward_packed`) over one
+batch of 32 synthetic bags of N=50k CONCH-like rows (D=512, P=R=4, fp32) per GPU; bags shard across ranks with no
+data-path collective (weak scaling).  Prints ONE JSON line (rank 0) that also carries: the dominant kernel's roofline,
+the training step, the shipped-checkpoint shape P=R=12 (`shipped_shape`), a ragged step (`ragged`), the end-to-end
+numbers (cold: every step from pinned host memory; cached: steps drawn from a device-resident cohort), the reference's
+eager-torch op sequence timed on the same GPU (`torch_gpu_baseline`) and on the host cores (`cpu_baseline`).
+See DESIGN.md §Measurement.
 """
 from __future__ import annotations
 
@@ -28,7 +32,7 @@ import torch
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bag-rows", type=int, default=50000, help="N, patches per bag")
@@ -39,6 +43,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (config 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shipped", action="store_true", help="skip the P=R=12 (shipped checkpoint shape) record")
+    ap.add_argument("--no-ragged", action="store_true", help="skip the ragged-step record (N_i ~ LogUniform(1k,100k))")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the eager-torch reference timed on the same GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -158,65 +165,89 @@ def synth_batch_device(n_bags, rows, dev, seed, dtype):
     return X
 
 
-def cpu_port_throughput(rows, P, R, seconds, threads):
-    """The oracle port (torch CPU restatement of the reference forward) on a bounded sample:
-    G1 bags of `rows` rows, forward only, repeated until ~`seconds` s of CPU work."""
+def _reference_forward_fn(P, R, device):
+    """(callable X[1,N,512] -> incidence, kind): the vendored unmodified reference when baseline/_ref is present
+    (kind 'reference'), else the oracle port of the same ATen op sequence (kind 'port')."""
+    from vlsa_b200 import synth
+    pr = synth.make_params(P, R, 1)
+    try:
+        from baseline import ref_harness as RH
+        if RH.available():
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                net = RH.build_reference_vlsa(pr, P, device=device)
+
+            def fwd(X):
+                logits, _, _ = net(X)                                   # model/vlsa.py:181-198, verbatim
+                return torch.softmax(logits, dim=-1)                    # utils/func.py:44
+            return fwd, "reference"
+    except Exception as ex:  # pragma: no cover
+        print(f"[bench] vendored reference unavailable ({ex!r}); timing the oracle port", file=sys.stderr)
     from oracle import vlsa_oracle as O
+    dev_pr = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in pr.items()}
+    Q = O.task_res_query(dev_pr["prompt_features"], dev_pr["residual_features"], dev_pr["res_ratio"])
+
+    def fwd(X):
+        return O.softmax_converter(O.vlsa_forward(X, Q, dev_pr["W"], dev_pr["b"], dev_pr["text_features"], dev_pr["logit_scale"])[0])
+    return fwd, "port"
+
+
+def cpu_reference_throughput(rows, P, R, seconds, threads):
+    """The reference forward on the host cores on a bounded sample: G1 bags of `rows` rows, forward only, repeated
+    until ~`seconds` s of CPU work."""
     from vlsa_b200 import synth
     torch.set_num_threads(threads)
-    pr = synth.make_params(P, R, 1)
-    Q = O.task_res_query(pr["prompt_features"], pr["residual_features"], pr["res_ratio"])
+    fwd, kind = _reference_forward_fn(P, R, "cpu")
     bags = [synth.make_bag("g1", rows, 10 + i).unsqueeze(0) for i in range(2)]
     with torch.no_grad():
-        for X in bags:                                    # warm-up
-            O.softmax_converter(O.vlsa_forward(X, Q, pr["W"], pr["b"], pr["text_features"], pr["logit_scale"])[0])
+        for X in bags:
+            fwd(X)
         n, t0 = 0, time.perf_counter()
         while True:
-            X = bags[n % len(bags)]
-            O.softmax_converter(O.vlsa_forward(X, Q, pr["W"], pr["b"], pr["text_features"], pr["logit_scale"])[0])
+            fwd(bags[n % len(bags)])
             n += 1
             el = time.perf_counter() - t0
             if el >= seconds or n >= 4096:
                 break
-    return n / el, n, el
+    return n / el, n, el, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: same ATen op
-    sequence as model/deepmil.py:187-204 + model/vlsa.py:185-192), all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path — the vendored unmodified
+    model/vlsa.py + model/deepmil.py (baseline/_ref) when present, else the oracle port —, all host threads, rank 0
+    only, each step a bounded sample of the workload."""
     if rank != 0:
         return
-    from oracle import vlsa_oracle as O
     from vlsa_b200 import synth
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     P, R, rows = args.P, args.R, args.bag_rows
     sample_bags = 2                                        # a step = 2 of the 32 bags of the workload
-    pr = synth.make_params(P, R, 1)
-    Q = O.task_res_query(pr["prompt_features"], pr["residual_features"], pr["res_ratio"])
+    fwd, kind = _reference_forward_fn(P, R, "cpu")
     bags = [synth.make_bag("g1", rows, 10 + i).unsqueeze(0) for i in range(sample_bags)]
     if args.dtype == "bf16":
         bags = [b.to(torch.bfloat16).float() for b in bags]
+    steps, warm = min(args.steps, 20), min(args.warmup, 3)    # bounded: the whole arm ends within a minute or two
 
     def step():
         for X in bags:
-            O.softmax_converter(O.vlsa_forward(X, Q, pr["W"], pr["b"], pr["text_features"], pr["logit_scale"])[0])
+            fwd(X)
 
     with torch.no_grad():
-        for _ in range(args.warmup):
+        for _ in range(warm):
             step()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         el = time.perf_counter() - t0
-    value = args.steps * sample_bags / el
-    sample = f"{sample_bags} of the {args.bags} bags per step (N={rows}, P={P}, R={R}), {args.steps} steps"
+    value = steps * sample_bags / el
+    sample = f"{sample_bags} of the {args.bags} bags per step (N={rows}, P={P}, R={R}), {steps} steps"
     line = {
         "impl": "reference", "metric": "WSIs/sec at N=50k patches D=512", "value": value, "unit": "WSI/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": el / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": "WSI/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "WSI/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "WSI/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -226,12 +257,124 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
     return {
         "workload": f"configs[3] variable-N sweep at N={args.bag_rows}: batch={args.bags} bags/GPU/step, D=512, "
-                    f"P={args.P} prototypes, R={args.R} ranks, X {args.dtype}, VLSA.forward (aggregation + adapter + "
+                    f"P={args.P} prototypes, R={args.R} ranks, X {args.dtype}, VLSA.forward_packed (aggregation + adapter + "
                     f"cosine head + incidence softmax)",
         "bag_rows": args.bag_rows, "bags_per_gpu_per_step": args.bags, "global_bags_per_step": args.bags * world,
         "P": args.P, "R": args.R, "D": 512, "x_dtype": args.dtype, "parallelism": f"bag-sharded x{world} (no data-path collective)",
         "l2_policy": "inputs larger than L2: each step reads a 3.3 GB batch, 2 distinct batches alternate",
     }
+
+
+def build_net(P, R, dev, seed=1):
+    from vlsa_b200 import synth
+    from vlsa_b200.model import VLSA
+    pr = synth.make_params(P, R, seed)
+    net = VLSA(text_encoder_cfg={"name": "mahmoodlab/conch"},
+               image_encoder_cfg=dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, query="Text",
+                                      num_query=P, gated_query=False, query_pooling="mean", pred_head="default",
+                                      query_text_method="TaskRes", query_text_res_ratio=0.5),
+               prompt_learner_cfg={"name": "CoOp"}, text_features=pr["text_features"],
+               query_prompt_features=pr["prompt_features"], logit_scale_init=float(pr["logit_scale"]),
+               vlsa_api="CONCH", path_clip_model=None).to(dev)
+    with torch.no_grad():
+        net.mil_encoder.Q.residual_features.copy_(pr["residual_features"])
+        net.mil_encoder.visual_adapter.weight.copy_(pr["W"])
+        net.mil_encoder.visual_adapter.bias.copy_(pr["b"])
+    return net.eval()
+
+
+class Timer:
+    """K timed calls of fn(i) between CUDA events on the current stream, after W warm-ups, sync on both sides."""
+
+    def __init__(self, dev, sync_all):
+        self.dev, self.sync_all = dev, sync_all
+
+    def __call__(self, fn, steps, warmup=3):
+        for i in range(max(warmup, 3)):
+            fn(i)
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.sync_all()
+        return e0.elapsed_time(e1) / steps
+
+
+def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, esize, train=True, labels_seed=77):
+    """Forward through the public API, the dominant kernel alone, and one optimizer step, for one (P, R) on the given
+    device-resident batches.  `plans[i]` goes with `batches[i]`."""
+    from vlsa_b200 import ops, synth
+    net = build_net(P, R, dev)
+    nb = plans[0].num_bags
+    rows_total = sum(int(p.cu_rows_host[-1]) for p in plans) / len(plans)
+    algo_bytes = rows_total * 512 * esize
+    T = net.forward_text_only().contiguous()
+    with torch.no_grad():
+        ms_fwd = timer(lambda i: net.forward_packed(batches[i % len(batches)], plans[i % len(plans)], T), steps)
+    Q = net.mil_encoder.get_query().detach().contiguous()
+    wss = [ops._workspace(p, P, dev) for p in plans]
+    ms_k = timer(lambda i: ops.aggregate_partial_only(batches[i % len(batches)], plans[i % len(plans)], Q, wss[i % len(plans)]), steps)
+    rec = {"P": P, "R": R, "value": nb * world / (ms_fwd * 1e-3), "unit": "WSI/s", "ms_per_step": ms_fwd,
+           "kernel": "agg_tma_kernel<false> (tcgen05 + TMA)" if (P > 5 and esize == 4) else "agg_simt_kernel<P,0,XT>",
+           "kernel_ms": ms_k, "achieved_gbs": algo_bytes / (ms_k * 1e-3) / 1e9, "frac": algo_bytes / (ms_k * 1e-3) / 1e9 / peak,
+           "frac_whole_forward": algo_bytes / (ms_fwd * 1e-3) / 1e9 / peak}
+    if train:
+        from vlsa_b200.runner import VLSAHandler
+        cfg = {"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4}
+        net.train()
+        handler = VLSAHandler(cfg, net=net, device=dev)
+        t_lab, e_lab = synth.make_labels(nb, R, labels_seed + rank)
+        label = torch.stack([t_lab, e_lab], 1).to(dev)
+        n_global = nb * world
+
+        def train_step(i):
+            handler.bucket.zero()
+            logits, _, _, _ = handler.net.forward_packed(batches[i % len(batches)], plans[i % len(plans)])
+            loss = handler.calc_objective_loss(logits, label, norm=n_global)
+            loss.backward()
+            handler.bucket.pack(loss.detach().reshape(1))
+            handler.bucket.all_reduce()
+            handler.bucket.unpack()
+            handler.optimizer.step()
+
+        ms_t = timer(train_step, max(3, min(steps, 30)), warmup=5)
+        rec["train_step"] = {"value": nb * world / (ms_t * 1e-3), "unit": "WSI/s", "ms_per_step": ms_t,
+                             "hbm_gbs_over_two_reads": 2 * algo_bytes / (ms_t * 1e-3) / 1e9,
+                             "frac_of_peak": 2 * algo_bytes / (ms_t * 1e-3) / 1e9 / peak,
+                             "what": "VLSAHandler step on device-resident bags: forward_packed + SurvIFMLE/SurvEMD + "
+                                     "backward (X read twice) + one flat-bucket all-reduce + Adam"}
+        net.eval()
+    return rec
+
+
+def reduce_max(rec, dev, dist):
+    """Times are max over ranks, throughputs follow (in place, nested one level)."""
+    if dist is None or rec is None:
+        return rec
+    def fix(d):
+        keys = [k for k in ("ms_per_step", "kernel_ms") if k in d]
+        if not keys:
+            return
+        t = torch.tensor([d[k] for k in keys], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for k, v in zip(keys, t.tolist()):
+            scale = d[k] / v if v > 0 else 1.0
+            if k == "ms_per_step":
+                for kk in ("value", "hbm_gbs_over_two_reads", "frac_of_peak", "frac_whole_forward"):
+                    if kk in d:
+                        d[kk] *= scale
+            else:
+                for kk in ("achieved_gbs", "frac"):
+                    if kk in d:
+                        d[kk] *= scale
+            d[k] = v
+    fix(rec)
+    for v in rec.values():
+        if isinstance(v, dict):
+            fix(v)
+    return rec
 
 
 def main():
@@ -252,45 +395,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from vlsa_b200 import ops, synth
-    from vlsa_b200.dataset import AsyncBagLoader
-    from vlsa_b200.model import VLSA
+    from vlsa_b200.dataset import AsyncBagLoader, DeviceCohort
 
     P, R, rows, nb = args.P, args.R, args.bag_rows, args.bags
     xdtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     esize = 4 if args.dtype == "fp32" else 2
-    pr = synth.make_params(P, R, 1)
-
-    # ---- the model, through the public API -----------------------------------------------------------
-    net = VLSA(text_encoder_cfg={"name": "mahmoodlab/conch"},
-               image_encoder_cfg=dict(name="VLFAN", dim_in=512, dim_hid=256, use_feat_proj=False, query="Text",
-                                      num_query=P, gated_query=False, query_pooling="mean", pred_head="default",
-                                      query_text_method="TaskRes", query_text_res_ratio=0.5),
-               prompt_learner_cfg={"name": "CoOp"}, text_features=pr["text_features"],
-               query_prompt_features=pr["prompt_features"], logit_scale_init=float(pr["logit_scale"]),
-               vlsa_api="CONCH", path_clip_model=None).to(dev)
-    with torch.no_grad():
-        net.mil_encoder.Q.residual_features.copy_(pr["residual_features"])
-        net.mil_encoder.visual_adapter.weight.copy_(pr["W"])
-        net.mil_encoder.visual_adapter.bias.copy_(pr["b"])
-    net.eval()
-
-    # ---- device-resident inputs: 2 distinct batches (each >> L2) -------------------------------------
-    n_batches = 2
-    batches = [synth_batch_device(nb, rows, dev, 1234 + 100 * rank + i, xdtype) for i in range(n_batches)]
-    plan = ops.make_plan([rows] * nb, dev)
-    Q = net.mil_encoder.get_query().detach().contiguous()
-    W, b = net.mil_encoder.visual_adapter.weight.detach(), net.mil_encoder.visual_adapter.bias.detach()
-    T, ls = net.forward_text_only().contiguous(), net.logit_scale.detach()
-    ws = ops._workspace(plan, P, dev)
-    use_tc = args.dtype == "fp32" and P > 5 and os.environ.get("VLSA_AGG_VARIANT", "")[:1] != "s" \
-        or os.environ.get("VLSA_AGG_VARIANT", "")[:1] == "t" and args.dtype == "fp32"
-    kernel_name = "agg_tc_kernel<false> (tcgen05)" if use_tc else "agg_simt_kernel<P,0,XT>"
-    two_level = plan.total_chunks >= 8 * nb
-    # streaming kernel, [merge level 1,] merge, adapter, head
-    launches_per_step = 4 + (1 if two_level else 0)
-
-    def step(i):
-        return ops.aggregate_forward_raw(batches[i % n_batches], plan, Q, W, b, T, ls, need_bwd=False, workspace=ws)
+    peak, peak_src = measured_peaks()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -298,77 +408,89 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for i in range(max(args.warmup, 3)):
-        out = step(i)
-    sync_all()
+    timer = Timer(dev, sync_all)
+
+    # ---- device-resident inputs: 2 distinct batches (each >> L2) -------------------------------------
+    n_batches = 2
+    batches = [synth_batch_device(nb, rows, dev, 1234 + 100 * rank + i, xdtype) for i in range(n_batches)]
+    plan = ops.make_plan([rows] * nb, dev)
+    plans = [plan] * n_batches
     sampler = ClockSampler(local_rank)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = step(i)
-    e1.record()
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
-
-    # ---- dominant kernel alone (roofline): same inputs, events on the launching stream ---------------
-    for i in range(3):
-        ops.aggregate_partial_only(batches[i % n_batches], plan, Q, ws)
-    torch.cuda.synchronize(dev)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for i in range(args.steps):
-        ops.aggregate_partial_only(batches[i % n_batches], plan, Q, ws)
-    k1.record()
-    torch.cuda.synchronize(dev)
-    kernel_ms = k0.elapsed_time(k1) / args.steps
+    main_rec = measure_shape(P, R, batches, plans, dev, timer, args.steps, world, rank, peak, esize, train=not args.no_train)
     clocks = sampler.stop()
+    reduce_max(main_rec, dev, dist)
+    two_level = plan.total_chunks >= 8 * nb
+    launches_per_step = 4 + (1 if two_level else 0)        # streaming kernel, [merge level 1,] merge, adapter, head
 
-    # ---- one optimizer step (config 3): forward + fused loss + backward + ONE flat all-reduce + Adam ------
-    train = None
-    if not args.no_train:
-        from vlsa_b200.runner import VLSAHandler
-        cfg = {"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4}
-        net.train()
-        handler = VLSAHandler(cfg, net=net, device=dev)
-        t_lab, e_lab = synth.make_labels(nb, R, 77 + rank)
-        label = torch.stack([t_lab, e_lab], 1).to(dev)
-        n_global = nb * world
+    # ---- the shipped-checkpoint shape (assert/blca-train-VLSA/config.yaml: num_query 12, 12 time bins) --------------
+    shipped = None
+    if not args.no_shipped and (P, R) != (12, 12):
+        shipped = measure_shape(12, 12, batches, plans, dev, timer, max(10, args.steps // 2), world, rank, peak, esize,
+                                train=not args.no_train)
+        reduce_max(shipped, dev, dist)
 
-        def train_step(i):
-            handler.bucket.zero()
-            logits, _, _, _ = handler.net.forward_packed(batches[i % n_batches], plan)
-            loss = handler.calc_objective_loss(logits, label, norm=n_global)
-            loss.backward()
-            handler.bucket.pack(loss.detach().reshape(1))
-            handler.bucket.all_reduce()
-            handler.bucket.unpack()
-            handler.optimizer.step()
+    # ---- a ragged step: N_i ~ LogUniform(1k, 100k), fixed seeds (BASELINE configs[2]) ---------------------
+    ragged = None
+    if not args.no_ragged:
+        rs = np.random.RandomState(4321 + rank)
+        rag_sizes = [[int(v) for v in np.exp(rs.uniform(np.log(1e3), np.log(1e5), nb))] for _ in range(n_batches)]
+        for sz in rag_sizes:                               # the draws live inside the resident batches (nb * rows rows each)
+            while sum(sz) > nb * rows:
+                sz[int(np.argmax(sz))] //= 2
+        rag_plans = [ops.make_plan(sz, dev) for sz in rag_sizes]
+        rag_batches = [batches[i][: sum(rag_sizes[i])] for i in range(n_batches)]      # views of the resident rows
+        ragged = {"sizes_min_max_mean": [int(min(map(min, rag_sizes))), int(max(map(max, rag_sizes))),
+                                         float(np.mean([np.mean(s) for s in rag_sizes]))],
+                  "note": "32 bags/GPU/step, N_i ~ LogUniform(1k, 100k); fractions count the rows actually read"}
+        for (p_, r_) in ((P, R), (12, 12)):
+            rec = measure_shape(p_, r_, rag_batches, rag_plans, dev, timer, max(10, args.steps // 2), world, rank, peak,
+                                esize, train=not args.no_train)
+            reduce_max(rec, dev, dist)
+            ragged[f"P{p_}"] = rec
+            if (P, R) == (12, 12):
+                break
 
-        n_train = max(3, min(args.steps, 20))
-        for i in range(5):
-            train_step(i)
-        sync_all()
-        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0e.record()
-        for i in range(n_train):
-            train_step(i)
-        t1e.record()
-        sync_all()
-        train_ms = t0e.elapsed_time(t1e) / n_train
-        tt_ = torch.tensor([train_ms], device=dev)
-        if dist is not None:
-            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-        train_ms = float(tt_[0])
-        train = {"value": nb * world / (train_ms * 1e-3), "unit": "WSI/s", "ms_per_step": train_ms, "steps": n_train,
-                 "what": "VLSAHandler step on device-resident bags: forward_packed + SurvIFMLE/SurvEMD + backward "
-                         "(X read twice) + one flat-bucket all-reduce + Adam",
-                 "hbm_gbs_over_two_reads": 2 * nb * rows * 512 * esize / (train_ms * 1e-3) / 1e9}   # per GPU
-        net.eval()
+    # ---- the reference's eager-torch op sequence on the SAME GPU (BASELINE configs[1]) ----------------
+    torch_gpu = None
+    if not args.no_torch_gpu and rank == 0:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch_gpu = {"allow_tf32": False}
+        timer0 = Timer(dev, lambda: torch.cuda.synchronize(dev))          # rank 0 only: no barrier in here
+        for (p_, r_) in ((P, R), (12, 12)):
+            fwd, kind = _reference_forward_fn(p_, r_, dev)
+            ournet = build_net(p_, r_, dev)
+            with torch.no_grad():
+                # one optimizer step's worth: 32 bags, one call per bag as the reference's loops do
+                def ref_step(i):
+                    X = batches[i % n_batches]
+                    for b in range(nb):
+                        fwd(X[b * rows:(b + 1) * rows].unsqueeze(0))
+                ms_ref = timer0(ref_step, 5, warmup=3)
+                # single bag of 10k rows (configs[1]): the reference call vs VLSA.forward of this repo, same bag
+                xs = [batches[0][k * 10000:(k + 1) * 10000].unsqueeze(0) for k in range(8)]
+                ms_ref1 = timer0(lambda i: fwd(xs[i % 8]), 50, warmup=5)
+                ms_our1 = timer0(lambda i: ournet(xs[i % 8]), 50, warmup=5)
+                t0 = time.perf_counter()
+                for i in range(200):
+                    ournet(xs[i % 8])
+                torch.cuda.synchronize(dev)
+                wall_our1 = (time.perf_counter() - t0) / 200 * 1e3
+            torch_gpu[f"P{p_}"] = {"kind": kind, "step_32x50k": {"value": nb / (ms_ref * 1e-3), "unit": "WSI/s", "ms_per_step": ms_ref},
+                                   "single_bag_10k": {"reference_ms": ms_ref1, "vlsa_b200_ms": ms_our1,
+                                                      "vlsa_b200_wall_ms_per_call": wall_our1,
+                                                      "speedup": ms_ref1 / ms_our1}}
+            if (P, R) == (12, 12):
+                break
+        torch_gpu["what"] = ("the reference's VLSA.forward (model/vlsa.py:181-198 -> model/deepmil.py:170-215, unmodified, "
+                             "baseline/_ref) in eager PyTorch on this GPU, fp32, TF32 off, one call per bag")
 
     # ---- e2e: host buffers -> public API -> host result, copies inside the timed region --------------
-    e2e = None
+    e2e = e2e_cached = None
     if not args.no_e2e:
+        net = build_net(P, R, dev)
+        T = net.forward_text_only().contiguous()
         # one pinned 3.28 GB batch per rank, re-sent every step (8 ranks would otherwise pin 52 GB of host memory)
         host = [torch.empty(nb * rows, 512, dtype=xdtype).pin_memory()]
         host[0].copy_(batches[0])
@@ -376,9 +498,9 @@ def main():
         sizes = [rows] * nb
         n_e2e = max(3, min(args.steps, 10))
 
-        def source(n):
+        def source(n, with_index=False):
             for i in range(n):
-                yield host[i % len(host)], sizes, None, None
+                yield host[i % len(host)], sizes, None, (torch.arange(i * nb, (i + 1) * nb) if with_index else None)
 
         def run_e2e(n):
             loader = AsyncBagLoader(source(n), dev, depth=2, max_rows=nb * rows, dtype=xdtype)
@@ -403,55 +525,87 @@ def main():
             dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e = {"value": n_e2e * nb * world / float(e2e_t.item()), "unit": "WSI/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": nb * R * 4, "steps": n_e2e,
-               "path": "pinned host batch -> AsyncBagLoader (copy stream, 2-slot ring) -> VLSA.forward_packed -> pinned host incidence"}
+               "path": "epoch 1 / cold: pinned host batch -> AsyncBagLoader (copy stream, 2-slot ring) -> VLSA.forward_packed "
+                       "-> pinned host incidence (every row crosses PCIe every step, as in the reference's loop)"}
 
-    # ---- reduce over ranks ----------------------------------------------------------------------------
-    tt = torch.tensor([ms_total, kernel_ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_total, kernel_ms = float(tt[0]), float(tt[1])
+        # epoch >= 2 on a device-resident cohort: the bags were uploaded ONCE (by the same loader, into their final place);
+        # a step is drawn from the cohort by a row-range plan — per step the host sends the range table and reads the result
+        n_coh = 2
+        cohort = DeviceCohort(dev, n_coh * nb * rows, dtype=xdtype)
+        loader = AsyncBagLoader(source(n_coh, with_index=True), dev, depth=2, dtype=xdtype, cohort=cohort)
+        with torch.no_grad():
+            for batch in loader:                           # epoch 1 (untimed here: it is the cold path above)
+                batch.wait()
+                net.forward_packed(batch.X, batch.plan, T)
+        torch.cuda.synchronize(dev)
+        rs = np.random.RandomState(7 + rank)
+        n_cached = max(10, min(args.steps, 50))
+        orders = [rs.permutation(n_coh * nb)[:nb].tolist() for _ in range(n_cached + 3)]     # shuffled steps over the cohort
+
+        def run_cached(k0, n):
+            with torch.no_grad():
+                for i in range(n):
+                    pl = cohort.plan(orders[k0 + i])
+                    logits, g, Tn, inc = net.forward_packed(cohort.X, pl, T)
+                    res_host.copy_(inc, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        run_cached(0, 3)
+        sync_all()
+        t0 = time.perf_counter()
+        run_cached(3, n_cached)
+        c_s = time.perf_counter() - t0
+        c_t = torch.tensor([c_s], device=dev)
+        if dist is not None:
+            dist.all_reduce(c_t, op=dist.ReduceOp.MAX)
+        e2e_cached = {"value": n_cached * nb * world / float(c_t.item()), "unit": "WSI/s",
+                      "h2d_bytes_per_step": 2 * nb * 8 + (nb + 1) * 4, "d2h_bytes_per_step": nb * R * 4, "steps": n_cached,
+                      "cohort_bytes": cohort.nbytes,
+                      "path": "epoch >= 2: DeviceCohort (bags resident in HBM after their first upload) -> row-range plan "
+                              "(16 B per bag H2D) -> VLSA.forward_packed -> pinned host incidence; shuffled steps"}
+        del cohort, loader
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peaks()
-    algo_bytes = nb * rows * 512 * esize                  # X read exactly once
-    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
-    value = args.steps * nb * world / (ms_total * 1e-3)
     line = {
-        "metric": "WSIs/sec at N=50k patches D=512", "value": value, "unit": "WSI/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "metric": "WSIs/sec at N=50k patches D=512", "value": main_rec["value"], "unit": "WSI/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": main_rec["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.dtype == "fp32" else "f32 accumulate, bf16 storage", "data": "synthetic",
         "config": workload_config(args, world),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": kernel_name, "kernel_ms": kernel_ms,
-                     "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
-                     "kernel_share_of_step": kernel_ms / (ms_total / args.steps),
+        "roofline": {"bound": "hbm", "achieved": main_rec["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": main_rec["frac"],
+                     "traffic": None, "kernel": main_rec["kernel"], "kernel_ms": main_rec["kernel_ms"],
+                     "algorithmic_bytes_per_launch": nb * rows * 512 * esize, "peak_source": peak_src,
+                     "kernel_share_of_step": main_rec["kernel_ms"] / main_rec["ms_per_step"],
                      "read_only_ceiling_gbs": 7300.0,
                      "read_only_ceiling_source": "scripts/dev_readbw.cu on this pool: a pure cp.async.bulk read stream "
                                                  "of the same 3.28 GB (profiles/readbw_r01.txt)"},
-        "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "e2e": e2e, "train_step": train,
+        "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "e2e": e2e, "e2e_cached": e2e_cached,
+        "train_step": main_rec.get("train_step"), "shipped_shape": shipped, "ragged": ragged,
+        "torch_gpu_baseline": torch_gpu,
     }
-    if train is not None:
-        train["frac_of_peak"] = train["hbm_gbs_over_two_reads"] / peak   # per GPU
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    # DRAM traffic of the dominant kernel from the committed ncu capture of THIS build (null when the kernels changed since)
+    traffic_file = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if os.path.exists(traffic_file):
         try:
+            from vlsa_b200 import build as _build
             with open(traffic_file) as fh:
                 tj = json.load(fh)
             key = f"P{P}_N{rows}_B{nb}_{args.dtype}"
-            if key in tj:
+            if key in tj and tj[key].get("build_sha256") == _build._digest():
                 line["roofline"]["traffic"] = tj[key]["dram_bytes_per_launch"]
                 line["roofline"]["traffic_source"] = tj[key].get("source")
         except Exception:
             pass
     if not args.no_cpu_baseline and world == 1:            # rank 0 at N=1 only
         cores = os.cpu_count() or 1
-        v, n, el = cpu_port_throughput(rows, P, R, args.cpu_seconds, cores)
-        line["cpu_baseline"] = {"value": v, "unit": "WSI/s", "cores": cores, "kind": "port",
-                                "sample": f"{n} forwards of one N={rows} bag (P={P}, R={R}, fp32, torch CPU oracle port) in {el:.1f} s"}
+        v, n, el, kind = cpu_reference_throughput(rows, P, R, args.cpu_seconds, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "WSI/s", "cores": cores, "kind": kind,
+                                "sample": f"{n} forwards of one N={rows} bag (P={P}, R={R}, fp32, "
+                                          f"{'the unmodified reference modules (baseline/_ref)' if kind == 'reference' else 'torch CPU oracle port'}) in {el:.1f} s"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -45,6 +45,11 @@ extern "C" {
  * All kernels compute the same function (model/deepmil.py:187-203). */
 #define VLSA_KERNEL_SIMT 0x100   /* CUDA-core kernel (agg_simt_kernel) */
 #define VLSA_KERNEL_TC 0x200     /* TMA-fed tcgen05 kernel (agg_tma_kernel) */
+/* Optional bit of x_dtype of the vlsa_agg_* calls: `cu_rows` holds 2 B entries (first row, one past the last row) per bag
+ * instead of B + 1 offsets — the bags of the call lie anywhere inside X [total_rows, 512], in any order.  This is how a
+ * step is drawn from a device-resident cohort (every patient of a split uploaded once; the reference re-uploads every
+ * bag every epoch, runner/vlsa_handler.py:205) without a gather copy.  The plan (vlsa_agg_plan) only needs the sizes. */
+#define VLSA_ROWS_RANGES 0x1000
 
 #define VLSA_EINVAL (-1)      /* bad argument (null pointer, P/R/D out of range, ...) */
 #define VLSA_EWORKSPACE (-2)  /* workspace too small */

@@ -338,3 +338,51 @@ def test_flat_store_to_async_loader_to_forward(tmp_path, dev):
             X = torch.cat([slides[s] for s in pid2sids[pid]], 0).unsqueeze(0).to(dev)
             ref = torch.softmax(net(X)[0], -1).cpu().numpy()
             assert np.abs(got[i] - ref[0]).max() <= 2e-6
+
+
+def test_device_cohort_row_range_plans_match_packed_batches(dev):
+    """Steps drawn from a device-resident cohort (row-range plans, VLSA_ROWS_RANGES) against the same bags packed:
+    forward bit-identical for both streaming kernels, gradients equal, loader-filled cohort included."""
+    from vlsa_b200 import ops, synth
+    from vlsa_b200.dataset import AsyncBagLoader, DeviceCohort
+    from vlsa_b200.runner import VLSAHandler
+    sizes = [1000, 37, 2798, 1, 513, 64, 4096, 255]
+    bags = [synth.make_bag("g1", n, 700 + i) for i, n in enumerate(sizes)]
+    for P in (4, 12):
+        pr = synth.make_params(P, P, 60 + P)
+        net = build_net(pr, P, P, dev).eval()
+        # cohort filled by the loader in two steps (bags 0-3, 4-7), each copied straight into its final place
+        cohort = DeviceCohort(dev, sum(sizes) + 100)
+        steps = [(bags[:4], None, torch.arange(0, 4)), (bags[4:], None, torch.arange(4, 8))]
+        loader = AsyncBagLoader(iter(steps), dev, depth=2, cohort=cohort)
+        with torch.no_grad():
+            first = []
+            for batch in loader:
+                batch.wait()
+                first.append(net.forward_packed(batch.X, batch.plan)[3])
+        assert len(cohort) == 8 and cohort.rows == sum(sizes)
+        # a shuffled step with a repeated bag, drawn from the cohort vs packed by hand
+        order = [6, 1, 3, 0, 6, 7]
+        with torch.no_grad():
+            inc_c = net.forward_packed(cohort.X, cohort.plan(order))[3]
+            Xp = torch.cat([bags[i] for i in order], 0).to(dev)
+            inc_p = net.forward_packed(Xp, ops.make_plan([sizes[i] for i in order], dev))[3]
+        assert torch.equal(inc_c, inc_p)
+        assert torch.equal(first[0], net.forward_packed(torch.cat(bags[:4], 0).to(dev), ops.make_plan(sizes[:4], dev))[3])
+        # one optimizer step from the cohort == one optimizer step on the packed bags (same initial weights)
+        cfg = dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4)
+        t, e = synth.make_labels(len(order), P, 5)
+        ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(order))]
+        net_a, net_b = build_net(pr, P, P, dev), build_net(pr, P, P, dev)
+        for n_ in (net_a, net_b):
+            n_.pretrained_text_features.requires_grad_(False)
+        ha, hb = VLSAHandler(cfg, net_a, device=dev), VLSAHandler(cfg, net_b, device=dev)
+        la, pa = ha.update_network_cached(cohort, order, ys)
+        lb, pb = hb._update_network([bags[i].unsqueeze(0).to(dev) for i in order], ys)
+        assert la == lb and torch.equal(pa, pb)
+        for (k, va), (_, vb) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+            assert torch.equal(va, vb), k
+    with pytest.raises(KeyError):
+        cohort.plan([99])
+    with pytest.raises(MemoryError):
+        cohort.reserve("x", 10 ** 9)

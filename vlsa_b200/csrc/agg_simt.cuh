@@ -13,7 +13,8 @@ namespace vlsa {
 
 struct AggParams {
     const void* X;              // [total_rows, D] fp32 or bf16
-    const long long* cu_rows;   // [B+1] row offsets of bags (device)
+    const long long* cu_rows;   // [B+1] row offsets of bags (device) | row_ranges: [2B] (first row, one past the last row) per bag
+    int row_ranges;             // 1: the bags lie anywhere inside X, in any order (a step drawn from a device-resident cohort)
     const int* chunk_start;     // [B+1] first chunk id of each bag (device)
     int B;
     int chunk_rows;             // rows per chunk (multiple of TN)
@@ -73,7 +74,7 @@ __device__ __forceinline__ void chunk_info(const AggParams& p, int c, int& bag, 
         if (__ldg(p.chunk_start + mid) <= c) lo = mid; else hi = mid;
     }
     bag = lo;
-    const long long b0 = __ldg(p.cu_rows + lo), b1 = __ldg(p.cu_rows + lo + 1);
+    const long long b0 = __ldg(p.cu_rows + (p.row_ranges ? 2 * lo : lo)), b1 = __ldg(p.cu_rows + (p.row_ranges ? 2 * lo + 1 : lo + 1));
     r0 = b0 + (long long)(c - __ldg(p.chunk_start + lo)) * p.chunk_rows;
     r1 = r0 + p.chunk_rows < b1 ? r0 + p.chunk_rows : b1;
 }

@@ -210,7 +210,7 @@ static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
 static bool dtype_ok(int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
-           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC)) == 0;
+           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_ROWS_RANGES)) == 0;
 }
 
 // prototypes per launch of the per-prototype-gradient backward (measured best, profiles/variant_time_r01.json)
@@ -303,6 +303,7 @@ int vlsa_agg_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
 
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.row_ranges = (x_dtype & VLSA_ROWS_RANGES) ? 1 : 0;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.q_prenorm = q_prenorm;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
@@ -343,6 +344,7 @@ int vlsa_agg_partial_fwd(const void* X, int x_dtype, int64_t total_rows, const i
     if ((base - reinterpret_cast<uintptr_t>(workspace)) + ws.bytes > workspace_bytes) return VLSA_EWORKSPACE;
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.row_ranges = (x_dtype & VLSA_ROWS_RANGES) ? 1 : 0;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -386,6 +388,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
 
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.row_ranges = (x_dtype & VLSA_ROWS_RANGES) ? 1 : 0;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.scale = coattn_scale;
     prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta; prm.q_prenorm = q_prenorm;
@@ -430,6 +433,7 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, int64_t total_rows, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.row_ranges = (x_dtype & VLSA_ROWS_RANGES) ? 1 : 0;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
     prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     int rc = launch_agg_fwd(prm, P, x_dtype, total_rows, st);
@@ -468,6 +472,7 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, int64_t total_rows, const in
     VLSA_CUDA(cudaGetLastError());
     AggParams prm{};
     prm.X = X; prm.cu_rows = reinterpret_cast<const long long*>(cu_rows); prm.chunk_start = chunk_start;
+    prm.row_ranges = (x_dtype & VLSA_ROWS_RANGES) ? 1 : 0;
     prm.B = B; prm.chunk_rows = chunk_rows; prm.total_chunks = total_chunks; prm.Q = Q; prm.q_prenorm = q_prenorm;
     prm.scale = coattn_scale; prm.part_m = ws.part_m; prm.part_l = ws.part_l; prm.part_O = ws.part_O;
     prm.p_stride = P;

@@ -1,0 +1,70 @@
+"""Device-resident cohort: every patient bag of a split uploaded to HBM ONCE, steps drawn from it without a copy.
+
+The reference re-reads and re-uploads every bag every epoch (dataset/PatchWSI.py:197-215: ``torch.load`` + ``cat`` +
+``.float()``; runner/vlsa_handler.py:205: a synchronous pageable ``.cuda()``), so its training loop is bound by disk and
+PCIe from the first epoch to the last.  A TCGA cohort is small next to a B200: 373 BLCA patients x 3-20k rows x 2 KB is
+2-8 GB of the 180 GB of HBM.  ``DeviceCohort`` keeps the rows of all bags back to back in one device buffer and hands
+out *row-range plans* (``ops.make_plan_ranges`` -> ``VLSA_ROWS_RANGES``): the kernels read the bags of a (shuffled)
+optimizer step straight out of the cohort buffer, wherever they lie — no gather, no H2D beyond the 16 bytes per bag of
+the range table.  Epoch 1 fills the cohort through the asynchronous loader (``AsyncBagLoader(cohort=...)`` copies each
+step's pinned rows directly into their final place); from epoch 2 on a step costs what the kernels cost.
+"""
+from __future__ import annotations
+
+from typing import Hashable, Iterable, Sequence
+
+import torch
+
+from .. import ops
+
+
+class DeviceCohort:
+    def __init__(self, device, capacity_rows: int, dtype: torch.dtype = torch.float32):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.X = torch.empty(max(int(capacity_rows), 1), ops.D_FEAT, dtype=dtype, device=self.device)
+        self.rows = 0                                    # rows handed out so far
+        self.index: dict[Hashable, tuple[int, int]] = {}   # key -> (first row, one past the last row)
+
+    # ---- filling ------------------------------------------------------------------------------------
+    def reserve(self, key: Hashable, n_rows: int) -> torch.Tensor:
+        """Claim the next ``n_rows`` rows for bag ``key`` and return the view to copy its rows into."""
+        if key in self.index:
+            raise KeyError(f"bag {key!r} is already in the cohort")
+        if self.rows + n_rows > self.X.shape[0]:
+            raise MemoryError(f"cohort capacity exceeded: {self.rows} + {n_rows} > {self.X.shape[0]} rows")
+        self.index[key] = (self.rows, self.rows + n_rows)
+        self.rows += n_rows
+        return self.X[self.index[key][0]:self.index[key][1]]
+
+    def reserve_step(self, keys: Sequence[Hashable], sizes: Sequence[int]) -> torch.Tensor:
+        """Claim one contiguous span for the bags of a packed step (in order); returns the [sum sizes, 512] view."""
+        start = self.rows
+        for k, n in zip(keys, sizes):
+            self.reserve(k, int(n))
+        return self.X[start:self.rows]
+
+    def add(self, key: Hashable, bag: torch.Tensor) -> None:
+        """Upload one bag ([N, 512] or [1, N, 512], host or device) into the cohort (current stream)."""
+        b = bag[0] if bag.dim() == 3 else bag
+        self.reserve(key, b.shape[0]).copy_(b.to(self.dtype), non_blocking=True)
+
+    # ---- drawing steps ------------------------------------------------------------------------------
+    def __contains__(self, key: Hashable) -> bool:
+        return key in self.index
+
+    def __len__(self) -> int:
+        return len(self.index)
+
+    def sizes(self, keys: Iterable[Hashable]) -> list[int]:
+        return [self.index[k][1] - self.index[k][0] for k in keys]
+
+    def plan(self, keys: Sequence[Hashable]) -> "ops.BagPlan":
+        """Row-range plan of the step made of the bags ``keys`` (any order, repeats allowed).  Use it with ``self.X``:
+        ``net.forward_packed(cohort.X, cohort.plan(keys))``."""
+        spans = [self.index[k] for k in keys]
+        return ops.make_plan_ranges([s[0] for s in spans], [s[1] for s in spans], self.X.shape[0], self.device)
+
+    @property
+    def nbytes(self) -> int:
+        return self.rows * ops.D_FEAT * self.X.element_size()

@@ -59,11 +59,19 @@ class AsyncBagLoader:
     """
 
     def __init__(self, source: Iterable, device, depth: int = 2, max_rows: int | None = None,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, cohort=None):
+        """``cohort``: a ``DeviceCohort``.  Every step is then copied straight into its final place in the cohort buffer
+        (no ring slot is used, nothing to release) and registered under its ``index`` entries (dataset indices, required);
+        the batch's plan is the cohort's row-range plan, so epoch 1 already runs on the resident rows."""
         self.source = source
+        self.cohort = cohort
         self.device = torch.device(device)
         self.depth = max(2, int(depth))
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        if cohort is not None:
+            # the cohort buffer comes from the current stream's allocator pool: whatever used that memory before is
+            # ordered on the current stream, the first writer of the rows is the copy stream
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         self.dtype = dtype
         self._dev = [None] * self.depth          # device ring slots
         self._pin = [None] * self.depth          # pinned staging per slot
@@ -126,21 +134,30 @@ class AsyncBagLoader:
                 self._copied[slot].synchronize()                     # the previous H2D copy still reads this staging buffer
             host, sizes = pack_bags(bags, self._pin[slot])
             self._pin[slot] = host
-        if self._busy[slot]:
+        if self.cohort is None and self._busy[slot]:
             raise RuntimeError("AsyncBagLoader: ring slot reused while its batch is still held by the consumer "
                                "(raise depth= or release() the batch)")
         rows = sum(sizes)
-        dst = self._slot_buffers(slot, rows)
+        if self.cohort is not None:
+            if index is None:
+                raise ValueError("AsyncBagLoader(cohort=...) needs the dataset indices of every step as cohort keys")
+            keys = [int(i) for i in (index.tolist() if isinstance(index, torch.Tensor) else index)]
+            dst = self.cohort.reserve_step(keys, sizes)
+            # the cohort buffer was allocated on the consumer's stream; nothing there touches the freshly reserved rows
+        else:
+            dst = self._slot_buffers(slot, rows)
         with torch.cuda.stream(self.copy_stream):
-            if self._free[slot] is not None:
+            if self.cohort is None and self._free[slot] is not None:
                 self.copy_stream.wait_event(self._free[slot])        # consumer done with this slot
             if rows:
                 dst[:rows].copy_(host[:rows], non_blocking=True)
                 self._copied[slot] = torch.cuda.Event()
                 self._copied[slot].record(self.copy_stream)
-            plan = ops.make_plan(sizes, self.device)
+            plan = self.cohort.plan(keys) if self.cohort is not None else ops.make_plan(sizes, self.device)
             lab = labels.to(self.device, non_blocking=True) if labels is not None else None
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
         self.h2d_bytes += rows * ops.D_FEAT * host.element_size()
+        if self.cohort is not None:
+            return PackedBatch(self.cohort.X, plan, lab, index, ready, slot)
         return PackedBatch(dst[:rows], plan, lab, index, ready, slot)

@@ -75,8 +75,10 @@ class BagPlan:
     cu_rows_host: np.ndarray        # int64 [B+1]
     chunk_start_host: np.ndarray    # int32 [B+1]
     chunk_rows: int
-    cu_rows: torch.Tensor           # device int64 [B+1]
+    cu_rows: torch.Tensor           # device int64 [B+1]  (ranges: [2B] = (first row, one past the last) per bag)
     chunk_start: torch.Tensor       # device int32 [B+1]
+    ranges: bool = False            # the bags lie anywhere inside a larger X (a step drawn from a DeviceCohort)
+    x_rows: int = -1                # ranges: rows of the buffer the ranges index into
 
     @property
     def num_bags(self) -> int:
@@ -84,7 +86,8 @@ class BagPlan:
 
     @property
     def total_rows(self) -> int:
-        return int(self.cu_rows_host[-1])
+        """Rows of the X this plan goes with (packed: the sum of the bag sizes; ranges: the whole cohort buffer)."""
+        return self.x_rows if self.ranges else int(self.cu_rows_host[-1])
 
     @property
     def total_chunks(self) -> int:
@@ -158,9 +161,31 @@ def _x_dtype_code(x: torch.Tensor) -> int:
     raise ValueError(f"X must be float32 or bfloat16, got {x.dtype}")
 
 
-def _agg_dtype_code(x: torch.Tensor) -> int:
-    """x_dtype of the vlsa_agg_* calls: storage type + the kernel the cross-check hook asks for (if any)."""
-    return _x_dtype_code(x) | _agg_variant_flag
+def _agg_dtype_code(x: torch.Tensor, plan: "BagPlan | None" = None) -> int:
+    """x_dtype of the vlsa_agg_* calls: storage type + the kernel the cross-check hook asks for (if any) + the
+    row-ranges bit of a cohort plan."""
+    return _x_dtype_code(x) | _agg_variant_flag | (0x1000 if plan is not None and plan.ranges else 0)
+
+
+def make_plan_ranges(begins, ends, x_rows: int, device, sms: int | None = None) -> BagPlan:
+    """Plan for bags that lie anywhere inside a larger buffer X [x_rows, 512] (VLSA_ROWS_RANGES): bag b is rows
+    begins[b] .. ends[b] - 1.  One small H2D copy (the 2 B ranges + the chunk table); no gather of the rows."""
+    begins = np.asarray(list(begins), dtype=np.int64)
+    ends = np.asarray(list(ends), dtype=np.int64)
+    if begins.shape != ends.shape or (ends < begins).any() or (begins < 0).any() or (len(ends) and ends.max() > x_rows):
+        raise ValueError("bad row ranges")
+    base = _build_plan(tuple(int(n) for n in ends - begins), torch.device("cpu"), sm_count(device) if sms is None else sms)
+    B = len(begins)
+    stage = torch.empty(2 * B + (B + 2) // 2 + 1, dtype=torch.int64)
+    if torch.device(device).type == "cuda" and B > 4:
+        stage = stage.pin_memory()
+    st = stage.numpy()
+    st[0:2 * B:2] = begins
+    st[1:2 * B:2] = ends
+    st[2 * B:].view(np.int32)[: B + 1] = base.chunk_start_host
+    dev = stage.to(device, non_blocking=True)
+    return BagPlan(base.cu_rows_host, base.chunk_start_host, base.chunk_rows, dev[: 2 * B], dev[2 * B:].view(torch.int32)[: B + 1],
+                   ranges=True, x_rows=int(x_rows))
 
 
 def _workspace(plan: BagPlan, P: int, device) -> torch.Tensor:
@@ -195,7 +220,7 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
         "Tn": torch.empty(R, D_FEAT, **f32),
     }
     ws = workspace if workspace is not None else _workspace(plan, P, dev)
-    rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+    rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                         plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, int(bool(q_prenorm)),
                         coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(),
                         T.data_ptr(), R, logit_scale.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -208,7 +233,7 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
 
 def aggregate_partial_only(X, plan: BagPlan, Q, workspace: torch.Tensor, scale: float | None = None) -> None:
     """Launch only the streaming kernel (vlsa_agg_partial_fwd); used to time the dominant kernel alone."""
-    rc = _lib.lib().vlsa_agg_partial_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
+    rc = _lib.lib().vlsa_agg_partial_fwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(),
                                          plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
                                          plan.total_chunks, Q.data_ptr(), Q.shape[0],
                                          coattn_scale() if scale is None else float(scale), workspace.data_ptr(),
@@ -247,7 +272,7 @@ class _AggregateFn(torch.autograd.Function):
         d_g = None if d_g is None else d_g.contiguous().float()
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
         dT, dls = torch.empty(R, D_FEAT, **f32), torch.empty((), **f32)
-        rc = L.vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+        rc = L.vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                             plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, ctx.prenorm,
                             coattn_scale() if ctx.scale is None else float(ctx.scale), W.data_ptr(), T.data_ptr(), R,
                             ls.data_ptr(), v.data_ptr(), f.data_ptr(), g.data_ptr(), logits.data_ptr(), ml.data_ptr(),
@@ -278,7 +303,7 @@ class _EncodeFn(torch.autograd.Function):
         ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
         ws = _workspace(plan, P, X.device)
         sc = coattn_scale() if scale is None else float(scale)
-        rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
+        rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(), B,
                             plan.chunk_rows, plan.total_chunks, Qc.data_ptr(), P, int(bool(q_prenorm)), sc, Wc.data_ptr(),
                             bc.data_ptr(), None, 0, None, ws.data_ptr(), ws.numel(), v.data_ptr(), f.data_ptr(), None,
                             None, None, ml.data_ptr(), O.data_ptr(), None, _stream())
@@ -301,7 +326,7 @@ class _EncodeFn(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=X.device)
         d_f = d_f.contiguous().float()
         dQ, dW, db = torch.empty(P, D_FEAT, **f32), torch.empty(D_FEAT, D_FEAT, **f32), torch.empty(D_FEAT, **f32)
-        rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_bwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(),
                                      plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows, plan.total_chunks,
                                      Q.data_ptr(), P, ctx.prenorm, ctx.scale, W.data_ptr(), None, 0, None, v.data_ptr(),
                                      None, None, None, ml.data_ptr(), O.data_ptr(), None, None, d_f.data_ptr(),
@@ -337,7 +362,7 @@ class _PooledFn(torch.autograd.Function):
         ml, O = torch.empty(B, P, 2, **f32), torch.empty(B, P, D_FEAT, **f32)
         ws = _workspace(plan, P, X.device)
         sc = coattn_scale() if scale is None else float(scale)
-        rc = _lib.lib().vlsa_agg_pooled_fwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_pooled_fwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(),
                                             plan.chunk_start.data_ptr(), B, plan.chunk_rows, plan.total_chunks,
                                             Qc.data_ptr(), P, int(bool(q_prenorm)), sc, ws.data_ptr(), ws.numel(),
                                             ml.data_ptr(), O.data_ptr(), _stream())
@@ -359,7 +384,7 @@ class _PooledFn(torch.autograd.Function):
         P = Q.shape[0]
         d_O = d_O.contiguous().float()
         dQ = torch.empty(P, D_FEAT, dtype=torch.float32, device=X.device)
-        rc = _lib.lib().vlsa_agg_pooled_bwd(X.data_ptr(), _agg_dtype_code(X), plan.total_rows, plan.cu_rows.data_ptr(),
+        rc = _lib.lib().vlsa_agg_pooled_bwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(),
                                             plan.chunk_start.data_ptr(), plan.num_bags, plan.chunk_rows,
                                             plan.total_chunks, Q.data_ptr(), P, ctx.prenorm, ctx.scale, ml.data_ptr(),
                                             O.data_ptr(), d_O.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
@@ -371,6 +396,8 @@ class _PooledFn(torch.autograd.Function):
 
 def _pooled_dx(X, plan: BagPlan, Q, prenorm: int, scale: float, ml, O, d_O):
     """vlsa_agg_pooled_bwd_dx: gradient of the pooled aggregation w.r.t. the (fp32) patch rows."""
+    if plan.ranges:
+        raise NotImplementedError("a gradient w.r.t. the patch rows needs a packed batch (not a cohort row-range plan)")
     dX = torch.empty_like(X)
     sizes = np.diff(plan.cu_rows_host)
     rc = _lib.lib().vlsa_agg_pooled_bwd_dx(X.data_ptr(), plan.cu_rows.data_ptr(), plan.num_bags,

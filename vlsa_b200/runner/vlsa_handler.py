@@ -144,11 +144,29 @@ class VLSAHandler:
         if sizes is None:
             sizes = [int(x.shape[-2]) for x in xs]
         mine = vdist.shard_indices(sizes, self.rank, self.world_size, self.balance_shards)
-        self.bucket.zero()
         bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
+        X = plan = None
         if mine:
             local = {i: (xs[i]() if callable(xs[i]) else xs[i]) for i in mine}
             X, plan = self._pack_local(local, mine)
+        return self._step(X, plan, bag_label, mine, n_sample)
+
+    def update_network_cached(self, cohort, keys: Sequence, ys):
+        """`_update_network` on bags that are already resident in a `DeviceCohort` (keys = their cohort keys, e.g. the
+        dataset indices): no staging, no H2D of rows — the step's plan points into the cohort buffer.  With several
+        ranks the cohort is partitioned STATICALLY (every bag lives in exactly one rank's cohort, e.g. key % world ==
+        rank, LPT-balanced over the whole split): a rank processes the bags of the step it holds."""
+        n_sample = len(keys)
+        mine = [i for i, k in enumerate(keys) if k in cohort]
+        if self.world_size == 1 and len(mine) != n_sample:
+            raise KeyError("update_network_cached: a bag of the step is not in the cohort")
+        bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
+        plan = cohort.plan([keys[i] for i in mine]) if mine else None
+        return self._step(cohort.X if mine else None, plan, bag_label, mine, n_sample)
+
+    def _step(self, X, plan, bag_label, mine, n_sample):
+        self.bucket.zero()
+        if mine:
             logits, _, _, _ = self.net.forward_packed(X, plan)                       # [B_local, R]
             sel = torch.as_tensor(mine, device=self.device)
             pred_loss = self.calc_objective_loss(logits, bag_label[sel], norm=n_sample)   # sum_local / n_sample
