@@ -1,0 +1,19 @@
+"""Dev helper (GPU box): a few launches of the aggregation kernel alone (for ncu).  argv: variant [P] [bwd]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from vlsa_b200 import ops, synth
+dev = torch.device("cuda:0")
+variant = sys.argv[1] if len(sys.argv) > 1 else "tc"
+P = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+N, B = 50000, 32
+pr = synth.make_params(P, P, 1)
+X = torch.randn(N * B, 512, device=dev) * 1.1 + 0.7
+Q = (0.5 * pr["residual_features"] + pr["prompt_features"]).to(dev)
+plan = ops.make_plan([N] * B, dev)
+ws = ops._workspace(plan, P, dev)
+ops.set_agg_variant(variant)
+for _ in range(4):
+    ops.aggregate_partial_only(X, plan, Q, ws)
+torch.cuda.synchronize()

@@ -11,7 +11,7 @@ X = torch.randn(N * B, 512, device=dev) * 1.1 + 0.7
 Q = (0.5 * pr["residual_features"] + pr["prompt_features"]).to(dev)
 plan = ops.make_plan([N] * B, dev)
 ws = ops._workspace(plan, P, dev)
-ops.set_agg_variant("tc")
+ops.set_agg_variant(sys.argv[1] if len(sys.argv) > 1 else "tc")
 for _ in range(3):
     ops.aggregate_partial_only(X, plan, Q, ws)
 torch.cuda.synchronize()
@@ -24,10 +24,10 @@ L.vlsa_debug_read_prof.restype = C.c_int
 assert L.vlsa_debug_read_prof(buf) == 0
 v = list(buf)
 tiles = max(v[19], 1)
-names = {0: "conv: wait landed", 1: "conv: group barrier", 2: "conv: proxy fence", 3: "conv: TOTAL",
+names = {0: "conv: wait landed | prod: wait empty", 1: "conv: group barrier | prod: loads + norm", 2: "conv: proxy fence | prod: split + STS", 3: "conv | prod: TOTAL",
          4: "tma: wait empty", 5: "tma: TOTAL", 6: "gemm1: wait s_free", 7: "gemm1: wait full", 8: "gemm1: TOTAL",
          9: "gemm2: wait w_ready", 10: "gemm2: wait d2_free", 11: "gemm2: TOTAL", 12: "wt: wait s_ready", 13: "wt: wait full",
          14: "wt: wait decided", 15: "wt: bar.red", 16: "wt: wait w_free", 17: "wt: wait d2_done", 18: "wt: TOTAL (set 0: every other tile)"}
 print(f"tiles per CTA: {tiles}")
 for k in range(19):
-    print(f"  {names[k]:22s} {v[k]/tiles:9.1f} cycles / tile")
+    print(f"  {names[k]:40s} {v[k]/tiles:9.1f} cycles / tile")

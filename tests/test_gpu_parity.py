@@ -299,7 +299,7 @@ def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dev):
     plan = ops.make_plan(sizes, dev)
     res = {}
     try:
-        for variant in ("simt", "tc"):
+        for variant in ("simt", "tc", "tc_tma"):
             ops.set_agg_variant(variant)
             leaf = lambda z: z.detach().clone().to(dev).requires_grad_(True)
             r, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))

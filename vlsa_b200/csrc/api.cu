@@ -10,6 +10,7 @@
 
 #include "agg_simt.cuh"
 #include "agg_tma.cuh"
+#include "agg_tc.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
@@ -196,21 +197,37 @@ static int launch_agg_tma(const AggParams& prm, int P, long long total_rows, cud
     return static_cast<int>(cudaGetLastError());
 }
 
+// register-staged tcgen05 kernel (agg_tc.cuh): rows through LDG, three shared-memory passes per byte
+template <bool BWD>
+static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
+    using C = TcCfg;
+    if (reinterpret_cast<uintptr_t>(prm.X) & 15u) return VLSA_EINVAL;
+    auto kern = agg_tc_kernel<BWD>;
+    static std::atomic<int> cache[kMaxDevices];
+    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
+    const int sms = device_sm_count();
+    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    if (grid <= 0) return 0;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P);
+    return static_cast<int>(cudaGetLastError());
+}
+
 // Which streaming kernel serves a pass.  Default: the TMA-fed tcgen05 kernel for fp32 rows and P > 5 (the CUDA-core
 // kernel is at the HBM roofline for P <= 5); bf16 rows run on CUDA cores.  The caller can force a
 // kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
-enum AggKernel { kAggSimt = 0, kAggTma = 1 };
+enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTc = 2 };
 static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     if (dtype != VLSA_DTYPE_F32) return kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
-    if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTma;
-    return P > 5 ? kAggTma : kAggSimt;
+    if (x_dtype_flags & VLSA_KERNEL_TC_TMA) return kAggTma;
+    if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTc;
+    return P > 5 ? kAggTc : kAggSimt;
 }
 static bool dtype_ok(int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
-           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_ROWS_RANGES)) == 0;
+           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_KERNEL_TC_TMA | VLSA_ROWS_RANGES)) == 0;
 }
 
 // prototypes per launch of the per-prototype-gradient backward (measured best, profiles/variant_time_r01.json)
@@ -219,6 +236,7 @@ static constexpr int kGenGroup = 8;
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long total_rows, cudaStream_t st) {
     const AggKernel k = agg_kernel_choice(P, x_dtype);
     if (k == kAggTma) return launch_agg_tma<false>(prm, P, total_rows, st);
+    if (k == kAggTc) return launch_agg_tc<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
@@ -396,6 +414,9 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
     const AggKernel kern = total_chunks > 0 ? agg_kernel_choice(P, x_dtype) : kAggSimt;
     if (kern == kAggTma) {
         rc = launch_agg_tma<true>(prm, P, total_rows, st);
+        if (rc) return rc;
+    } else if (kern == kAggTc) {
+        rc = launch_agg_tc<true>(prm, P, st);
         if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {

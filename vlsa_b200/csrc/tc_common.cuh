@@ -145,7 +145,9 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_hint(bar, parity, 4000u)) return;
     uint32_t spins = 0;
     do {
-        if (++spins > (1u << 22)) { printf("vlsa: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        // brkpt, not trap / printf: an exit edge or a call inside the kernel makes ptxas ignore setmaxnreg when it allocates
+        // registers (every role is then held to the launch bound and the producers of agg_tc_kernel spill)
+        if (++spins > (1u << 22)) { asm volatile("brkpt;"); spins = 0; }
     } while (!mbar_try_wait_hint(bar, parity, 4000u));
 }
 
