@@ -317,7 +317,8 @@ def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, es
     wss = [ops._workspace(p, P, dev) for p in plans]
     ms_k = timer(lambda i: ops.aggregate_partial_only(batches[i % len(batches)], plans[i % len(plans)], Q, wss[i % len(plans)]), steps)
     rec = {"P": P, "R": R, "value": nb * world / (ms_fwd * 1e-3), "unit": "WSI/s", "ms_per_step": ms_fwd,
-           "kernel": "agg_tc_kernel<false> (tcgen05, register-staged rows)" if (P > 5 and esize == 4) else "agg_simt_kernel<P,0,XT>",
+           "kernel": ("agg_bf16_kernel<false> (tcgen05, TMA-fed bf16 rows)" if esize == 2 else
+                      "agg_tc_kernel<false> (tcgen05, register-staged rows)" if P > 5 else "agg_simt_kernel<P,0,float>"),
            "kernel_ms": ms_k, "achieved_gbs": algo_bytes / (ms_k * 1e-3) / 1e9, "frac": algo_bytes / (ms_k * 1e-3) / 1e9 / peak,
            "frac_whole_forward": algo_bytes / (ms_fwd * 1e-3) / 1e9 / peak}
     if train:

@@ -41,7 +41,8 @@ extern "C" {
 #define VLSA_DTYPE_BF16 1
 #define VLSA_DTYPE_MASK 0xff
 /* Optional bits OR-ed into x_dtype of the vlsa_agg_* calls: force the streaming kernel of an fp32 pass for THIS call
- * (cross-checks in the parity tests; default = automatic: TMA-fed tcgen05 kernel for P > 5, CUDA-core kernel otherwise).
+ * (cross-checks in the parity tests; default = automatic: fp32 rows — register-staged tcgen05 kernel for P > 5, CUDA-core
+ * kernel otherwise; bf16 rows — TMA-fed tcgen05 kernel agg_bf16_kernel, VLSA_KERNEL_SIMT selects the CUDA-core kernel).
  * All kernels compute the same function (model/deepmil.py:187-203). */
 #define VLSA_KERNEL_SIMT 0x100   /* CUDA-core kernel (agg_simt_kernel) */
 #define VLSA_KERNEL_TC 0x200     /* register-staged tcgen05 kernel (agg_tc_kernel) */

@@ -10,6 +10,8 @@ P = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 N, B = 50000, 32
 pr = synth.make_params(P, P, 1)
 X = torch.randn(N * B, 512, device=dev) * 1.1 + 0.7
+if os.environ.get('DEV_DTYPE') == 'bf16':
+    X = X.to(torch.bfloat16)
 Q = (0.5 * pr["residual_features"] + pr["prompt_features"]).to(dev)
 plan = ops.make_plan([N] * B, dev)
 ws = ops._workspace(plan, P, dev)

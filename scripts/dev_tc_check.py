@@ -11,9 +11,12 @@ dev = torch.device("cuda:0")
 mode = sys.argv[1] if len(sys.argv) > 1 else "full"
 variants = sys.argv[2:] or ["tc", "tc_tma"]
 FEWP = bool(os.environ.get("VLSA_DEV_FEWP"))
+DT = torch.bfloat16 if os.environ.get("DEV_DTYPE") == "bf16" else torch.float32
+PS = [int(v) for v in os.environ.get("DEV_PS", "").split(",") if v]
 
 
-def run(variant, bags, pr, dtype=torch.float32):
+def run(variant, bags, pr, dtype=None):
+    dtype = dtype or DT
     ops.set_agg_variant(variant)
     X = torch.cat(bags, 0).to(dev).to(dtype)
     plan = ops.make_plan([b.shape[0] for b in bags], dev)
@@ -72,9 +75,9 @@ def timeit(fn, iters=20, warm=3):
 
 
 N, B = 50000, 32
-for P in ([12] if (mode == "quick" or FEWP) else [12, 8, 16]):
+for P in (PS or ([12] if (mode == "quick" or FEWP) else [12, 8, 16])):
     pr = synth.make_params(P, P, 1)
-    Xs = [torch.randn(N * B, 512, device=dev) * 1.1 + 0.7 for _ in range(2)]
+    Xs = [(torch.randn(N * B, 512, device=dev) * 1.1 + 0.7).to(DT) for _ in range(2)]
     leaf = lambda z: z.detach().clone().to(dev).requires_grad_(True)
     res, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))
     pf = pr["prompt_features"].to(dev)
@@ -82,7 +85,7 @@ for P in ([12] if (mode == "quick" or FEWP) else [12, 8, 16]):
     plan = ops.make_plan([N] * B, dev)
     ws = ops._workspace(plan, P, dev)
     Qd = (0.5 * res + pf).detach()
-    gb = N * B * 512 * 4 / 1e9
+    gb = N * B * 512 * Xs[0].element_size() / 1e9
     for variant in variants + ["simt"]:
         ops.set_agg_variant(variant)
         ms_k = timeit(lambda i: ops.aggregate_partial_only(Xs[i % 2], plan, Qd, ws))

@@ -284,22 +284,28 @@ def test_argument_errors(dev):
         ops.logit_pool(X, args[3], args[4], "logit_median")
 
 
-@pytest.mark.parametrize("P,sizes,kind", [(4, [10000], "g1"), (12, [2798, 1000, 37], "g1"), (16, [5000, 33], "g0"),
-                                          (1, [700], "g0"), (7, [50000], "g1")])
-def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dev):
-    """Both streaming kernels (tcgen05 and CUDA-core) are complete implementations of the same pass; every case
-    runs forward + loss + backward through each and the results must agree to the parity tolerances, and each
-    must match the fp64 oracle."""
+@pytest.mark.parametrize("P,sizes,kind,dtype", [(4, [10000], "g1", "fp32"), (12, [2798, 1000, 37], "g1", "fp32"),
+                                                (16, [5000, 33], "g0", "fp32"), (1, [700], "g0", "fp32"), (7, [50000], "g1", "fp32"),
+                                                (4, [10000, 33], "g1", "bf16"), (12, [2798, 1000, 37, 1, 17], "g1", "bf16"),
+                                                (16, [5000, 33], "g0", "bf16"), (8, [50000], "g1", "bf16")])
+def test_tensor_core_and_cuda_core_kernels_agree(P, sizes, kind, dtype, dev):
+    """The streaming kernels (tcgen05: register-staged and TMA-fed for fp32 rows, TMA-fed for bf16 rows; CUDA-core) are
+    complete implementations of the same pass; every case runs forward + loss + backward through each and the results
+    must agree to the parity tolerances, and each must match the fp64 oracle (bf16: on the same rounded values)."""
     from oracle import vlsa_oracle as O
     from vlsa_b200 import ops, synth
     bags = [synth.make_bag(kind, n, 900 + i + P) for i, n in enumerate(sizes)]
+    if dtype == "bf16":
+        bags = [b.to(torch.bfloat16).float() for b in bags]          # the stored values ARE the inputs
     pr = synth.make_params(P, P, 21 + P)
     t, e = synth.make_labels(len(sizes), P, 5)
     X = torch.cat(bags, 0).to(dev)
+    if dtype == "bf16":
+        X = X.to(torch.bfloat16)
     plan = ops.make_plan(sizes, dev)
     res = {}
     try:
-        for variant in ("simt", "tc", "tc_tma"):
+        for variant in (("simt", "tc", "tc_tma") if dtype == "fp32" else ("simt", "tc")):
             ops.set_agg_variant(variant)
             leaf = lambda z: z.detach().clone().to(dev).requires_grad_(True)
             r, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))

@@ -42,6 +42,9 @@ namespace vlsa {
 #ifndef VLSA_TC_R
 #define VLSA_TC_R 2
 #endif
+#ifndef VLSA_TC_PF
+#define VLSA_TC_PF 0             // L2 prefetch distance in tiles ahead of the producers' loads (0 = off), warp 10
+#endif
 
 struct TcCfg {
     static constexpr int D = VLSA_D;
@@ -106,11 +109,13 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     uint64_t* d2_free = s_ready + 9;             //        weight warps (8)          -> GEMM2 of the next chunk
     uint64_t* decided = s_ready + 10;            // [2]    weight set s (4 warps): softmax reference settled for its tile -> other set
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + C::NBAR);
+    volatile uint32_t* s_prog = tmem_ptr + 1;    // tiles whose loads the producers have issued (L2 prefetcher only)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for ptxas
 
     if (tid == 0) {
         for (int s = 0; s < C::NBUF; ++s) { mbar_init(full + s, C::NPROD); mbar_init(empty + s, 1); }
+        *s_prog = 0u;
         for (int s = 0; s < 2; ++s) {
             mbar_init(s_ready + s, 1); mbar_init(s_free + s, C::NSOFT / 2);
             mbar_init(w_ready + s, C::NSOFT / 2); mbar_init(w_free + s, 1);
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         float4 dvr[BWD ? 4 : 1];                           // dv / P at this lane's columns (backward)
         int dv_bag = -1;
         uint32_t b = 0, par = 1;                           // ring position, parity to wait for on empty[b]
+        uint32_t n_issued = 0;
         PROF_DECL
 #define VLSA_TC_ISSUE(S)                                                                                     \
         if (ld.valid) {                                                                                      \
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                 _Pragma("unroll") for (int i = 0; i < 4; ++i) buf[S][j][i] = ldg_stream_f4(src + 128 * i, policy); \
             }                                                                                                \
             cur_next(ld);                                                                                    \
+            if (VLSA_TC_PF > 0 && pw == 0 && lane == 0) *s_prog = ++n_issued;                                \
         }
 #pragma unroll
         for (int s = 0; s < R; ++s) { VLSA_TC_ISSUE(s) }
@@ -319,7 +326,26 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         PROF_FLUSH(0, 3, pw == 0 && lane == 0)
     } else if (warp >= C::NSOFT) {
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_ISSUE));
-      if (warp == C::W_G1) {
+      if (VLSA_TC_PF > 0 && warp == C::W_G1 + 2) {
+        // =========================================================================== L2 prefetcher (development option)
+        // one bulk prefetch per tile, VLSA_TC_PF tiles ahead of the producers' loads: a producer's first use of a register
+        // set waits for EVERY load its warp has in flight (ptxas puts them on one scoreboard), i.e. for a full memory
+        // latency per rotation of its registers; loads that hit L2 shorten that wait
+        if (lane == 0) {
+            const float* Xf = reinterpret_cast<const float*>(prm.X);
+            uint32_t done = 0;
+            for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x) {
+                int bag; long long r0, r1;
+                chunk_info(prm, c, bag, r0, r1);
+                for (long long r = r0; r < r1; r += TR, ++done) {
+                    while (int(done) >= int(*s_prog) + VLSA_TC_PF) __nanosleep(64);
+                    const long long n = r1 - r < TR ? r1 - r : TR;
+                    l2_prefetch_bulk(Xf + r * D, uint32_t(n) * D * 4u);
+                }
+            }
+        }
+        __syncwarp();
+      } else if (warp == C::W_G1) {
         // =========================================================================== GEMM1 issuer
         if (elect_one()) {
             constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, UMMA_F16, 128, 2 * TR, false, false);

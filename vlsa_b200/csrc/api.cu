@@ -11,6 +11,7 @@
 #include "agg_simt.cuh"
 #include "agg_tma.cuh"
 #include "agg_tc.cuh"
+#include "agg_bf16.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
@@ -54,6 +55,9 @@ using namespace vlsa;
     }
 #endif
 
+#ifndef VLSA_BF16_TC_MIN_P
+#define VLSA_BF16_TC_MIN_P 1     // bf16 rows: tensor-core kernel from this P on (measured: 315 vs 472 us at P = 4, 332 vs 1226 us at P = 12)
+#endif
 static constexpr int kRowTile = 32;   // a multiple of TmaCfg::TR and of the CUDA-core kernel's AggCfg::TN
 static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile % TmaCfg::TR == 0, "chunk_rows must suit both streaming kernels");
 
@@ -197,6 +201,34 @@ static int launch_agg_tma(const AggParams& prm, int P, long long total_rows, cud
     return static_cast<int>(cudaGetLastError());
 }
 
+// bf16-stored rows on the tensor cores (agg_bf16.cuh): X [total_rows, 512] bf16 as a 2-D tensor, box = 16 rows x 64 columns
+// landing as two 128-byte-swizzled K-major atoms
+template <bool BWD>
+static int launch_agg_bf16(const AggParams& prm, int P, long long total_rows, cudaStream_t st) {
+    using C = Bf16Cfg;
+    if (total_rows <= 0 || total_rows > 0x7fffffffLL) return VLSA_EINVAL;
+    if (reinterpret_cast<uintptr_t>(prm.X) & 15u) return VLSA_EINVAL;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return VLSA_EUNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {cuuint64_t(VLSA_D), cuuint64_t(total_rows)};
+    const cuuint64_t gstr[1] = {cuuint64_t(VLSA_D) * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {64u, cuuint32_t(C::TR)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(prm.X), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return VLSA_EINVAL;
+    auto kern = agg_bf16_kernel<BWD>;
+    static std::atomic<int> cache[kMaxDevices];
+    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
+    const int sms = device_sm_count();
+    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    if (grid <= 0) return 0;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P, tmap);
+    return static_cast<int>(cudaGetLastError());
+}
+
 // register-staged tcgen05 kernel (agg_tc.cuh): rows through LDG, three shared-memory passes per byte
 template <bool BWD>
 static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
@@ -212,14 +244,14 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
     return static_cast<int>(cudaGetLastError());
 }
 
-// Which streaming kernel serves a pass.  Default: the TMA-fed tcgen05 kernel for fp32 rows and P > 5 (the CUDA-core
-// kernel is at the HBM roofline for P <= 5); bf16 rows run on CUDA cores.  The caller can force a
+// Which streaming kernel serves a pass.  Default: fp32 rows — the register-staged tcgen05 kernel for P > 5 (the CUDA-core
+// kernel is at the HBM roofline for P <= 5); bf16 rows — the TMA-fed tcgen05 kernel for every P.  The caller can force a
 // kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
-enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTc = 2 };
+enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTc = 2, kAggBf16 = 3 };
 static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
-    if (dtype != VLSA_DTYPE_F32) return kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
+    if (dtype == VLSA_DTYPE_BF16) return ((x_dtype_flags & VLSA_KERNEL_TC) || P > VLSA_BF16_TC_MIN_P - 1) ? kAggBf16 : kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_TC_TMA) return kAggTma;
     if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTc;
     return P > 5 ? kAggTc : kAggSimt;
@@ -237,6 +269,7 @@ static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long to
     const AggKernel k = agg_kernel_choice(P, x_dtype);
     if (k == kAggTma) return launch_agg_tma<false>(prm, P, total_rows, st);
     if (k == kAggTc) return launch_agg_tc<false>(prm, P, st);
+    if (k == kAggBf16) return launch_agg_bf16<false>(prm, P, total_rows, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
@@ -417,6 +450,9 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
         if (rc) return rc;
     } else if (kern == kAggTc) {
         rc = launch_agg_tc<true>(prm, P, st);
+        if (rc) return rc;
+    } else if (kern == kAggBf16) {
+        rc = launch_agg_bf16<true>(prm, P, total_rows, st);
         if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {

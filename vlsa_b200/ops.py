@@ -45,7 +45,14 @@ def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """Handle of torch's current stream on the current device (the C entry costs ~0.3 us; torch.cuda.current_stream()
+    builds a Python Stream object per call: ~20 us, three times per optimizer step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
