@@ -45,8 +45,7 @@ extern "C" {
  * kernel otherwise; bf16 rows — TMA-fed tcgen05 kernel agg_bf16_kernel, VLSA_KERNEL_SIMT selects the CUDA-core kernel).
  * All kernels compute the same function (model/deepmil.py:187-203). */
 #define VLSA_KERNEL_SIMT 0x100   /* CUDA-core kernel (agg_simt_kernel) */
-#define VLSA_KERNEL_TC 0x200     /* register-staged tcgen05 kernel (agg_tc_kernel) */
-#define VLSA_KERNEL_TC_TMA 0x400 /* TMA-fed tcgen05 kernel, fp16 planes converted in place (agg_tma_kernel) */
+#define VLSA_KERNEL_TC 0x200     /* tcgen05 kernel (fp32 rows: agg_tc_kernel, bf16 rows: agg_bf16_kernel) */
 /* Optional bit of x_dtype of the vlsa_agg_* calls: `cu_rows` holds 2 B entries (first row, one past the last row) per bag
  * instead of B + 1 offsets — the bags of the call lie anywhere inside X [total_rows, 512], in any order.  This is how a
  * step is drawn from a device-resident cohort (every patient of a split uploaded once; the reference re-uploads every

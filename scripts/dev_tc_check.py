@@ -1,4 +1,4 @@
-"""Dev helper (GPU box): the tcgen05 kernels (register-staged `tc`, TMA-fed `tc_tma`) against the CUDA-core kernel
+"""Dev helper (GPU box): the tcgen05 kernels (variant `tc`: register-staged for fp32 rows, TMA-fed for bf16 rows) against the CUDA-core kernel
 (parity of forward outputs and gradients on the same inputs), run-to-run bit stability, and kernel / train-step times.
     VLSA_B200_LIB=/path/to/variant.so python scripts/dev_tc_check.py [quick|timeonly] [variants ...]"""
 import os, sys
@@ -9,7 +9,7 @@ from vlsa_b200 import ops, synth
 
 dev = torch.device("cuda:0")
 mode = sys.argv[1] if len(sys.argv) > 1 else "full"
-variants = sys.argv[2:] or ["tc", "tc_tma"]
+variants = sys.argv[2:] or ["tc"]
 FEWP = bool(os.environ.get("VLSA_DEV_FEWP"))
 DT = torch.bfloat16 if os.environ.get("DEV_DTYPE") == "bf16" else torch.float32
 PS = [int(v) for v in os.environ.get("DEV_PS", "").split(",") if v]

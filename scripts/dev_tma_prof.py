@@ -1,4 +1,4 @@
-"""Dev helper (GPU box): per-role wait accounting of agg_tma_kernel (library built with -DVLSA_TMA_PROF)."""
+"""Dev helper (GPU box): per-role wait accounting of the tcgen05 kernels (agg_tc_kernel / agg_bf16_kernel) (library built with -DVLSA_TMA_PROF)."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,4 +1,4 @@
-"""Per-role accounting of an .ncu-rep of agg_tc_kernel / agg_tma_kernel: the SASS is cut at the USETMAXREG instructions
+"""Per-role accounting of an .ncu-rep of agg_tc_kernel / agg_bf16_kernel: the SASS is cut at the USETMAXREG instructions
 (producers | issuers | weights) and samples / stall reasons / executed instructions are summed per region.
     python scripts/ncu_regions.py report.ncu-rep [kernel index] [top lines per region]"""
 import csv, io, subprocess, sys

@@ -16,12 +16,17 @@
 // Tile = 16 rows = 16 KB: slot s (64 features) at s * 2048; row group g (8 rows) at + g * 1024 (128-byte swizzle).  Ring
 // of 8 tiles (128 KB), all of it available as TMA prefetch depth.
 //
-// Warp roles (20 warps, 1 persistent CTA / SM, static round-robin over chunks):
-//   warps 0-7   weights (two alternating sets of four, one warp per TMEM quadrant)      [as agg_tc.cuh]
-//   warp  8     GEMM1 issuer + TMEM allocation      warp 9   GEMM2 issuer      warp 10  TMA issuer      warp 11  idle
-//   warps 12-19 row norms: rows 2 (w - 12), 2 (w - 12) + 1 of every tile
+// Warp roles (28 warps, 1 persistent CTA / SM, static round-robin over chunks).  With 16 KB per tile the HBM time of a
+// tile is ~730 cycles, shorter than the latency chain of any role (mbarrier waits, TMEM / shared-memory round trips), so
+// every stage runs in several alternating sets:
+//   warps 0-15  weights: FOUR sets of four (one warp per TMEM quadrant), tile tt -> set tt % 4 (own score / weight buffer);
+//               the 8 partial sums of a score are added by a transposed shuffle butterfly (no shared memory)
+//   warp  16    GEMM1 issuer + TMEM allocation      warp 17  GEMM2 issuer      warp 18  TMA issuer      warp 19  idle
+//   warps 20-27 row norms: TWO sets of four, tile tt -> set tt & 1; warp: four rows of its tiles
+// Registers (setmaxnreg): weights 80, issuers 24, norm warps 80 of the 72 x 896 the launch bound grants.
 #pragma once
-#include "agg_tma.cuh"
+#include "agg_simt.cuh"
+#include "tc_common.cuh"
 
 namespace vlsa {
 
@@ -42,8 +47,8 @@ struct Bf16Cfg {
     static constexpr int WBUF = 2 * NP * 128;     // weight operand: 32 rows (term, prototype) x 128 B (32 B used)
     static constexpr int OFF_W = NBUF * TILE;
     static constexpr int OFF_F = OFF_W + NSET * WBUF;
-    // floats: rowinfo[NBUF][TR][4] | alpha[16] | mref[16] | lsum[NSET][16] | exE[4] | tr[NSOFT][16][36]
-    static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 16 + NSET * 16 + 4 + NSOFT * 16 * 36;
+    // floats: rowinfo[NBUF][TR][4] | alpha[16] | mref[16] | lsum[NSET][16] | exE[4]
+    static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 16 + NSET * 16 + 4;
     static constexpr int OFF_BAR = OFF_F + NFLOAT * 4;
     static constexpr int NBAR = 3 * NBUF + 5 * NSET + 2;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16 + 1024;
@@ -77,7 +82,6 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
     float* s_mref = s_alpha + 16;                                    // [16] current softmax reference (fwd) | log2 H_p (bwd)
     float* s_lsum = s_mref + 16;                                     // [NSET][16] per-set softmax sums at a chunk end
     int* s_exE = reinterpret_cast<int*>(s_lsum + C::NSET * 16);                // [4] reference row-scale exponent of the chunk (127 here)
-    float* s_tr = s_lsum + C::NSET * 16 + 4;                         // [weight warps][16 rows][36] score transposition
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint64_t* landed = bars;                     // [NBUF] TMA (expect_tx)           -> GEMM1, norm warps
     uint64_t* full = bars + C::NBUF;             // [NBUF] norm warps (8)            -> weight warps (row info)
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     *reinterpret_cast<float4*>(s_rowinfo + (b * TR + row + 2 * h) * 4) = info;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full + b);
+                mbar_arrive_if(full + b, lane == 0);
             }
         }
         PROF_FLUSH(0, 3, cw == 0 && lane == 0)
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         // NSET sets of four warps (one per TMEM quadrant) take the tiles in turn: tile tt belongs to set tt % NSET, which
         // also owns score buffer and weight buffer tt % NSET — NSET tiles are in this stage at any time (the stage is a
         // chain of mbarrier / TMEM / shared-memory round trips: latency, not issue slots, is what a set spends per tile).  A thread owns
-        // (prototype p = 4 q + (lane & 3)) x (tile rows rj, 8 + rj), so a warp sees all 16 rows of its four prototypes and
+        // (prototype p = 4 q + (lane & 3)) x (tile rows 2 rj, 2 rj + 1), so a warp sees all 16 rows of its four prototypes and
         // settles their softmax reference on its own.  What the sets share is the reference itself (s_mref): set s may
         // only decide tile tt after the other set has decided tile tt - 1 (mbarrier `decided`), and every thread folds a
         // reference it finds changed into its running sum before going on.
@@ -360,7 +364,8 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         const bool pvalid = p < P;
         const uint32_t tq = tmem + (uint32_t(32 * q) << 16);
         constexpr int NT = C::NSOFT * 32, NTS = 128;
-        float* tr = s_tr + warp * (16 * 36);
+        // B operand of GEMM2: row (term * 16 + p), K = tile row: rows 2 rj, 2 rj + 1 -> 16-byte chunk rj >> 2, bytes 4 (rj & 3)
+        const uint32_t w_off = sw128_offset(p, rj >> 2, 4 * (rj & 3));
         uint32_t tt = 0, cc = 0;
         PROF_DECL
         for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x, ++cc) {
@@ -400,25 +405,28 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_free + set);
-                    // transpose through shared memory (row pitch 36 floats: conflict-free both ways): the 8 (term, range)
-                    // partial sums of a (row, prototype) are added in a fixed order
+                    mbar_arrive_if(s_free + set, lane == 0);
+                    // the 8 (term, range) partial sums of a (row, prototype) sit in the lanes that differ in bits 2-4: a
+                    // transposed butterfly adds them in a fixed order and halves the rows a lane keeps at every level
+                    // (14 shuffles, no shared memory): lane bit 4 -> row bit 3, bit 3 -> row bit 2, bit 2 -> row bit 1
+                    float v8[8], v4[4];
+                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) tr[n * 36 + lane] = __uint_as_float(sa[n]);
-                    __syncwarp();
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float* rd = tr + (8 * k + rj) * 36 + pl;
-                        sc2[k] = ((rd[0] + rd[4]) + (rd[8] + rd[12])) + ((rd[16] + rd[20]) + (rd[24] + rd[28]));
+                    for (int i = 0; i < 8; ++i) {
+                        const float lo = __uint_as_float(sa[i]), hi = __uint_as_float(sa[8 + i]);
+                        v8[i] = (u16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, u16 ? lo : hi, 16);
                     }
-                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v4[i] = (u8 ? v8[4 + i] : v8[i]) + __shfl_xor_sync(0xffffffffu, u8 ? v8[i] : v8[4 + i], 8);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) sc2[i] = (u4 ? v4[2 + i] : v4[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v4[i] : v4[2 + i], 4);
                 }
                 PROF_BEGIN();
-                mbar_wait_wd(full + b, ph);                            // acquire the converters' row info
+                mbar_wait_wd(full + b, ph);                            // acquire the norm warps' row info
                 PROF_END(1);
                 float4 info[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + 8 * k + rj) * 4);
+                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + 2 * rj + k) * 4);
                 // ---- in tile order from here: the other set has settled tile tt - 1
                 PROF_BEGIN();
                 if (tt > 0) mbar_wait_wd(decided + prev_set, ((tt - 1) / C::NSET) & 1u);
@@ -443,7 +451,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     for (int k = 0; k < 2; ++k) {
                         int de = int(__float_as_uint(info[k].y) >> 23) - exE;
                         de = de < -100 ? -100 : (de > 100 ? 100 : de);
-                        ts[k] = (8 * k + rj < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
+                        ts[k] = (2 * rj + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
                         unscale[k] = __uint_as_float(uint32_t(127 - de) << 23);       // 2^-(e_row - E)
                     }
                     grow = pvalid && (fmaxf(ts[0], ts[1]) > m_loc + C::MARGIN);        // true on the first tile
@@ -452,7 +460,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const float a = expf(sc2[k] * info[k].x - bw_m) * bw_il;       // A_pn (deepmil.py:198)
-                        cw[k] = (pvalid && 8 * k + rj < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
+                        cw[k] = (pvalid && 2 * rj + k < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
                     }
                     // binary exponent of the larger |cw| (zero / denormal -> very small, non-finite -> very large)
                     int et = int((__float_as_uint(fmaxf(fabsf(cw[0]), fabsf(cw[1]))) >> 23) & 0xffu) - 127;
@@ -501,11 +509,11 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     if (lane < 4) s_mref[p] = m_new;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(decided + set);             // releases s_mref / s_exE to the other set
+                mbar_arrive_if(decided + set, lane == 0);             // releases s_mref / s_exE to the other set
                 if (!BWD) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        w[k] = (pvalid && 8 * k + rj < nvalid) ? expf(ts[k] - m_loc) : 0.f;
+                        w[k] = (pvalid && 2 * rj + k < nvalid) ? expf(ts[k] - m_loc) : 0.f;
                         lsum = fmaf(w[k], unscale[k], lsum);
                     }
                 } else {
@@ -514,7 +522,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     for (int k = 0; k < 2; ++k) w[k] = cw[k] * inv_h;
                 }
                 // weights as two bf16 terms (w = t0 + t1, 16 significant bits; bf16 has the exponent range of fp32, no scaling);
-                // B operand row (term * 16 + p), K = tile row (rj | 8 + rj)
+                // B operand row (term * 16 + p), K = tile row (2 rj, 2 rj + 1)
                 unsigned short b0[2], b1[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
@@ -525,14 +533,12 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 PROF_BEGIN();
                 mbar_wait_wd(w_free + set, (v & 1u) ^ 1u);             // GEMM2 of tile tt - 2 has read this buffer
                 PROF_END(4);
-                unsigned char* wb = wt + set * C::WBUF;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    *reinterpret_cast<unsigned short*>(wb + sw128_offset(p, k, 2 * rj)) = b0[k];
-                    *reinterpret_cast<unsigned short*>(wb + sw128_offset(NP + p, k, 2 * rj)) = b1[k];
-                }
+                // tile rows 2 rj, 2 rj + 1 are neighbours along K: one 32-bit store per term
+                unsigned char* wb = wt + set * C::WBUF + w_off;
+                *reinterpret_cast<uint32_t*>(wb) = uint32_t(b0[0]) | (uint32_t(b0[1]) << 16);
+                *reinterpret_cast<uint32_t*>(wb + NP * 128) = uint32_t(b1[0]) | (uint32_t(b1[1]) << 16);
                 __syncwarp();                                          // (the GEMM2 issuer fences for the async proxy)
-                if (lane == 0) mbar_arrive(w_ready + set);
+                mbar_arrive_if(w_ready + set, lane == 0);
             }
             // ---- chunk end: both sets meet, agree on the final reference, write (m, l), drain O^T
             named_bar_sync(1 + 2 * C::NSET, NT);
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(d2_free);
+            mbar_arrive_if(d2_free, lane == 0);
             named_bar_sync(1 + 2 * C::NSET, NT);                                     // s_alpha / s_lsum / s_mref / s_exE are free again
         }
         PROF_FLUSH(12, 6, warp == 0 && lane == 0)

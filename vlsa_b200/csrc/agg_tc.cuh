@@ -6,11 +6,23 @@
 //   GEMM1  S^T[128, 32]  = Qn'[128, 512] (A, resident in TMEM) . [X_hi ; X_lo][32, 512]^T (B, K-major smem)
 //   GEMM2  O^T[512 d, 32 | 16] += X_hi^T | X_lo^T [512, 16] (A, MN-major, the SAME smem bytes) . W[32 | 16, 16]^T
 //
-// Precision design: as agg_tma.cuh (fp16 hi / lo planes of X and Qn, 8 accumulation steps per accumulator, two fp16
-// weight terms, lazily rescaled softmax reference / power-of-two normaliser).
+// Precision design (the tensor core truncates its fp32 accumulator toward zero after every instruction, so the number of
+// accumulation steps per accumulator is kept small):
+//   * every row of X is split into fp16 (hi, lo) planes: 22 significant bits at 4 bytes of shared memory per element; rows
+//     with |x| in [2, 2^14) are split as they are (every CONCH-like row), any other row is first scaled by a power of two
+//     from its own norm (|x~| in [1, 2)) that the weight warps undo exactly; Qn is split the same way;
+//   * A-operand row (TMEM lane) 32 w + j holds prototype p = 4 w + (j & 3), part (j >> 2) & 1 (hi / lo) of Qn restricted
+//     to the feature range 128 (j >> 3) .. +127 (zeros elsewhere): every accumulator only sees 8 non-zero steps, and the
+//     16 partial sums of a score (2 parts x 4 ranges x 2 planes) are added in fp32 registers.  TMEM quadrant q therefore
+//     owns prototypes 4 q .. 4 q + 3 completely;
+//   * the per-row weights go to the tensor core as two fp16 terms scaled 1 and 2^11 (22 bits); products with the hi and
+//     the lo plane of X accumulate in separate TMEM columns (a merged accumulator costs the backward three orders of
+//     magnitude of gradient accuracy: tiny lo-plane products are absorbed by a large, cancelling accumulator);
+//     tcgen05.mma needs A and B in the same 16-bit format, hence fp16 weights kept in range by a lazily rescaled softmax
+//     reference (forward) / a lazily grown power-of-two normaliser per prototype (backward, exact rescale).
 //
-// What bounds this pass on a B200 is SHARED-MEMORY BANDWIDTH, not HBM and not the tensor pipe (ncu of the TMA-fed
-// kernel, profiles/agg_tma_r02_ncu_summary.md: LSU + tensor-core shared-memory wavefronts = 96 % of the cycles).  Every
+// What bounds this pass on a B200 is SHARED-MEMORY BANDWIDTH, not HBM and not the tensor pipe (ncu of the TMA-fed kernel
+// this one replaced, profiles/agg_tc_r02_ncu_summary.md: LSU + tensor-core shared-memory wavefronts = 96 % of the cycles).  Every
 // byte of X crosses shared memory once per GEMM (two operand reads) plus whatever it takes to get the fp16 planes there:
 //   TMA-fed, converted in place : TMA write + LDS + STS + 2 operand reads = 5 passes  -> 0.70-0.77 of the HBM roofline
 //   this kernel                 : STS of the planes     + 2 operand reads = 3 passes
@@ -24,15 +36,16 @@
 //   * <= ~160 KB of shared memory per CTA: the loads in flight live in the L1 carve-out; above ~200 KB of shared memory
 //     the register path is capped at 6.3 TB/s (profiles/readbw_r01.txt).
 //
-// Tile = 16 rows, buffer layout as agg_tma.cuh: slot s (64 features) at s * 4096; row group g (8 rows) at + g * 2048;
+// Tile = 16 rows: slot s (64 features) at s * 4096; row group g (8 rows) at + g * 2048;
 // hi atom at + 0, lo atom at + 1024 (128-byte swizzle).
 //
 // Warp roles (20 warps, 1 persistent CTA / SM, static round-robin over chunks):
-//   warps 0-7   weights (two alternating sets of four, one warp per TMEM quadrant)      [as agg_tma.cuh]
+//   warps 0-7   weights (two alternating sets of four, one warp per TMEM quadrant)
 //   warp  8     GEMM1 issuer + TMEM allocation      warp 9   GEMM2 issuer      warps 10-11 idle (24 registers)
 //   warps 12-19 producers: rows 2 (w - 12), 2 (w - 12) + 1 of every tile
 #pragma once
-#include "agg_tma.cuh"
+#include "agg_simt.cuh"
+#include "tc_common.cuh"
 
 namespace vlsa {
 
@@ -59,8 +72,8 @@ struct TcCfg {
     static constexpr int WBUF = 2 * NP * 128;     // weight operand: 32 rows (term, prototype) x 128 B (32 B used)
     static constexpr int OFF_W = NBUF * TILE;
     static constexpr int OFF_F = OFF_W + 2 * WBUF;
-    // floats: rowinfo[NBUF][TR][4] | alpha[16] | mref[16] | lsum[2][16] | exE[4] | tr[8][16][36]
-    static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 16 + 32 + 4 + 8 * 16 * 36;
+    // floats: rowinfo[NBUF][TR][4] | alpha[16] | mref[16] | lsum[2][16] | exE[4]
+    static constexpr int NFLOAT = NBUF * TR * 4 + 16 + 16 + 32 + 4;
     static constexpr int OFF_BAR = OFF_F + NFLOAT * 4;
     static constexpr int NBAR = 2 * NBUF + 12;
     static constexpr int SMEM = OFF_BAR + NBAR * 8 + 16 + 1024;
@@ -97,7 +110,6 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
     float* s_mref = s_alpha + 16;                                    // [16] current softmax reference (fwd) | log2 H_p (bwd)
     float* s_lsum = s_mref + 16;                                     // [2][16] per-set softmax sums at a chunk end
     int* s_exE = reinterpret_cast<int*>(s_lsum + 32);                // [4] reference row-scale exponent of the chunk
-    float* s_tr = s_lsum + 32 + 4;                                   // [8 weight warps][16 rows][36] score transposition
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
     uint64_t* full = bars;                       // [NBUF] producers (8 warps)       -> GEMM1, weight warps (row info)
     uint64_t* empty = bars + C::NBUF;            // [NBUF] GEMM2 commit              -> producers
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                 // the register set is free: the tile R ahead goes in flight before this one is published
                 VLSA_TC_ISSUE(s)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full + b);
+                mbar_arrive_if(full + b, lane == 0);
                 cur_next(cv);
                 if (++b == uint32_t(C::NBUF)) { b = 0; par ^= 1u; }
             }
@@ -407,7 +419,8 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     PROF_BEGIN();
                     if (t == 0) mbar_wait_wd(d2_free, (cc & 1u) ^ 1u);   // previous chunk's accumulators drained
                     PROF_END(1);
-                    fence_proxy_async_smem();                            // as in the GEMM1 issuer (same tile buffer)
+                    fence_proxy_async_smem();                            // as in the GEMM1 issuer: the tile buffer and the weight
+                                                                         // operand the weight warps wrote with plain stores
                     tc_fence_after();
                     const uint64_t tb = umma_desc_advance(a0, b * C::TILE), wb = umma_desc_advance(w0, i * C::WBUF);
                     const uint32_t acc0 = t != 0;
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_SOFT));
         // Two sets of four warps (one per TMEM quadrant) take the tiles alternately: tile tt belongs to set tt & 1, which
         // also owns score buffer tt & 1 and weight buffer tt & 1 — two tiles are in this stage at any time.  A thread owns
-        // (prototype p = 4 q + (lane & 3)) x (tile rows rj, 8 + rj), so a warp sees all 16 rows of its four prototypes and
+        // (prototype p = 4 q + (lane & 3)) x (tile rows 2 rj, 2 rj + 1), so a warp sees all 16 rows of its four prototypes and
         // settles their softmax reference on its own.  What the sets share is the reference itself (s_mref): set s may
         // only decide tile tt after the other set has decided tile tt - 1 (mbarrier `decided`), and every thread folds a
         // reference it finds changed into its running sum before going on.
@@ -441,7 +454,8 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
         const bool pvalid = p < P;
         const uint32_t tq = tmem + (uint32_t(32 * q) << 16);
         constexpr int NT = C::NSOFT * 32, NTS = NT / 2;
-        float* tr = s_tr + warp * (16 * 36);
+        // B operand of GEMM2: row (term * 16 + p), K = tile row: rows 2 rj, 2 rj + 1 -> 16-byte chunk rj >> 2, bytes 4 (rj & 3)
+        const uint32_t w_off = sw128_offset(p, rj >> 2, 4 * (rj & 3));
         uint32_t tt = 0, cc = 0;
         PROF_DECL
         for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x, ++cc) {
@@ -481,28 +495,29 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(s_free + set);
-                    // add the planes, then transpose through shared memory (row pitch 36 floats: conflict-free both ways):
-                    // the 8 (part, range) partial sums of a (row, prototype) are added in a fixed order
+                    mbar_arrive_if(s_free + set, lane == 0);
+                    // add the planes; the 8 (part, range) partial sums of a (row, prototype) then sit in the lanes that differ
+                    // in bits 2-4: a transposed butterfly adds them in a fixed order and halves the rows a lane keeps at every
+                    // level (14 shuffles, no shared memory): lane bit 4 -> row bit 3, bit 3 -> row bit 2, bit 2 -> row bit 1
+                    float v8[8], v4[4];
+                    const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) {
-                        tr[n * 36 + lane] = __uint_as_float(sa[n]) + __uint_as_float(sa[8 + n]);
-                        tr[(8 + n) * 36 + lane] = __uint_as_float(sa[16 + n]) + __uint_as_float(sa[24 + n]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float lo = __uint_as_float(sa[i]) + __uint_as_float(sa[8 + i]);            // rows 0 .. 7
+                        const float hi = __uint_as_float(sa[16 + i]) + __uint_as_float(sa[24 + i]);      // rows 8 .. 15
+                        v8[i] = (u16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, u16 ? lo : hi, 16);
                     }
-                    __syncwarp();
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const float* rd = tr + (8 * k + rj) * 36 + pl;
-                        sc2[k] = ((rd[0] + rd[4]) + (rd[8] + rd[12])) + ((rd[16] + rd[20]) + (rd[24] + rd[28]));
-                    }
-                    __syncwarp();
+                    for (int i = 0; i < 4; ++i) v4[i] = (u8 ? v8[4 + i] : v8[i]) + __shfl_xor_sync(0xffffffffu, u8 ? v8[i] : v8[4 + i], 8);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) sc2[i] = (u4 ? v4[2 + i] : v4[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v4[i] : v4[2 + i], 4);
                 }
                 PROF_BEGIN();
                 mbar_wait_wd(full + b, ph);                            // acquire the converters' row info
                 PROF_END(1);
                 float4 info[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + 8 * k + rj) * 4);
+                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + 2 * rj + k) * 4);
                 // ---- in tile order from here: the other set has settled tile tt - 1
                 PROF_BEGIN();
                 if (tt > 0) mbar_wait_wd(decided + (set ^ 1), ((tt - 1) >> 1) & 1u);
@@ -527,7 +542,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     for (int k = 0; k < 2; ++k) {
                         int de = int(__float_as_uint(info[k].y) >> 23) - exE;
                         de = de < -100 ? -100 : (de > 100 ? 100 : de);
-                        ts[k] = (8 * k + rj < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
+                        ts[k] = (2 * rj + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
                         unscale[k] = __uint_as_float(uint32_t(127 - de) << 23);       // 2^-(e_row - E)
                     }
                     grow = pvalid && (fmaxf(ts[0], ts[1]) > m_loc + C::MARGIN);        // true on the first tile
@@ -536,7 +551,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const float a = expf(sc2[k] * info[k].x - bw_m) * bw_il;       // A_pn (deepmil.py:198)
-                        cw[k] = (pvalid && 8 * k + rj < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
+                        cw[k] = (pvalid && 2 * rj + k < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
                     }
                     // binary exponent of the larger |cw| (zero / denormal -> very small, non-finite -> very large)
                     int et = int((__float_as_uint(fmaxf(fabsf(cw[0]), fabsf(cw[1]))) >> 23) & 0xffu) - 127;
@@ -585,11 +600,11 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                     if (lane < 4) s_mref[p] = m_new;
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(decided + set);             // releases s_mref / s_exE to the other set
+                mbar_arrive_if(decided + set, lane == 0);             // releases s_mref / s_exE to the other set
                 if (!BWD) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        w[k] = (pvalid && 8 * k + rj < nvalid) ? expf(ts[k] - m_loc) : 0.f;
+                        w[k] = (pvalid && 2 * rj + k < nvalid) ? expf(ts[k] - m_loc) : 0.f;
                         lsum = fmaf(w[k], unscale[k], lsum);
                     }
                 } else {
@@ -597,7 +612,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
 #pragma unroll
                     for (int k = 0; k < 2; ++k) w[k] = cw[k] * inv_h;
                 }
-                // weights as two fp16 terms (w = t0 + 2^-11 t1); B operand row (term * 16 + p), K = tile row (rj | 8 + rj)
+                // weights as two fp16 terms (w = t0 + 2^-11 t1); B operand row (term * 16 + p), K = tile row (2 rj, 2 rj + 1)
                 unsigned short b0[2], b1[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
@@ -608,15 +623,12 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
                 PROF_BEGIN();
                 mbar_wait_wd(w_free + set, (v & 1u) ^ 1u);             // GEMM2 of tile tt - 2 has read this buffer
                 PROF_END(4);
-                unsigned char* wb = wt + set * C::WBUF;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    *reinterpret_cast<unsigned short*>(wb + sw128_offset(p, k, 2 * rj)) = b0[k];
-                    *reinterpret_cast<unsigned short*>(wb + sw128_offset(NP + p, k, 2 * rj)) = b1[k];
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(w_ready + set);
+                // tile rows 2 rj, 2 rj + 1 are neighbours along K: one 32-bit store per term
+                unsigned char* wb = wt + set * C::WBUF + w_off;
+                *reinterpret_cast<uint32_t*>(wb) = uint32_t(b0[0]) | (uint32_t(b0[1]) << 16);
+                *reinterpret_cast<uint32_t*>(wb + NP * 128) = uint32_t(b1[0]) | (uint32_t(b1[1]) << 16);
+                __syncwarp();                                          // (the GEMM2 issuer fences for the async proxy)
+                mbar_arrive_if(w_ready + set, lane == 0);
             }
             // ---- chunk end: both sets meet, agree on the final reference, write (m, l), drain O^T
             named_bar_sync(7, NT);
@@ -664,7 +676,7 @@ __global__ void __launch_bounds__(TcCfg::THREADS, 1) agg_tc_kernel(const AggPara
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(d2_free);
+            mbar_arrive_if(d2_free, lane == 0);
             named_bar_sync(7, NT);                                     // s_alpha / s_lsum / s_mref / s_exE are free again
         }
         PROF_FLUSH(12, 6, warp == 0 && lane == 0)

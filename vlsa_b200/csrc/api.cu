@@ -9,7 +9,6 @@
 #include <atomic>
 
 #include "agg_simt.cuh"
-#include "agg_tma.cuh"
 #include "agg_tc.cuh"
 #include "agg_bf16.cuh"
 #include "head_kernels.cuh"
@@ -58,8 +57,9 @@ using namespace vlsa;
 #ifndef VLSA_BF16_TC_MIN_P
 #define VLSA_BF16_TC_MIN_P 1     // bf16 rows: tensor-core kernel from this P on (measured: 315 vs 472 us at P = 4, 332 vs 1226 us at P = 12)
 #endif
-static constexpr int kRowTile = 32;   // a multiple of TmaCfg::TR and of the CUDA-core kernel's AggCfg::TN
-static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile % TmaCfg::TR == 0, "chunk_rows must suit both streaming kernels");
+static constexpr int kRowTile = 32;   // a multiple of the tcgen05 kernels' tile (16 rows) and of the CUDA-core kernel's AggCfg::TN
+static_assert(kRowTile % (4 * VLSA_AGG_WARPS) == 0 && kRowTile % TcCfg::TR == 0 && kRowTile % Bf16Cfg::TR == 0,
+              "chunk_rows must suit every streaming kernel");
 
 static int device_sm_count() {
     int dev = 0, sms = 0;
@@ -174,33 +174,6 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// TMA-fed tcgen05 kernel: X [total_rows, 512] fp32 as a 2-D tensor, box = 16 rows x 64 columns (one slot of a tile)
-template <bool BWD>
-static int launch_agg_tma(const AggParams& prm, int P, long long total_rows, cudaStream_t st) {
-    using C = TmaCfg;
-    if (total_rows <= 0 || total_rows > 0x7fffffffLL) return VLSA_EINVAL;
-    if (reinterpret_cast<uintptr_t>(prm.X) & 15u) return VLSA_EINVAL;
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return VLSA_EUNSUPPORTED;
-    CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {cuuint64_t(VLSA_D), cuuint64_t(total_rows)};
-    const cuuint64_t gstr[1] = {cuuint64_t(VLSA_D) * sizeof(float)};
-    const cuuint32_t box[2] = {64u, cuuint32_t(C::TR)};
-    const cuuint32_t estr[2] = {1u, 1u};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(prm.X), gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return VLSA_EINVAL;
-    auto kern = agg_tma_kernel<BWD>;
-    static std::atomic<int> cache[kMaxDevices];
-    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
-    const int sms = device_sm_count();
-    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
-    if (grid <= 0) return 0;
-    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P, tmap);
-    return static_cast<int>(cudaGetLastError());
-}
-
 // bf16-stored rows on the tensor cores (agg_bf16.cuh): X [total_rows, 512] bf16 as a 2-D tensor, box = 16 rows x 64 columns
 // landing as two 128-byte-swizzled K-major atoms
 template <bool BWD>
@@ -247,19 +220,18 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
 // Which streaming kernel serves a pass.  Default: fp32 rows — the register-staged tcgen05 kernel for P > 5 (the CUDA-core
 // kernel is at the HBM roofline for P <= 5); bf16 rows — the TMA-fed tcgen05 kernel for every P.  The caller can force a
 // kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
-enum AggKernel { kAggSimt = 0, kAggTma = 1, kAggTc = 2, kAggBf16 = 3 };
+enum AggKernel { kAggSimt = 0, kAggTc = 2, kAggBf16 = 3 };
 static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
     if (dtype == VLSA_DTYPE_BF16) return ((x_dtype_flags & VLSA_KERNEL_TC) || P > VLSA_BF16_TC_MIN_P - 1) ? kAggBf16 : kAggSimt;
-    if (x_dtype_flags & VLSA_KERNEL_TC_TMA) return kAggTma;
     if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTc;
     return P > 5 ? kAggTc : kAggSimt;
 }
 static bool dtype_ok(int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
     return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
-           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_KERNEL_TC_TMA | VLSA_ROWS_RANGES)) == 0;
+           (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_ROWS_RANGES)) == 0;
 }
 
 // prototypes per launch of the per-prototype-gradient backward (measured best, profiles/variant_time_r01.json)
@@ -267,7 +239,6 @@ static constexpr int kGenGroup = 8;
 
 static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long total_rows, cudaStream_t st) {
     const AggKernel k = agg_kernel_choice(P, x_dtype);
-    if (k == kAggTma) return launch_agg_tma<false>(prm, P, total_rows, st);
     if (k == kAggTc) return launch_agg_tc<false>(prm, P, st);
     if (k == kAggBf16) return launch_agg_bf16<false>(prm, P, total_rows, st);
     int rc = 0;
@@ -445,10 +416,7 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
     prm.dv = ws.dv; prm.ml = ml; prm.delta = ws.delta; prm.q_prenorm = q_prenorm;
     int rc = 0;
     const AggKernel kern = total_chunks > 0 ? agg_kernel_choice(P, x_dtype) : kAggSimt;
-    if (kern == kAggTma) {
-        rc = launch_agg_tma<true>(prm, P, total_rows, st);
-        if (rc) return rc;
-    } else if (kern == kAggTc) {
+    if (kern == kAggTc) {
         rc = launch_agg_tc<true>(prm, P, st);
         if (rc) return rc;
     } else if (kern == kAggBf16) {

@@ -29,6 +29,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive only where `pred` holds — a predicated instruction, no divergent branch (no BSSY / BSYNC pair around it)
+__device__ __forceinline__ void mbar_arrive_if(uint64_t* bar, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(uint32_t(pred)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

@@ -1,6 +1,7 @@
 // tcgen05 / TMEM / UMMA-descriptor helpers (sm_100a).  Raw PTX; layouts follow the PTX ISA canonical
 // shared-memory layouts for tcgen05.mma (128-byte swizzle) — see DESIGN.md §4 (tensor-core variant).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
 
@@ -139,7 +140,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
     return ok != 0;
 }
 // Fast path first: one try_wait (it sleeps in hardware up to its suspend hint) decides almost every wait.  The watchdog
-// loop stays INLINE: moving it into a __noinline__ function made the backward of agg_tma_kernel fault intermittently
+// loop stays INLINE: moving it into a __noinline__ function made the backward of the TMA-fed tcgen05 kernel of round 2 fault intermittently
 // (illegal address, only without compute-sanitizer) — a call from single-elected-lane / tcgen05 code is not worth it.
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_hint(bar, parity, 4000u)) return;
@@ -179,6 +180,35 @@ __device__ __forceinline__ bool named_bar_or(int id, int nthreads, bool pred) {
         : "=r"(out) : "r"(id), "r"(nthreads), "r"(uint32_t(pred)) : "memory");
     return out != 0;
 }
+
+// 2-D tiled TMA load global -> shared (SASS: UTMALDG), completion on an mbarrier, L2 evict-first
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// Development build (-DVLSA_TMA_PROF): block 0 of a tcgen05 kernel accumulates, per role, the cycles spent in every kind
+// of wait (read back with vlsa_debug_read_prof, scripts/dev_tma_prof.py).  Compiled out of the shipped library.
+#ifdef VLSA_TMA_PROF
+__device__ long long g_tma_prof[32];
+#define PROF_DECL long long prof_t0 = 0, prof_acc[6] = {0, 0, 0, 0, 0, 0}; const long long prof_start = clock64(); (void)prof_t0;
+#define PROF_BEGIN() prof_t0 = clock64()
+#define PROF_END(k) prof_acc[k] += clock64() - prof_t0
+#define PROF_FLUSH(base, n, who)                                                                 \
+    if (blockIdx.x == 0 && (who)) {                                                              \
+        for (int k_ = 0; k_ < (n); ++k_) g_tma_prof[(base) + k_] = prof_acc[k_];                 \
+        g_tma_prof[(base) + (n)] = clock64() - prof_start;                                       \
+    }
+#else
+#define PROF_DECL
+#define PROF_BEGIN()
+#define PROF_END(k)
+#define PROF_FLUSH(base, n, who)
+#endif
 
 }  // namespace vlsa
 

@@ -28,14 +28,14 @@ def coattn_scale() -> float:
     return float((torch.ones([]) * np.log(100)).exp())
 
 
-_KERNEL_FLAG = {None: 0, "auto": 0, "simt": 0x100, "tc": 0x200, "tc_tma": 0x400}
+_KERNEL_FLAG = {None: 0, "auto": 0, "simt": 0x100, "tc": 0x200}
 _agg_variant_flag = 0
 
 
 def set_agg_variant(variant: str | None) -> None:
     """Cross-check hook of the parity tests: force the streaming kernel of fp32 passes — 'simt' = CUDA cores, 'tc' = the
-    register-staged tcgen05 kernel, 'tc_tma' = the TMA-fed tcgen05 kernel — or None for the automatic choice ('tc' for
-    P > 5).  The choice travels with every call as a VLSA_KERNEL_* bit of x_dtype (include/vlsa_b200.h); the library
+    tcgen05 kernel (register-staged for fp32 rows, TMA-fed for bf16 rows) — or None for the automatic choice (fp32: 'tc' for
+    P > 5; bf16: always 'tc').  The choice travels with every call as a VLSA_KERNEL_* bit of x_dtype (include/vlsa_b200.h); the library
     itself keeps no switch."""
     global _agg_variant_flag
     _agg_variant_flag = _KERNEL_FLAG[variant]
