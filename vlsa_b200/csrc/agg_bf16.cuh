@@ -9,8 +9,8 @@
 // the two 8-row K-major atoms the tensor core reads, so a byte of X crosses shared memory four times at HALF the bytes of
 // the fp32 kernels: TMA write, one LDS pass for the row norms (fp32 FMAs on the unpacked values; backward: also
 // u = dv . x / P), and the two operand reads.  The values the tensor core multiplies are exactly the stored ones; the
-// bf16 terms of Qn (two: 16 significant bits, one accumulator per 128-feature range as in agg_tc.cuh) and of the weights
-// (two) carry the rest of the precision, accumulation is fp32 in TMEM.  bf16 has the exponent range of fp32: no row
+// bf16 terms of Qn (three: 24 significant bits, one accumulator per term and 256-feature range) and of the weights (two)
+// carry the rest of the precision, accumulation is fp32 in TMEM.  bf16 has the exponent range of fp32: no row
 // scaling, no weight-term scaling (the lazily rescaled softmax reference is still what keeps the ACCUMULATORS in range).
 //
 // Tile = 16 rows = 16 KB: slot s (64 features) at s * 2048; row group g (8 rows) at + g * 1024 (128-byte swizzle).  Ring
@@ -128,20 +128,20 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     if (warp < 4) {
-        // TMEM lane 32 warp + lane: prototype 4 warp + (lane & 3), bf16 term (lane >> 2) & 1, feature range lane >> 3
+        // TMEM lane 32 warp + lane: prototype 4 warp + (lane & 3); c = lane >> 2: bf16 term c % 3 of Qn (three terms: 24
+        // significant bits) restricted to the feature range 256 (c / 3) .. + 255 for c < 6, a zero row for c = 6, 7
         const float* qrow = reinterpret_cast<const float*>(ring) + (4 * warp + (lane & 3)) * C::QPITCH;
-        const bool lo_part = (lane >> 2) & 1;
-        const int range = lane >> 3;
+        const int c8 = lane >> 2, term = c8 % 3, range = c8 / 3;
         const uint32_t tq = tmem + (uint32_t(32 * warp) << 16) + C::TM_Q;
 #pragma unroll 1
         for (int cb = 0; cb < 8; ++cb) {
             uint32_t v[32];
-            const bool mine = (cb >> 1) == range;
+            const bool mine = c8 < 6 && (cb >> 2) == range;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                uint32_t hi, lo;
-                split_bf16x2(qrow[cb * 64 + 2 * i], qrow[cb * 64 + 2 * i + 1], hi, lo);
-                v[i] = mine ? (lo_part ? lo : hi) : 0u;
+                uint32_t t0, t1, t2;
+                split_bf16x3(qrow[cb * 64 + 2 * i], qrow[cb * 64 + 2 * i + 1], t0, t1, t2);
+                v[i] = mine ? (term == 0 ? t0 : (term == 1 ? t1 : t2)) : 0u;
             }
             tmem_st32(tq + 32 * cb, v);
         }
@@ -399,14 +399,14 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 tc_fence_after();
                 float sc2[2];
                 {
-                    // 16 partial scores of this lane's (prototype, term, range): tile rows 0 .. 15
+                    // 16 partial scores of this lane's (prototype, term, range): tile rows 0 .. 15 (zeros in the two spare lanes)
                     uint32_t sa[16];
                     tmem_ld16(tq + C::TM_D1 + TR * set, sa);
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
                     mbar_arrive_if(s_free + set, lane == 0);
-                    // the 8 (term, range) partial sums of a (row, prototype) sit in the lanes that differ in bits 2-4: a
+                    // the 6 (term, range) partial sums of a (row, prototype) (and two zeros) sit in the lanes that differ in bits 2-4: a
                     // transposed butterfly adds them in a fixed order and halves the rows a lane keeps at every level
                     // (14 shuffles, no shared memory): lane bit 4 -> row bit 3, bit 3 -> row bit 2, bit 2 -> row bit 1
                     float v8[8], v4[4];

@@ -159,6 +159,15 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 
+// x = t0 + t1 + t2 with bf16 terms (24 significant bits); packs (a, b) -> bf16x2 with a in the low half
+__device__ __forceinline__ void split_bf16x3(float a, float b, uint32_t& t0, uint32_t& t1, uint32_t& t2) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t0) : "f"(b), "f"(a));
+    const float ra = a - __uint_as_float(t0 << 16), rb = b - __uint_as_float(t0 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t1) : "f"(rb), "f"(ra));
+    const float sa = ra - __uint_as_float(t1 << 16), sb = rb - __uint_as_float(t1 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(sb), "f"(sa));
+}
+
 // x = hi + lo with hi, lo fp16 (packed pairs, first element in the low half); SASS: 2 F2FP + 2 HADD2.F32 + 1 FADD2
 __device__ __forceinline__ void split_f16x2(float2 a, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __float22half2_rn(a);
