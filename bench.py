@@ -302,7 +302,7 @@ class Timer:
         return e0.elapsed_time(e1) / steps
 
 
-def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, esize, train=True, labels_seed=77):
+def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, esize, train=True, labels_seed=77, kernel=None):
     """Forward through the public API, the dominant kernel alone, and one optimizer step, for one (P, R) on the given
     device-resident batches.  `plans[i]` goes with `batches[i]`."""
     from vlsa_b200 import ops, synth
@@ -317,8 +317,8 @@ def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, es
     wss = [ops._workspace(p, P, dev) for p in plans]
     ms_k = timer(lambda i: ops.aggregate_partial_only(batches[i % len(batches)], plans[i % len(plans)], Q, wss[i % len(plans)]), steps)
     rec = {"P": P, "R": R, "value": nb * world / (ms_fwd * 1e-3), "unit": "WSI/s", "ms_per_step": ms_fwd,
-           "kernel": ("agg_bf16_kernel<false> (tcgen05, TMA-fed bf16 rows)" if esize == 2 else
-                      "agg_tc_kernel<false> (tcgen05, register-staged rows)" if P > 5 else "agg_simt_kernel<P,0,float>"),
+           "kernel": kernel or ("agg_bf16_kernel<false> (tcgen05, TMA-fed bf16 rows)" if esize == 2 else
+                                "agg_tc_kernel<false> (tcgen05, register-staged rows)" if P > 5 else "agg_simt_kernel<P,0,float>"),
            "kernel_ms": ms_k, "achieved_gbs": algo_bytes / (ms_k * 1e-3) / 1e9, "frac": algo_bytes / (ms_k * 1e-3) / 1e9 / peak,
            "frac_whole_forward": algo_bytes / (ms_fwd * 1e-3) / 1e9 / peak}
     if train:
@@ -430,6 +430,30 @@ def main():
         shipped = measure_shape(12, 12, batches, plans, dev, timer, max(10, args.steps // 2), world, rank, peak, esize,
                                 train=not args.no_train)
         reduce_max(shipped, dev, dist)
+        if esize == 4:
+            # the same bags as a device cohort stored as pre-split tile images (DeviceCohort(layout="split16"): packed ONCE at
+            # upload, the pass converts nothing).  Forward results are bit-identical to the fp32-row record above.
+            cohorts16 = []
+            t_pack = []
+            for bt in batches:
+                c16 = DeviceCohort(dev, nb * ((rows + 15) // 16 * 16), layout="split16")
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for b_ in range(nb):
+                    c16.add(b_, bt[b_ * rows:(b_ + 1) * rows])
+                e1.record()
+                torch.cuda.synchronize(dev)
+                t_pack.append(e0.elapsed_time(e1))
+                cohorts16.append(c16)
+            rec16 = measure_shape(12, 12, [c.X for c in cohorts16], [c.plan(list(range(nb))) for c in cohorts16], dev, timer,
+                                  max(10, args.steps // 2), world, rank, peak, esize, train=not args.no_train,
+                                  kernel="agg_split_kernel<false> (tcgen05, one bulk copy per pre-split 16-row record)")
+            reduce_max(rec16, dev, dist)
+            rec16["pack_ms_per_step_of_rows"] = float(np.mean(t_pack))
+            rec16["what"] = ("the P=R=12 record on a device cohort in the split16 layout (2 056 B per row instead of 2 048; fractions "
+                             "count 2 048): packed once per cohort upload by vlsa_split16_pack, steps drawn by row-range plans")
+            shipped["cohort_split16"] = rec16
+            del cohorts16
 
     # ---- a ragged step: N_i ~ LogUniform(1k, 100k), fixed seeds (BASELINE configs[2]) ---------------------
     ragged = None

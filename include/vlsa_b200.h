@@ -39,6 +39,8 @@ extern "C" {
 
 #define VLSA_DTYPE_F32 0
 #define VLSA_DTYPE_BF16 1
+#define VLSA_DTYPE_SPLIT16 2 /* pre-split tile images of a device cohort, see vlsa_split16_pack (vlsa_agg_fwd / _partial_fwd / _bwd /
+                              * _pooled_fwd only, together with VLSA_ROWS_RANGES) */
 #define VLSA_DTYPE_MASK 0xff
 /* Optional bits OR-ed into x_dtype of the vlsa_agg_* calls: force the streaming kernel of an fp32 pass for THIS call
  * (cross-checks in the parity tests; default = automatic: fp32 rows — register-staged tcgen05 kernel for P > 5, CUDA-core
@@ -62,6 +64,17 @@ extern "C" {
 
 int vlsa_version(void);
 const char* vlsa_error_string(int code);
+/* Device cohort stored as pre-split tile images (VLSA_DTYPE_SPLIT16).  Replaces, for bags that stay resident in HBM across
+ * epochs, the per-epoch `.cuda()` of fp32 rows (runner/vlsa_handler.py:205, dataset/PatchWSI.py:197-215) AND the fp32 -> fp16
+ * (hi, lo) split the tensor-core kernel would redo on every pass: rows are packed ONCE, at upload time, into records of 16 rows
+ * — the shared-memory image of the tensor-core kernel's tile (8 slots x 2 row groups x (hi | lo) 128-byte-swizzled atoms) followed
+ * by 16 x (1 / |x~|, 2^e) — `vlsa_split16_row_bytes()` = 2 056 bytes per row, the same 4 bytes per element as fp32.  A pass then
+ * lands a tile with one bulk copy and converts nothing; results are bit-identical to the fp32-row tensor-core kernel's.
+ * `image` holds records back to back; a bag starts at a record boundary: `first_row` (padded row space) % 16 == 0, and the
+ * ranges of a plan (VLSA_ROWS_RANGES) are given in that padded row space.  X [n_rows, 512] fp32 on the device. */
+size_t vlsa_split16_row_bytes(void);
+int vlsa_split16_pack(const float* X, int64_t n_rows, void* image, int64_t first_row, void* stream);
+
 /* Host-only helper: split the bags of one call into row chunks for the streaming kernels.
  * cu_rows_host[B+1] are the row offsets of the bags inside the packed X.  Writes chunk_start_host[B+1]
  * (first chunk id of every bag; chunk_start_host[B] = total chunks) and *chunk_rows_out (rows per

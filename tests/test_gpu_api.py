@@ -386,3 +386,69 @@ def test_device_cohort_row_range_plans_match_packed_batches(dev):
         cohort.plan([99])
     with pytest.raises(MemoryError):
         cohort.reserve("x", 10 ** 9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P", [7, 12, 16, 4])
+def test_split16_cohort_is_bit_identical_to_the_fp32_tensor_core_kernel(P, dev):
+    """A device cohort stored as pre-split tile images (layout='split16', vlsa_split16_pack + agg_split_kernel) against the
+    same bags as fp32 rows through the register-staged tensor-core kernel: same planes, same summation orders — the FORWARD
+    (incidence, logits, per-prototype softmax statistics) must be bit-identical, for shuffled steps with a repeated bag, bags
+    of 1 row, of tiny and of huge rows (the power-of-two row scale).  The backward takes u = dv . x / P from the (hi + lo)
+    planes instead of the raw row (another summation order): gradients within 2e-5 of their largest entry, and an optimizer
+    step leaves the same weights to 1e-6."""
+    from vlsa_b200 import ops, synth
+    from vlsa_b200.dataset import DeviceCohort
+    from vlsa_b200.runner import VLSAHandler
+    sizes = [1000, 37, 2798, 1, 513, 64, 4096, 255, 16, 17]
+    bags = [synth.make_bag("g1", n, 300 + i) for i, n in enumerate(sizes)]
+    bags[2] = bags[2] * 1e-3
+    bags[5] = bags[5] * 3e3
+    pr = synth.make_params(P, P, 40 + P)
+    cohort = DeviceCohort(dev, sum((n + 15) // 16 * 16 for n in sizes), layout="split16")
+    for i, b in enumerate(bags):
+        cohort.add(i, b)
+    assert len(cohort) == len(sizes) and cohort.X.shape[1] == ops.SPLIT16_COLS
+    order = [6, 1, 3, 0, 6, 7, 2, 5, 9, 8, 4]
+    t, e = synth.make_labels(len(order), P, 5)
+    res = {}
+    try:
+        ops.set_agg_variant("tc")                       # fp32 rows on the tensor-core kernel whatever P
+        for name in ("rows", "split16"):
+            leaf = lambda z: z.detach().clone().to(dev).requires_grad_(True)
+            r, W, b, T, ls = (leaf(pr[k]) for k in ("residual_features", "W", "b", "text_features", "logit_scale"))
+            Q = pr["res_ratio"] * r + pr["prompt_features"].to(dev)
+            if name == "rows":
+                X, plan = torch.cat([bags[i] for i in order], 0).to(dev), ops.make_plan([sizes[i] for i in order], dev)
+            else:
+                X, plan = cohort.X, cohort.plan(order)
+            logits, g, Tn, inc, ml = ops.aggregate(X, plan, Q, W, b, T, ls)
+            total, *_ = ops.surv_loss(logits, t.to(dev), e.to(dev), ls)
+            total.backward()
+            torch.cuda.synchronize()
+            res[name] = dict(inc=inc.detach(), logits=logits.detach(), ml=ml.detach(), d_res=r.grad, d_W=W.grad, d_b=b.grad,
+                             d_T=T.grad, d_ls=ls.grad)
+    finally:
+        ops.set_agg_variant(None)
+    for k in ("inc", "logits", "ml"):
+        assert torch.equal(res["rows"][k], res["split16"][k]), k
+    for k in ("d_res", "d_W", "d_b", "d_T", "d_ls"):
+        a, b_ = res["rows"][k], res["split16"][k]
+        assert float((a - b_).abs().max()) <= 2e-5 * max(float(a.abs().max()), 1e-30), k
+    # the handler on the cohort: default dispatch (P > 5: the same tensor-core arithmetic -> identical weights)
+    if P > 5:
+        cfg = dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4)
+        ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(order))]
+        net_a, net_b = build_net(pr, P, P, dev), build_net(pr, P, P, dev)
+        for n_ in (net_a, net_b):
+            n_.pretrained_text_features.requires_grad_(False)
+        ha, hb = VLSAHandler(cfg, net_a, device=dev), VLSAHandler(cfg, net_b, device=dev)
+        la, pa = ha.update_network_cached(cohort, order, ys)
+        lb, pb = hb._update_network([bags[i].unsqueeze(0).to(dev) for i in order], ys)
+        assert la == lb and torch.equal(pa, pb)
+        for (k, va), (_, vb) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+            assert torch.allclose(va, vb, rtol=0, atol=1e-6), k
+    with pytest.raises(RuntimeError):
+        cohort.reserve("x", 10)
+    with pytest.raises(ValueError):
+        ops.aggregate(cohort.X, ops.make_plan([16], dev), Q.detach(), W.detach(), b.detach(), T.detach(), ls.detach())

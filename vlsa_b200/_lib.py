@@ -22,6 +22,8 @@ _SIGNATURES = {
     "vlsa_error_string": (C.c_char_p, [C.c_int]),
     "vlsa_agg_plan": (C.c_int, [C.POINTER(C.c_int64), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32)]),
     "vlsa_agg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "vlsa_split16_row_bytes": (C.c_size_t, []),
+    "vlsa_split16_pack": (C.c_int, [c_f32p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "vlsa_agg_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_i64p, c_i32p, C.c_int, C.c_int, C.c_int, c_f32p, C.c_int,
                                C.c_int, C.c_float, c_f32p, c_f32p, c_f32p, C.c_int, c_f32p, C.c_void_p, C.c_size_t,
                                c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p]),

@@ -11,6 +11,7 @@
 #include "agg_simt.cuh"
 #include "agg_tc.cuh"
 #include "agg_bf16.cuh"
+#include "agg_split.cuh"
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
@@ -202,6 +203,22 @@ static int launch_agg_bf16(const AggParams& prm, int P, long long total_rows, cu
     return static_cast<int>(cudaGetLastError());
 }
 
+// pre-split tile images of a device cohort (agg_split.cuh): one bulk copy per 16-row record
+template <bool BWD>
+static int launch_agg_split(const AggParams& prm, int P, cudaStream_t st) {
+    using C = SplitCfg;
+    if (reinterpret_cast<uintptr_t>(prm.X) & 15u) return VLSA_EINVAL;
+    if (!prm.row_ranges) return VLSA_EINVAL;                 // bags start at record boundaries: ranges in the padded row space
+    auto kern = agg_split_kernel<BWD>;
+    static std::atomic<int> cache[kMaxDevices];
+    if (kernel_slots(kern, C::THREADS, int(C::SMEM), cache) <= 0) return static_cast<int>(cudaGetLastError());
+    const int sms = device_sm_count();
+    const int grid = prm.total_chunks < sms ? prm.total_chunks : sms;
+    if (grid <= 0) return 0;
+    kern<<<grid, C::THREADS, C::SMEM, st>>>(prm, P);
+    return static_cast<int>(cudaGetLastError());
+}
+
 // register-staged tcgen05 kernel (agg_tc.cuh): rows through LDG, three shared-memory passes per byte
 template <bool BWD>
 static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
@@ -220,9 +237,10 @@ static int launch_agg_tc(const AggParams& prm, int P, cudaStream_t st) {
 // Which streaming kernel serves a pass.  Default: fp32 rows — the register-staged tcgen05 kernel for P > 5 (the CUDA-core
 // kernel is at the HBM roofline for P <= 5); bf16 rows — the TMA-fed tcgen05 kernel for every P.  The caller can force a
 // kernel per call with the VLSA_KERNEL_* bits of x_dtype (cross-checks in the parity tests): no process-wide switch.
-enum AggKernel { kAggSimt = 0, kAggTc = 2, kAggBf16 = 3 };
+enum AggKernel { kAggSimt = 0, kAggTc = 2, kAggBf16 = 3, kAggSplit = 4 };
 static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
+    if (dtype == VLSA_DTYPE_SPLIT16) return kAggSplit;
     if (x_dtype_flags & VLSA_KERNEL_SIMT) return kAggSimt;
     if (dtype == VLSA_DTYPE_BF16) return ((x_dtype_flags & VLSA_KERNEL_TC) || P > VLSA_BF16_TC_MIN_P - 1) ? kAggBf16 : kAggSimt;
     if (x_dtype_flags & VLSA_KERNEL_TC) return kAggTc;
@@ -230,6 +248,7 @@ static AggKernel agg_kernel_choice(int P, int x_dtype_flags) {
 }
 static bool dtype_ok(int x_dtype_flags) {
     const int dtype = x_dtype_flags & VLSA_DTYPE_MASK;
+    if (dtype == VLSA_DTYPE_SPLIT16) return (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_TC)) == VLSA_ROWS_RANGES;
     return (dtype == VLSA_DTYPE_F32 || dtype == VLSA_DTYPE_BF16) &&
            (x_dtype_flags & ~(VLSA_DTYPE_MASK | VLSA_KERNEL_SIMT | VLSA_KERNEL_TC | VLSA_ROWS_RANGES)) == 0;
 }
@@ -241,6 +260,7 @@ static int launch_agg_fwd(const AggParams& prm, int P, int x_dtype, long long to
     const AggKernel k = agg_kernel_choice(P, x_dtype);
     if (k == kAggTc) return launch_agg_tc<false>(prm, P, st);
     if (k == kAggBf16) return launch_agg_bf16<false>(prm, P, total_rows, st);
+    if (k == kAggSplit) return launch_agg_split<false>(prm, P, st);
     int rc = 0;
     VLSA_DISPATCH_P(P, {
         if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 0, float>(prm, st);
@@ -266,6 +286,18 @@ const char* vlsa_error_string(int code) {
     if (code == VLSA_EUNSUPPORTED) return "vlsa: unsupported configuration";
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "vlsa: unknown error";
+}
+
+size_t vlsa_split16_row_bytes(void) { return size_t(SplitCfg::ROW_BYTES); }
+
+int vlsa_split16_pack(const float* X, int64_t n_rows, void* image, int64_t first_row, void* stream) {
+    if (n_rows == 0) return 0;
+    if (!X || !image || n_rows < 0 || first_row < 0 || first_row % SplitCfg::TR) return VLSA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(X) & 15u) || (reinterpret_cast<uintptr_t>(image) & 15u)) return VLSA_EINVAL;
+    const long long records = (n_rows + SplitCfg::TR - 1) / SplitCfg::TR;
+    if (records > 0x7fffffffLL) return VLSA_EINVAL;
+    split16_pack_kernel<<<unsigned(records), 512, 0, static_cast<cudaStream_t>(stream)>>>(X, n_rows, static_cast<unsigned char*>(image), first_row);
+    return static_cast<int>(cudaGetLastError());
 }
 
 int vlsa_agg_plan(const int64_t* cu_rows_host, int B, int sm_count, int* chunk_rows_out, int32_t* chunk_start_host) {
@@ -422,6 +454,9 @@ int vlsa_agg_bwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
     } else if (kern == kAggBf16) {
         rc = launch_agg_bf16<true>(prm, P, total_rows, st);
         if (rc) return rc;
+    } else if (kern == kAggSplit) {
+        rc = launch_agg_split<true>(prm, P, st);
+        if (rc) return rc;
     } else {
         VLSA_DISPATCH_P(P, {
             if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_F32) rc = launch_agg<kP, 1, float>(prm, st);
@@ -488,6 +523,7 @@ int vlsa_agg_pooled_bwd(const void* X, int x_dtype, int64_t total_rows, const in
     if (q_prenorm != 0 && q_prenorm != 1) return VLSA_EINVAL;
     if (!dtype_ok(x_dtype)) return VLSA_EUNSUPPORTED;
     (void)total_rows;                                          // this pass runs on the CUDA-core kernel for every P
+    if ((x_dtype & VLSA_DTYPE_MASK) == VLSA_DTYPE_SPLIT16) return VLSA_EUNSUPPORTED;   // ... which reads plain rows
     if (total_chunks > 0 && !X) return VLSA_EINVAL;
     uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
     AggWorkspace ws = carve(reinterpret_cast<void*>(base), total_chunks, B, P);

@@ -161,7 +161,16 @@ def _build_plan(bag_sizes, device, sms: int | None) -> BagPlan:
     return BagPlan(cu, cs, int(chunk_rows.value), dev[: len(cu)], dev[len(cu):].view(torch.int32)[: len(cs)])
 
 
+SPLIT16_COLS = 514      # fp32 words per row of a pre-split tile image (vlsa_split16_row_bytes() / 4, include/vlsa_b200.h)
+
+
+def _is_split16(x: torch.Tensor) -> bool:
+    return x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == SPLIT16_COLS
+
+
 def _x_dtype_code(x: torch.Tensor) -> int:
+    if _is_split16(x):
+        return 2
     if x.dtype == torch.float32:
         return 0
     if x.dtype == torch.bfloat16:
@@ -196,6 +205,18 @@ def make_plan_ranges(begins, ends, x_rows: int, device, sms: int | None = None) 
                    ranges=True, x_rows=int(x_rows))
 
 
+def split16_pack(X: torch.Tensor, image: torch.Tensor, first_row: int) -> None:
+    """vlsa_split16_pack: rows of X [n, 512] fp32 (device) -> the records of `image` [rows_padded, 514] that start at padded
+    row `first_row` (a multiple of 16).  Current stream."""
+    _check_cuda(X, "X")
+    if X.dim() != 2 or X.shape[1] != D_FEAT or not _is_split16(image) or not image.is_cuda or not image.is_contiguous():
+        raise ValueError("split16_pack: X [n, 512] fp32 and image [rows, 514] fp32, both on the device")
+    n = X.shape[0]
+    if first_row % 16 or first_row + (n + 15) // 16 * 16 > image.shape[0]:
+        raise ValueError("split16_pack: first_row must be a multiple of 16 and the records must fit the image")
+    _lib.check(_lib.lib().vlsa_split16_pack(X.data_ptr(), n, image.data_ptr(), first_row, _stream()), "vlsa_split16_pack")
+
+
 def _workspace(plan: BagPlan, P: int, device) -> torch.Tensor:
     nbytes = _lib.lib().vlsa_agg_workspace_bytes(plan.total_chunks, plan.num_bags, P)
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -206,8 +227,10 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
     """Launch vlsa_agg_fwd.  Returns a dict of fresh output tensors (no autograd)."""
     L = _lib.lib()
     B, P, R = plan.num_bags, Q.shape[0], T.shape[0]
-    if X.dim() != 2 or X.shape[1] != D_FEAT:
+    if X.dim() != 2 or (X.shape[1] != D_FEAT and not _is_split16(X)):
         raise ValueError(f"packed X must be [total_rows, {D_FEAT}], got {tuple(X.shape)}")
+    if _is_split16(X) and not plan.ranges:
+        raise ValueError("a pre-split cohort image goes with a row-range plan (DeviceCohort.plan)")
     if X.shape[0] != plan.total_rows:
         raise ValueError(f"packed X has {X.shape[0]} rows but the plan covers {plan.total_rows}")
     if not (1 <= P <= MAX_P):
@@ -299,7 +322,7 @@ class _EncodeFn(torch.autograd.Function):
         L = _lib.lib()
         Qc, Wc, bc = (t.detach().contiguous() for t in (Q, W, bias))
         B, P = plan.num_bags, Qc.shape[0]
-        if X.dim() != 2 or X.shape[1] != D_FEAT or X.shape[0] != plan.total_rows:
+        if X.dim() != 2 or (X.shape[1] != D_FEAT and not _is_split16(X)) or X.shape[0] != plan.total_rows:
             raise ValueError(f"packed X must be [{plan.total_rows}, {D_FEAT}], got {tuple(X.shape)}")
         if not (1 <= P <= MAX_P):
             raise ValueError(f"num_query P={P} outside 1..{MAX_P}")
@@ -358,7 +381,7 @@ class _PooledFn(torch.autograd.Function):
     def forward(ctx, X, plan, Q, q_prenorm, scale):
         Qc = Q.detach().contiguous()
         B, P = plan.num_bags, Qc.shape[0]
-        if X.dim() != 2 or X.shape[1] != D_FEAT or X.shape[0] != plan.total_rows:
+        if X.dim() != 2 or (X.shape[1] != D_FEAT and not _is_split16(X)) or X.shape[0] != plan.total_rows:
             raise ValueError(f"packed X must be [{plan.total_rows}, {D_FEAT}], got {tuple(X.shape)}")
         if not (1 <= P <= MAX_P):
             raise ValueError(f"num_query P={P} outside 1..{MAX_P}")
