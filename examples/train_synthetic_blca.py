@@ -53,6 +53,9 @@ def main():
     ap.add_argument("--gated-query", action="store_true")
     ap.add_argument("--query-pooling", default="mean", choices=["mean", "max", "weight", "attention", "gated_attention"])
     ap.add_argument("--feat-proj", action="store_true")
+    ap.add_argument("--cohort", default="none", choices=["none", "rows", "split16"],
+                    help="keep every bag of this rank's shard resident in HBM after epoch 0 (DeviceCohort): 'rows' = fp32 rows, "
+                         "'split16' = pre-split tile records (the tensor-core kernel then converts nothing per epoch)")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -64,7 +67,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from vlsa_b200 import synth
-    from vlsa_b200.dataset import PatchFeatureStore, WSIPatchSurvStore, build_store
+    from vlsa_b200.dataset import PatchFeatureStore, WSIPatchSurvStore, build_store, DeviceCohort
     from vlsa_b200.model import VLSA
     from vlsa_b200.runner import VLSAHandler
 
@@ -120,16 +123,28 @@ def main():
     loader = OneBagLoader()
     bs = cfg["bp_every_batch"]
     sizes_all = [store.n_rows(pid2sids[p]) for p in pids]
+    cohort = None
+    if args.cohort != "none":
+        # static partition of the split: patient i lives on rank i % world (every epoch's steps then find their bags there)
+        mine_all = [i for i in range(len(pids)) if i % world == rank]
+        cap = sum((sizes_all[i] + 15) // 16 * 16 for i in mine_all)
+        cohort = DeviceCohort(dev, cap, layout=args.cohort)
     for epoch in range(args.epochs):
         torch.cuda.synchronize(); t0 = time.time()
         handler.net.train()
         losses = []
+        if cohort is not None and epoch == 0:
+            for i in mine_all:                               # the one upload of the run (epoch 0 pays the store reads and H2D)
+                cohort.add(i, ds[i][1][0])
         for s0 in range(0, len(pids), bs):                   # one optimizer step = 32 patients (vlsa_handler.py:260-289)
             ids = list(range(s0, min(s0 + bs, len(pids))))
             # lazy bags: a rank only reads the patients of its own shard from the store
             xs = [(lambda i=i: ds[i][1][0].unsqueeze(0)) for i in ids]
             ys = [torch.tensor(pid2label[pids[i]]).reshape(1, 2) for i in ids]
-            loss, _ = handler._update_network(xs, ys, sizes=[sizes_all[i] for i in ids])
+            if cohort is not None:
+                loss, _ = handler.update_network_cached(cohort, ids, ys)
+            else:
+                loss, _ = handler._update_network(xs, ys, sizes=[sizes_all[i] for i in ids])
             losses.append(loss)
         torch.cuda.synchronize(); dt = time.time() - t0
         pred = handler.test_model(handler.net, loader)["pred"]

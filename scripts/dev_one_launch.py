@@ -14,6 +14,12 @@ if os.environ.get('DEV_DTYPE') == 'bf16':
     X = X.to(torch.bfloat16)
 Q = (0.5 * pr["residual_features"] + pr["prompt_features"]).to(dev)
 plan = ops.make_plan([N] * B, dev)
+if os.environ.get('DEV_LAYOUT') == 'split16':
+    from vlsa_b200.dataset import DeviceCohort
+    cohort = DeviceCohort(dev, B * ((N + 15) // 16 * 16), layout="split16")
+    for b in range(B):
+        cohort.add(b, X[b * N:(b + 1) * N])
+    X, plan = cohort.X, cohort.plan(list(range(B)))
 ws = ops._workspace(plan, P, dev)
 ops.set_agg_variant(variant)
 for _ in range(4):
