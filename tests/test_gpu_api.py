@@ -452,3 +452,30 @@ def test_split16_cohort_is_bit_identical_to_the_fp32_tensor_core_kernel(P, dev):
         cohort.reserve("x", 10)
     with pytest.raises(ValueError):
         ops.aggregate(cohort.X, ops.make_plan([16], dev), Q.detach(), W.detach(), b.detach(), T.detach(), ls.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["rows", "split16"])
+def test_test_model_cached_matches_test_model(layout, dev):
+    """`VLSAHandler.test_model_cached` (bags drawn from a DeviceCohort by row-range plans) against `test_model` on a loader of
+    the same bags: identical raw predictions and incidence (P = 12: both run the tensor-core arithmetic)."""
+    from vlsa_b200 import synth
+    from vlsa_b200.dataset import DeviceCohort
+    from vlsa_b200.runner import VLSAHandler
+    P = 12
+    sizes = [700, 33, 1, 2049, 512, 90, 4000]
+    bags = [synth.make_bag("g1", n, 800 + i) for i, n in enumerate(sizes)]
+    pr = synth.make_params(P, P, 13)
+    net = build_net(pr, P, P, dev)
+    h = VLSAHandler(dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4), net, device=dev)
+    t, e = synth.make_labels(len(sizes), P, 3)
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(sizes))]
+    loader = [(torch.tensor([[i]]), (bags[i].unsqueeze(0), torch.zeros(1)), ys[i]) for i in range(len(sizes))]
+    ref = h.test_model(h.net, loader, "test", bags_per_launch=3)["pred"]
+    cohort = DeviceCohort(dev, sum((n + 15) // 16 * 16 for n in sizes), layout=layout)
+    for i, b in enumerate(bags):
+        cohort.add(i, b)
+    got = h.test_model_cached(h.net, cohort, list(range(len(sizes))), ys, bags_per_launch=3)["pred"]
+    for k in ("raw_y_hat", "y_hat", "y"):
+        assert torch.equal(ref[k], got[k]), k
+    assert got["uid"].tolist() == list(range(len(sizes)))

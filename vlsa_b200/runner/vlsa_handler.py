@@ -16,6 +16,7 @@ from __future__ import annotations
 import os
 from typing import Sequence
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -239,6 +240,24 @@ class VLSAHandler:
         flush()
         return {"pred": {"y": torch.cat(all_gt, 0), "raw_y_hat": torch.cat(all_raw, 0),
                          "y_hat": torch.cat(all_pred, 0), "uid": torch.cat(all_idx, 0)}}
+
+    @torch.no_grad()
+    def test_model_cached(self, model, cohort, keys: Sequence, labels: Sequence | None = None, bags_per_launch: int = 32):
+        """``test_model`` on bags that are resident in a ``DeviceCohort`` (keys = their cohort keys, in evaluation order): no
+        loader, no staging, no H2D of rows — every launch draws ``bags_per_launch`` bags by a row-range plan.  Same result
+        dict; ``labels[i]`` is the [2] / [1,2] label of ``keys[i]`` (``y`` is omitted when labels are not given)."""
+        model.eval()
+        T = model.forward_text_only()
+        raw, pred = [], []
+        for s0 in range(0, len(keys), bags_per_launch):
+            logits, _, _, inc = model.forward_packed(cohort.X, cohort.plan(list(keys[s0:s0 + bags_per_launch])), T)
+            raw.append(logits)
+            pred.append(inc)
+        out = {"raw_y_hat": torch.cat(raw, 0).cpu(), "y_hat": torch.cat(pred, 0).cpu(),
+               "uid": torch.as_tensor([int(k) if isinstance(k, (int, np.integer)) else i for i, k in enumerate(keys)])}
+        if labels is not None:
+            out["y"] = torch.cat([torch.as_tensor(y, dtype=torch.float32).reshape(1, 2) for y in labels], 0)
+        return {"pred": out}
 
     # ---- checkpoint (runner/base_handler.py:641-682) ---------------------------------------------------
     def save_model(self, path: str, epoch: int, module_filter: str | None = "prompt_encoder") -> None:
