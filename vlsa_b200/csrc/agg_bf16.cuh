@@ -30,16 +30,27 @@
 
 namespace vlsa {
 
+#ifndef VLSA_BF16_TR
+#define VLSA_BF16_TR 32          // rows per tile: 16 or 32
+#endif
+#ifndef VLSA_BF16_NSET
+#define VLSA_BF16_NSET (VLSA_BF16_TR == 16 ? 4 : 2)
+#endif
+
 struct Bf16Cfg {
     static constexpr int D = VLSA_D;
     static constexpr int NP = 16;
-    static constexpr int TR = 16;                 // rows per tile
+    static constexpr int TR = VLSA_BF16_TR;       // rows per tile
+    static constexpr int RPT = TR / 8;            // tile rows per weight thread
     static constexpr int NSLOT = 8;               // 64-feature slots
     static constexpr int GRP = 1024;              // bytes of one 8-row group of a slot (one swizzled atom)
-    static constexpr int SLOT = 2 * GRP;          // 2 KB
-    static constexpr int TILE = NSLOT * SLOT;     // 16 KB
-    static constexpr int NBUF = 8;
-    static constexpr int NSET = 4;                // sets of four weight warps; tile tt belongs to set tt % NSET
+    static constexpr int SLOT = (TR / 8) * GRP;   // 2 KB | 4 KB
+    static constexpr int TILE = NSLOT * SLOT;     // 16 KB | 32 KB
+#ifndef VLSA_BF16_NBUF
+#define VLSA_BF16_NBUF (VLSA_BF16_TR == 16 ? 8 : 6)
+#endif
+    static constexpr int NBUF = VLSA_BF16_NBUF;
+    static constexpr int NSET = VLSA_BF16_NSET;   // sets of four weight warps; tile tt belongs to set tt % NSET
     static constexpr int NSOFT = 4 * NSET, NCONV = 8;   // norm warps: two sets of four (tile tt: set tt & 1)
     // register budget (setmaxnreg, per warpgroup): the launch bound grants 72 to each of the 896 threads
     static constexpr int REG_SOFT = 80, REG_ISSUE = 24, REG_NORM = 80;
@@ -60,7 +71,11 @@ struct Bf16Cfg {
     static constexpr int D2W = 2 * NP;            // per 128-feature block: t0 (16 prototypes) | t1
     static constexpr int TM_D2 = 256;
     static constexpr int TM_D1 = TM_D2 + 4 * D2W;   // 384: NSET score buffers of 16 columns
-    static_assert(TM_D1 + NSET * TR <= 512 && NBUF % NSET == 0, "TMEM columns / ring");
+    // NBUF is a multiple of the number of norm-warp sets (2) and of NSET: a buffer is always served by the SAME set, whose warps
+    // take their tiles in order — with an odd ring a set could reach a buffer's next phase before the other set had seen the
+    // current one land, and an mbarrier parity wait that is a phase ahead returns at once (measured: an intermittent hang)
+    static_assert((TR == 16 || TR == 32) && TM_D1 + NSET * TR <= 512 && NBUF % NSET == 0 && NBUF % 2 == 0 && 4 % NSET == 0,
+                  "TMEM columns / ring");
     static constexpr int TMEM_COLS = 512;
     static constexpr float HEADROOM = 6.f, MARGIN = 10.f;
     static constexpr int BWD_MAXE = 14, BWD_SETE = 6;
@@ -97,6 +112,9 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for ptxas
 
+#ifdef VLSA_WD_DEBUG
+    if (tid == 0 && blockIdx.x == 0) g_wd[1] = smem_u32(bars);
+#endif
     if (tid == 0) {
         for (int s = 0; s < C::NBUF; ++s) { mbar_init(landed + s, 1); mbar_init(full + s, 4); mbar_init(empty + s, 1); }
         for (int s = 0; s < C::NSET; ++s) {
@@ -157,14 +175,15 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         // =========================================================================== row norms
         // Two sets of four warps take the tiles alternately (set = tile index & 1): the per-tile work is a latency chain
         // (mbarrier -> LDS -> FMA chain -> shuffles -> STS -> mbarrier) longer than the HBM time of a 16 KB tile.
-        // Warp cw4 of a set: tile rows 4 cw4 + 2 h (lanes 0-15) and 4 cw4 + 2 h + 1 (lanes 16-31), h = 0, 1.  A lane reads
-        // the 16-byte chunk at PHYSICAL position (lane & 7) ^ 2 h of its row in slots 2 it + ((lane >> 3) & 1), it = 0 .. 3:
-        // the eight lanes of a quarter warp cover one 128-byte swizzled row segment (conflict-free LDS.128), and the
-        // LOGICAL chunk = position ^ (row & 7) is the same for both h (rows 4 cw4 .. + 3 lie in one 8-row group and differ
-        // by 2 h in row & 7), so one set of dv registers serves both rows in the backward.
+        // Warp cw4 of a set: tile rows (TR / 4) cw4 + 2 h (lanes 0-15) and + 2 h + 1 (lanes 16-31), h = 0 .. TR / 8 - 1.  A lane
+        // reads the 16-byte chunk at PHYSICAL position (lane & 7) ^ 2 h of its row in slots 2 it + ((lane >> 3) & 1), it =
+        // 0 .. 3: the eight lanes of a quarter warp cover one 128-byte swizzled row segment (conflict-free LDS.128), and the
+        // LOGICAL chunk = position ^ (row & 7) is the same for every h (the rows of a warp lie in one 8-row group and differ
+        // by 2 h in row & 7), so one set of dv registers serves all of them in the backward.
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REG_NORM));
         const int cw = warp - C::W_CONV, nset = cw >> 2, cw4 = cw & 3;
-        const int row = 4 * cw4 + (lane >> 4), sub = (lane >> 3) & 1, pos = lane & 7;     // row of h = 0 (h = 1: + 2)
+        constexpr int NH = TR / 8;                                                 // row pairs of a warp per tile
+        const int row = (TR / 4) * cw4 + (lane >> 4), sub = (lane >> 3) & 1, pos = lane & 7;   // row of h = 0 (h: + 2 h)
         const int chunk = pos ^ (row & 7);
         const uint32_t ld_off = sub * C::SLOT + (row >> 3) * C::GRP + (row & 7) * 128;
         float dvr[BWD ? 32 : 1];                               // dv / P at this lane's 32 features (backward)
@@ -194,19 +213,17 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 PROF_BEGIN();
                 mbar_wait_wd(landed + b, ph);
                 PROF_END(0);
-                uint4 raw[2][4];
+                float ss[NH], uu[NH];
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < NH; ++h) {
+                    uint4 raw[4];
 #pragma unroll
                     for (int it = 0; it < 4; ++it)
-                        raw[h][it] = *reinterpret_cast<const uint4*>(tile + h * 256 + ((pos ^ (2 * h)) << 4) + 2 * it * C::SLOT);
-                float ss[2], uu[2];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                        raw[it] = *reinterpret_cast<const uint4*>(tile + h * 256 + ((pos ^ (2 * h)) << 4) + 2 * it * C::SLOT);
                     float2 a2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, u2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
-                        const uint32_t w4[4] = {raw[h][it].x, raw[h][it].y, raw[h][it].z, raw[h][it].w};
+                        const uint32_t w4[4] = {raw[it].x, raw[it].y, raw[it].z, raw[it].w};
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float2 xy = make_float2(bf16_lo(w4[k]), bf16_hi(w4[k]));
@@ -219,23 +236,25 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < NH; ++h) {
                         ss[h] += __shfl_xor_sync(0xffffffffu, ss[h], o);
                         if (BWD) uu[h] += __shfl_xor_sync(0xffffffffu, uu[h], o);
                     }
-                if ((lane & 7) == 0) {
-                    // lanes 0 / 16: rows of h = 0, lanes 8 / 24: rows of h = 1.  Row info: score = info.x (Qn . x), info.x =
-                    // scale / max(|x|, eps); info.y = 1 (no row scaling); info.z = dv . x / P (backward).
+                if ((lane & 15) < NH) {
+                    // lane h of each half warp writes the row of pair h.  Row info: score = info.x (Qn . x), info.x = scale /
+                    // max(|x|, eps); info.y = 1 (no row scaling); info.z = dv . x / P (backward).
                     // 1 / |x| = rsqrt + one Newton step.
-                    const int h = (lane >> 3) & 1;
-                    const float sq = h ? ss[1] : ss[0];
+                    const int h = lane & 15;
+                    float sq = ss[0], uq = uu[0];
+#pragma unroll
+                    for (int i = 1; i < NH; ++i) { sq = h == i ? ss[i] : sq; uq = h == i ? uu[i] : uq; }
                     float4 info;
                     float y = rsqrtf(sq);
                     y = y * fmaf(-0.5f * sq * y, y, 1.5f);
                     y = fminf(y, 1.f / VLSA_NORM_EPS);                         // also catches ss == 0 (NaN -> cap)
                     info.x = prm.scale * y;
                     info.y = 1.f;
-                    info.z = BWD ? (h ? uu[1] : uu[0]) : 0.f;
+                    info.z = BWD ? uq : 0.f;
                     info.w = 0.f;
                     *reinterpret_cast<float4*>(s_rowinfo + (b * TR + row + 2 * h) * 4) = info;
                 }
@@ -297,7 +316,7 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
 #pragma unroll
                     for (int s = 0; s < C::NSLOT; ++s) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)      // B = 16 rows: [g0 | g1] of the slot
+                        for (int ks = 0; ks < 4; ++ks)      // B = TR rows: the 8-row groups of the slot
                             tc_mma_ts(d1, tq0 + (s * 4 + ks) * 8, umma_desc_advance(tb, s * C::SLOT + ks * 32), idesc1,
                                       (s | ks) != 0);
                     }
@@ -338,7 +357,9 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     for (int gg = 0; gg < 4; ++gg) {
                         const uint32_t d2 = tmem + C::TM_D2 + gg * C::D2W;
                         const uint64_t ah = umma_desc_advance(tb, (2 * gg) * C::SLOT);
-                        tc_mma_ss(d2, ah, wb, idesc2, acc0);
+#pragma unroll
+                        for (int k2 = 0; k2 < TR / 16; ++k2)             // 16 tile rows per instruction: two 8-row groups
+                            tc_mma_ss(d2, umma_desc_advance(ah, k2 * 2 * C::GRP), umma_desc_advance(wb, k2 * 32), idesc2, k2 == 0 ? acc0 : 1u);
                     }
                     tc_commit(empty + b);
                     tc_commit(w_free + i);
@@ -364,8 +385,8 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         const bool pvalid = p < P;
         const uint32_t tq = tmem + (uint32_t(32 * q) << 16);
         constexpr int NT = C::NSOFT * 32, NTS = 128;
-        // B operand of GEMM2: row (term * 16 + p), K = tile row: rows 2 rj, 2 rj + 1 -> 16-byte chunk rj >> 2, bytes 4 (rj & 3)
-        const uint32_t w_off = sw128_offset(p, rj >> 2, 4 * (rj & 3));
+        // B operand of GEMM2: row (term * 16 + p), K = tile row: rows RPT rj .. + RPT - 1 -> 16-byte chunk (RPT rj) >> 3, bytes 2 ((RPT rj) & 7)
+        const uint32_t w_off = sw128_offset(p, (C::RPT * rj) >> 3, 2 * ((C::RPT * rj) & 7));
         uint32_t tt = 0, cc = 0;
         PROF_DECL
         for (int c = blockIdx.x; c < prm.total_chunks; c += gridDim.x, ++cc) {
@@ -397,36 +418,39 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 mbar_wait_wd(s_ready + set, v & 1u);
                 PROF_END(0);
                 tc_fence_after();
-                float sc2[2];
+                float sc2[C::RPT];
                 {
-                    // 16 partial scores of this lane's (prototype, term, range): tile rows 0 .. 15 (zeros in the two spare lanes)
-                    uint32_t sa[16];
-                    tmem_ld16(tq + C::TM_D1 + TR * set, sa);
+                    // TR partial scores of this lane's (prototype, term, range): the tile's rows (zeros in the two spare lanes)
+                    uint32_t sa[TR];
+                    if constexpr (TR == 32) tmem_ld32(tq + C::TM_D1 + TR * set, *reinterpret_cast<uint32_t(*)[32]>(sa));
+                    else tmem_ld16(tq + C::TM_D1 + TR * set, *reinterpret_cast<uint32_t(*)[16]>(sa));
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
                     mbar_arrive_if(s_free + set, lane == 0);
                     // the 6 (term, range) partial sums of a (row, prototype) (and two zeros) sit in the lanes that differ in bits 2-4: a
                     // transposed butterfly adds them in a fixed order and halves the rows a lane keeps at every level
-                    // (14 shuffles, no shared memory): lane bit 4 -> row bit 3, bit 3 -> row bit 2, bit 2 -> row bit 1
-                    float v8[8], v4[4];
+                    // (7 TR / 8 shuffles, no shared memory): lane bit 4 -> the top row bit, bit 3 -> the next, bit 2 -> the next; a
+                    // thread ends up with rows RPT (lane >> 2) .. + RPT - 1 of prototype lane & 3
+                    constexpr int H1 = TR / 2, H2 = TR / 4, H3 = TR / 8;
+                    float v1[H1], v2[H2];
                     const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float lo = __uint_as_float(sa[i]), hi = __uint_as_float(sa[8 + i]);
-                        v8[i] = (u16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, u16 ? lo : hi, 16);
+                    for (int i = 0; i < H1; ++i) {
+                        const float lo = __uint_as_float(sa[i]), hi = __uint_as_float(sa[H1 + i]);
+                        v1[i] = (u16 ? hi : lo) + __shfl_xor_sync(0xffffffffu, u16 ? lo : hi, 16);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) v4[i] = (u8 ? v8[4 + i] : v8[i]) + __shfl_xor_sync(0xffffffffu, u8 ? v8[i] : v8[4 + i], 8);
+                    for (int i = 0; i < H2; ++i) v2[i] = (u8 ? v1[H2 + i] : v1[i]) + __shfl_xor_sync(0xffffffffu, u8 ? v1[i] : v1[H2 + i], 8);
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) sc2[i] = (u4 ? v4[2 + i] : v4[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v4[i] : v4[2 + i], 4);
+                    for (int i = 0; i < H3; ++i) sc2[i] = (u4 ? v2[H3 + i] : v2[i]) + __shfl_xor_sync(0xffffffffu, u4 ? v2[i] : v2[H3 + i], 4);
                 }
                 PROF_BEGIN();
                 mbar_wait_wd(full + b, ph);                            // acquire the norm warps' row info
                 PROF_END(1);
-                float4 info[2];
+                float4 info[C::RPT];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + 2 * rj + k) * 4);
+                for (int k = 0; k < C::RPT; ++k) info[k] = *reinterpret_cast<const float4*>(s_rowinfo + (b * TR + C::RPT * rj + k) * 4);
                 // ---- in tile order from here: the other set has settled tile tt - 1
                 PROF_BEGIN();
                 if (tt > 0) mbar_wait_wd(decided + prev_set, ((tt - 1) / C::NSET) & 1u);
@@ -442,28 +466,34 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                         m_loc = m_sh;
                     }
                 }
-                float w[2];                                            // weights fed to GEMM2 (before the fp16 split)
-                float ts[2], unscale[2], cw[2];
+                float w[C::RPT];                                       // weights fed to GEMM2 (before the bf16 split)
+                float ts[C::RPT], unscale[C::RPT], cw[C::RPT];
                 bool grow;
                 if (!BWD) {
                     // ts = score + (e_row - E) ln 2: the weight is exp(ts - m) = A-weight x 2^(e_row - E)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < C::RPT; ++k) {
                         int de = int(__float_as_uint(info[k].y) >> 23) - exE;
                         de = de < -100 ? -100 : (de > 100 ? 100 : de);
-                        ts[k] = (2 * rj + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
+                        ts[k] = (C::RPT * rj + k < nvalid) ? fmaf(float(de), 0.693147180559945f, sc2[k] * info[k].x) : -INFINITY;
                         unscale[k] = __uint_as_float(uint32_t(127 - de) << 23);       // 2^-(e_row - E)
                     }
-                    grow = pvalid && (fmaxf(ts[0], ts[1]) > m_loc + C::MARGIN);        // true on the first tile
+                    float tmax = ts[0];
+#pragma unroll
+                    for (int k = 1; k < C::RPT; ++k) tmax = fmaxf(tmax, ts[k]);
+                    grow = pvalid && (tmax > m_loc + C::MARGIN);                       // true on the first tile
                 } else {
                     // c = scale A (u - delta) / |x| = A (u - delta) info.x 2^-e; the weight on x~ = 2^-e x is c 2^e
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
+                    for (int k = 0; k < C::RPT; ++k) {
                         const float a = expf(sc2[k] * info[k].x - bw_m) * bw_il;       // A_pn (deepmil.py:198)
-                        cw[k] = (pvalid && 2 * rj + k < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
+                        cw[k] = (pvalid && C::RPT * rj + k < nvalid) ? a * (info[k].z - bw_delta) * info[k].x : 0.f;
                     }
                     // binary exponent of the larger |cw| (zero / denormal -> very small, non-finite -> very large)
-                    int et = int((__float_as_uint(fmaxf(fabsf(cw[0]), fabsf(cw[1]))) >> 23) & 0xffu) - 127;
+                    float cmax = fabsf(cw[0]);
+#pragma unroll
+                    for (int k = 1; k < C::RPT; ++k) cmax = fmaxf(cmax, fabsf(cw[k]));
+                    int et = int((__float_as_uint(cmax) >> 23) & 0xffu) - 127;
                     et = et < -100 ? -100 : (et > 100 ? 100 : et);
                     ts[0] = float(et);
                     grow = pvalid && (t == 0 || ts[0] > m_loc + float(C::BWD_MAXE));
@@ -475,7 +505,11 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                     // rare (always on the first tile of a chunk): the warp settles the new reference of its four prototypes
                     // from all 16 rows; from the second tile on the TMEM accumulators are rescaled once GEMM2 of the
                     // previous tile has completed (every warp of the set needs every prototype's factor: s_alpha)
-                    float mt = BWD ? ts[0] : fmaxf(ts[0], ts[1]);
+                    float mt = ts[0];
+                    if (!BWD) {
+#pragma unroll
+                        for (int k = 1; k < C::RPT; ++k) mt = fmaxf(mt, ts[k]);
+                    }
                     mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 4));
                     mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 8));
                     mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 16));
@@ -512,20 +546,20 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 mbar_arrive_if(decided + set, lane == 0);             // releases s_mref / s_exE to the other set
                 if (!BWD) {
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        w[k] = (pvalid && 2 * rj + k < nvalid) ? expf(ts[k] - m_loc) : 0.f;
+                    for (int k = 0; k < C::RPT; ++k) {
+                        w[k] = (pvalid && C::RPT * rj + k < nvalid) ? expf(ts[k] - m_loc) : 0.f;
                         lsum = fmaf(w[k], unscale[k], lsum);
                     }
                 } else {
                     const float inv_h = pvalid ? __uint_as_float(uint32_t(127 - int(m_loc)) << 23) : 0.f;   // 1 / H_p
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) w[k] = cw[k] * inv_h;
+                    for (int k = 0; k < C::RPT; ++k) w[k] = cw[k] * inv_h;
                 }
                 // weights as two bf16 terms (w = t0 + t1, 16 significant bits; bf16 has the exponent range of fp32, no scaling);
                 // B operand row (term * 16 + p), K = tile row (2 rj, 2 rj + 1)
-                unsigned short b0[2], b1[2];
+                unsigned short b0[C::RPT], b1[C::RPT];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < C::RPT; ++k) {
                     const __nv_bfloat16 h0 = __float2bfloat16_rn(w[k]);
                     const __nv_bfloat16 h1 = __float2bfloat16_rn(w[k] - __bfloat162float(h0));
                     b0[k] = __bfloat16_as_ushort(h0); b1[k] = __bfloat16_as_ushort(h1);
@@ -533,10 +567,15 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
                 PROF_BEGIN();
                 mbar_wait_wd(w_free + set, (v & 1u) ^ 1u);             // GEMM2 of tile tt - 2 has read this buffer
                 PROF_END(4);
-                // tile rows 2 rj, 2 rj + 1 are neighbours along K: one 32-bit store per term
+                // the thread's RPT tile rows are neighbours along K: one 4- or 8-byte store per term
                 unsigned char* wb = wt + set * C::WBUF + w_off;
-                *reinterpret_cast<uint32_t*>(wb) = uint32_t(b0[0]) | (uint32_t(b0[1]) << 16);
-                *reinterpret_cast<uint32_t*>(wb + NP * 128) = uint32_t(b1[0]) | (uint32_t(b1[1]) << 16);
+                if constexpr (C::RPT == 4) {
+                    *reinterpret_cast<uint2*>(wb) = make_uint2(uint32_t(b0[0]) | (uint32_t(b0[1]) << 16), uint32_t(b0[2]) | (uint32_t(b0[3]) << 16));
+                    *reinterpret_cast<uint2*>(wb + NP * 128) = make_uint2(uint32_t(b1[0]) | (uint32_t(b1[1]) << 16), uint32_t(b1[2]) | (uint32_t(b1[3]) << 16));
+                } else {
+                    *reinterpret_cast<uint32_t*>(wb) = uint32_t(b0[0]) | (uint32_t(b0[1]) << 16);
+                    *reinterpret_cast<uint32_t*>(wb + NP * 128) = uint32_t(b1[0]) | (uint32_t(b1[1]) << 16);
+                }
                 __syncwarp();                                          // (the GEMM2 issuer fences for the async proxy)
                 mbar_arrive_if(w_ready + set, lane == 0);
             }

@@ -279,6 +279,14 @@ int vlsa_debug_read_prof(long long* out_host) {          // development builds o
 }
 #endif
 
+#ifdef VLSA_WD_DEBUG
+int vlsa_debug_read_wd(unsigned int* out_host, int reset) {          // development builds only
+    int rc = static_cast<int>(cudaMemcpyFromSymbol(out_host, vlsa::g_wd, sizeof(unsigned int) * (4 + 4 * 1000)));
+    if (rc == 0 && reset) { static unsigned int zero[4 + 4 * 1000]; rc = static_cast<int>(cudaMemcpyToSymbol(vlsa::g_wd, zero, sizeof(zero))); }
+    return rc;
+}
+#endif
+
 const char* vlsa_error_string(int code) {
     if (code == 0) return "success";
     if (code == VLSA_EINVAL) return "vlsa: invalid argument";

@@ -142,6 +142,27 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 // Fast path first: one try_wait (it sleeps in hardware up to its suspend hint) decides almost every wait.  The watchdog
 // loop stays INLINE: moving it into a __noinline__ function made the backward of the TMA-fed tcgen05 kernel of round 2 fault intermittently
 // (illegal address, only without compute-sanitizer) — a call from single-elected-lane / tcgen05 code is not worth it.
+#ifdef VLSA_WD_DEBUG
+// Development build: a wait that times out (~50 ms) records (line, block, thread, barrier address | parity) and RETURNS, so the
+// kernel ends (with garbage) and the host can read who was stuck where (vlsa_debug_read_wd)
+__device__ unsigned int g_wd[4 + 4 * 1000];
+__device__ __forceinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+    if (mbar_try_wait_hint(bar, parity, 4000u)) return;
+    uint32_t spins = 0;
+    do {
+        if (++spins > (1u << 14)) {
+            const unsigned am = __activemask();
+            const unsigned slot = (threadIdx.x & 31u) == unsigned(__ffs(am) - 1) ? atomicAdd(&g_wd[0], 1u) : 1000u;
+            if (slot < 1000u) {
+                g_wd[4 + 4 * slot] = unsigned(line); g_wd[5 + 4 * slot] = blockIdx.x; g_wd[6 + 4 * slot] = threadIdx.x;
+                g_wd[7 + 4 * slot] = (smem_u32(bar) << 1) | parity;
+            }
+            return;
+        }
+    } while (!mbar_try_wait_hint(bar, parity, 4000u));
+}
+#define mbar_wait_wd(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_hint(bar, parity, 4000u)) return;
     uint32_t spins = 0;
@@ -151,6 +172,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 22)) { asm volatile("brkpt;"); spins = 0; }
     } while (!mbar_try_wait_hint(bar, parity, 4000u));
 }
+#endif
 
 // x = hi + lo with hi, lo bf16 (16 significant bits in total); packs (a, b) -> bf16x2 with a in the low half
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
