@@ -327,18 +327,13 @@ def measure_shape(P, R, batches, plans, dev, timer, steps, world, rank, peak, es
         net.train()
         handler = VLSAHandler(cfg, net=net, device=dev)
         t_lab, e_lab = synth.make_labels(nb, R, labels_seed + rank)
-        label = torch.stack([t_lab, e_lab], 1).to(dev)
+        label = handler._labels(torch.stack([t_lab, e_lab], 1))
         n_global = nb * world
 
         def train_step(i):
-            handler.bucket.zero()
-            logits, _, _, _ = handler.net.forward_packed(batches[i % len(batches)], plans[i % len(plans)])
-            loss = handler.calc_objective_loss(logits, label, norm=n_global)
-            loss.backward()
-            handler.bucket.pack(loss.detach().reshape(1))
-            handler.bucket.all_reduce()
-            handler.bucket.unpack()
-            handler.optimizer.step()
+            # the handler's own step on packed device-resident bags (public API): forward + loss + backward, the flat-bucket
+            # all-reduce, Adam; no host synchronisation inside (the epoch loop of the handler runs it the same way)
+            handler.step_packed(batches[i % len(batches)], plans[i % len(plans)], label, n_global)
 
         ms_t = timer(train_step, max(3, min(steps, 30)), warmup=5)
         rec["train_step"] = {"value": nb * world / (ms_t * 1e-3), "unit": "WSI/s", "ms_per_step": ms_t,

@@ -141,12 +141,14 @@ def main():
             # lazy bags: a rank only reads the patients of its own shard from the store
             xs = [(lambda i=i: ds[i][1][0].unsqueeze(0)) for i in ids]
             ys = [torch.tensor(pid2label[pids[i]]).reshape(1, 2) for i in ids]
+            # sync=False: loss and predictions stay on the device, the epoch reads them back once (as _train_each_epoch does)
             if cohort is not None:
-                loss, _ = handler.update_network_cached(cohort, ids, ys)
+                loss, _ = handler.update_network_cached(cohort, ids, ys, sync=False)
             else:
-                loss, _ = handler._update_network(xs, ys, sizes=[sizes_all[i] for i in ids])
+                loss, _ = handler._update_network(xs, ys, sizes=[sizes_all[i] for i in ids], sync=False)
             losses.append(loss)
         torch.cuda.synchronize(); dt = time.time() - t0
+        losses = [float(l) for l in losses]
         pred = handler.test_model(handler.net, loader)["pred"]
         inc = pred["y_hat"].numpy()                                            # incidence function [n, R]
         score = (inc * np.arange(R)[None, :]).sum(1)                           # expected time bin: low = high risk

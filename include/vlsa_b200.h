@@ -208,6 +208,20 @@ int vlsa_feat_pool_fwd(const void* X, int x_dtype, int64_t N, int mode, const fl
  * out [N,512] fp32. */
 int vlsa_row_normalize(const void* X, int x_dtype, int64_t N, float* out, void* stream);
 
+/* One Adam step over the S trainable tensors of the path in one launch — `self.optimizer.step()` of the reference's
+ * `_update_network` (runner/vlsa_handler.py:283) with the optimizer optim/optim_factory.py:25-37 builds for
+ * cfg_vlsa_conch.yaml:111-118: torch.optim.Adam semantics (L2 weight decay added to the gradient, bias-corrected moments,
+ * eps added to sqrt(v_hat)), amsgrad off.  Gradients and both moments are flat fp32 buffers of one layout (the all-reduce
+ * bucket); `segments` is a DEVICE array of S records of vlsa_adam_segment_bytes() bytes:
+ *     { float* param; int64 offset (floats, into the flat buffers); int64 n; float weight_decay; float lr; }
+ * `step_count` [S] (device, float) holds the steps each tensor has taken and is incremented here; `flags` [S] (device, may be
+ * NULL): a tensor whose flag is 0 received no gradient this step and is skipped — moments, count and decay untouched, as
+ * torch.optim.Adam skips `grad is None` — decided on the device, so an optimizer step needs no device -> host read.
+ * max_n = the largest n of the segments. */
+size_t vlsa_adam_segment_bytes(void);
+int vlsa_adam_step(const void* segments, int S, int64_t max_n, const float* grads_flat, float* exp_avg, float* exp_avg_sq,
+                   float* step_count, const float* flags, float beta1, float beta2, float eps, void* stream);
+
 /* Whole path with HOST buffers (what a caller holding CPU tensors — the reference's DataLoader output,
  * dataset/PatchWSI.py:197-215 + runner/vlsa_handler.py:205,322-330 — would call): stage the packed bags
  * X_host [total_rows, D] (pinned memory for a truly asynchronous copy) to the device on `stream_copy`,

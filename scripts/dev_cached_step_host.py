@@ -11,6 +11,7 @@ from vlsa_b200.runner import VLSAHandler
 dev = torch.device("cuda:0")
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 layout = sys.argv[2] if len(sys.argv) > 2 else "split16"
+sync = (sys.argv[3] == "sync") if len(sys.argv) > 3 else False
 n_pat, bs = 128, 32
 sizes = np.exp(np.random.default_rng(0).uniform(np.log(1000), np.log(20000), n_pat)).astype(int)
 cohort = DeviceCohort(dev, int(sum((n + 15) // 16 * 16 for n in sizes)), layout=layout)
@@ -27,7 +28,7 @@ def epoch():
     order = rng.permutation(n_pat).tolist()
     for s0 in range(0, n_pat, bs):
         ids = order[s0:s0 + bs]
-        handler.update_network_cached(cohort, ids, [ys_all[i] for i in ids])
+        handler.update_network_cached(cohort, ids, [ys_all[i] for i in ids], sync=sync)
 
 
 for _ in range(3): epoch()
@@ -35,7 +36,14 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(10): epoch()
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print(f"P={P} {layout}: {1e3 * dt / (10 * n_pat / bs):.3f} ms per optimizer step (32 bags, mean {sizes.mean():.0f} rows), {10 * n_pat / dt:.0f} bags/s")
+# GPU time of the same steps: everything queued behind a long-running spin so that the host is far ahead
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda._sleep(int(2e9 * 0.05))
+e0.record()
+for _ in range(2): epoch()
+e1.record(); torch.cuda.synchronize()
+print(f"GPU time per step when the host is ahead: {e0.elapsed_time(e1) / (2 * n_pat / bs):.3f} ms")
 pr = cProfile.Profile(); pr.enable()
 for _ in range(10): epoch()
 torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(32)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)

@@ -151,11 +151,9 @@ def test_handler_update_network_and_test_model(name, dev):
     np.testing.assert_allclose(preds.numpy(), case["logits_f64"], atol=2e-4, rtol=1e-5)
     # the reduced gradient bucket holds what the reference's autograd produced
     named = [(n, p) for n, p in h.net.named_parameters() if p.requires_grad]
-    at = 0
     got = {}
-    for (n, p), sz in zip(named, h.bucket.sizes):
+    for (n, p), sz, at in zip(named, h.bucket.sizes, h.bucket.offsets):
         got[n] = h.bucket.flat[at:at + sz].view_as(p).cpu().numpy()
-        at += sz
     for key, ref in (("mil_encoder.Q.residual_features", case["d_residual_f64"]),
                      ("mil_encoder.visual_adapter.bias", case["d_b_f64"]), ("logit_scale", case["d_logit_scale_f64"])):
         assert np.abs(got[key] - ref).max() <= max(2e-4 * np.abs(ref).max(), 1e-7), key
@@ -479,3 +477,132 @@ def test_test_model_cached_matches_test_model(layout, dev):
     for k in ("raw_y_hat", "y_hat", "y"):
         assert torch.equal(ref[k], got[k]), k
     assert got["uid"].tolist() == list(range(len(sizes)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,gated", [(4, False), (12, False), (7, True)])
+def test_fused_train_step_equals_the_autograd_step(P, gated, dev):
+    """`ops.FusedTrainStep` (three C calls on persistent buffers, gradients written into the bucket, losses into its tail, no
+    host synchronisation) against the autograd path of the same handler: the SAME kernels run in the same order, so losses,
+    predictions and the weights after two optimizer steps must be bit-identical — for fp32 rows on both dispatches (P = 4:
+    CUDA cores, P = 12: tcgen05), for the gated query (difference rows, no normalisation), from a split16 cohort, with a
+    trainable text tensor, and through `step_packed` / `sync=False`."""
+    from vlsa_b200 import ops, synth
+    from vlsa_b200.dataset import DeviceCohort
+    from vlsa_b200.model import VLSA
+    from vlsa_b200.runner import VLSAHandler
+    sizes = [1000, 37, 2798, 1, 513, 64, 4096, 255]
+    bags = [synth.make_bag("g1", n, 300 + i) for i, n in enumerate(sizes)]
+    pr = synth.make_params(P, P, 20 + P)
+    cfg = dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4,
+               loss_survifmle_weight=0.7, loss_survemd_weight=1.3)
+    t, e = synth.make_labels(len(sizes), P, 5)
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(sizes))]
+    xs = [b.unsqueeze(0).to(dev) for b in bags]
+
+    def make(fused, train_text):
+        torch.manual_seed(1234)                      # the gate's residual row is drawn at construction
+        if gated:
+            img = dict(name="VLFAN", dim_in=512, use_feat_proj=False, query="Text", num_query=P, gated_query=True,
+                       query_text_method="TaskRes")
+            g = torch.Generator().manual_seed(9)
+            net = VLSA({"name": "mahmoodlab/conch"}, img, {"name": "CoOp"}, text_features=pr["text_features"],
+                       query_prompt_features=pr["prompt_features"], query_neg_prompt_features=torch.randn(1, 512, generator=g),
+                       logit_scale_init=float(pr["logit_scale"])).to(dev)
+        else:
+            net = build_net(pr, P, P, dev)
+        if train_text:
+            net = net.to(dev)
+            del net.pretrained_text_features
+            net._text_param = torch.nn.Parameter(pr["text_features"].clone().to(dev))
+            net._text_fn = lambda: net._text_param
+        h = VLSAHandler(dict(cfg, vlsa_fused_step=fused), net, device=dev)
+        assert h._fused_ok() == fused
+        return h
+
+    for train_text in (False, True):
+        ha, hb = make(True, train_text), make(False, train_text)
+        for step in range(2):
+            la, pa = ha._update_network(xs, ys)
+            lb, pb = hb._update_network(xs, ys)
+            assert la == lb and torch.equal(pa, pb), (step, la, lb)
+        for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
+            assert torch.equal(va, vb), k
+        if train_text:
+            assert torch.equal(ha.net._text_param, hb.net._text_param)
+            assert not torch.equal(ha.net._text_param, pr["text_features"].to(dev))
+        # no-sync entry points: device tensors back, same numbers; component losses ride the bucket tail
+        X = torch.cat(bags, 0).to(dev)
+        plan = ops.make_plan(sizes, dev)
+        lab = torch.cat(ys, 0)
+        l1, p1 = ha.step_packed(X, plan, lab)
+        l2, p2 = hb._update_network(xs, ys, sync=False)
+        assert l1.is_cuda and p1.is_cuda and float(l1) == float(l2) and torch.equal(p1, p2)
+        tail = ha.bucket.tail.cpu()
+        assert abs(float(tail[0]) - (0.7 * float(tail[1]) + 1.3 * float(tail[2]))) <= 1e-5 * abs(float(tail[0]))
+    # from a split16 cohort
+    if not gated:
+        cohort = DeviceCohort(dev, sum((n + 15) // 16 * 16 for n in sizes), layout="split16")
+        for i, b in enumerate(bags):
+            cohort.add(i, b)
+        ha, hb = make(True, False), make(False, False)
+        order = [6, 1, 3, 0, 7, 2]
+        la, pa = ha.update_network_cached(cohort, order, [ys[i] for i in order])
+        lb, pb = hb.update_network_cached(cohort, order, [ys[i] for i in order])
+        assert la == lb and torch.equal(pa, pb)
+        for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
+            assert torch.equal(va, vb), k
+
+
+@pytest.mark.gpu
+def test_bucket_adam_follows_torch_adam(dev):
+    """`BucketAdam` (one launch over the flat gradient bucket, untouched parameters skipped on the device) against
+    torch.optim.Adam on the same gradients: decay / no-decay groups, a 0-dim parameter, sizes that are no multiple of four, a
+    parameter without a gradient in some steps (torch: grad None -> no update, no step count), and checkpoints that load
+    into each other."""
+    from vlsa_b200.runner.dist import FlatBucket
+    from vlsa_b200.runner.optim import BucketAdam
+    torch.manual_seed(3)
+    shapes = [(), (513,), (37, 19), (512, 512), (5,)]
+
+    def make():
+        torch.manual_seed(11)
+        return [torch.nn.Parameter(torch.randn(s, device=dev)) for s in shapes]
+    pa, pb = make(), make()
+    groups = lambda ps: [{"params": [ps[1], ps[4]], "weight_decay": 0.0}, {"params": [ps[0], ps[2], ps[3]], "weight_decay": 1e-2}]
+    ref = torch.optim.Adam(groups(pa), lr=3e-3)
+    bk = FlatBucket(pb, extra=3, align=4)
+    bk.attach()
+    opt = BucketAdam(groups(pb), bk, lr=3e-3)
+
+    def one_step(step):
+        bk.zero()
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 2 and step % 2 == 1:            # no gradient for this tensor on odd steps
+                a.grad = None
+                continue
+            g = torch.randn_like(a) * (0.1 + step)
+            a.grad = g.clone()
+            b.grad.copy_(g)
+            bk.mark_touched(b)
+        bk.pack(None)
+        bk.all_reduce()
+        opt.step()
+        ref.step()
+
+    for step in range(6):
+        one_step(step)
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-7)
+    sd = opt.state_dict()
+    assert float(sd["state"][2]["step"]) == 6 and float(sd["state"][3]["step"]) == 3      # torch numbering: group by group
+    assert float(ref.state_dict()["state"][3]["step"]) == 3
+    # checkpoints interchange: each continues from the other's state
+    ref2 = torch.optim.Adam(groups(pa), lr=3e-3)
+    ref2.load_state_dict(sd)
+    opt.load_state_dict(ref.state_dict())
+    ref = ref2
+    for step in range(6, 9):
+        one_step(step)
+    for a, b in zip(pa, pb):
+        torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-7)

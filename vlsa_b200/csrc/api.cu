@@ -15,6 +15,7 @@
 #include "head_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "aux_kernels.cuh"
+#include "optim_kernels.cuh"
 
 using namespace vlsa;
 
@@ -278,6 +279,21 @@ int vlsa_debug_read_prof(long long* out_host) {          // development builds o
     return static_cast<int>(cudaMemcpyFromSymbol(out_host, vlsa::g_tma_prof, sizeof(long long) * 32));
 }
 #endif
+
+size_t vlsa_adam_segment_bytes(void) { return sizeof(AdamSeg); }
+
+int vlsa_adam_step(const void* segments, int S, int64_t max_n, const float* grads_flat, float* exp_avg, float* exp_avg_sq,
+                   float* step_count, const float* flags, float beta1, float beta2, float eps, void* stream) {
+    if (S < 0 || max_n < 0 || !segments || !grads_flat || !exp_avg || !exp_avg_sq || !step_count) return VLSA_EINVAL;
+    if (S == 0 || max_n == 0) return 0;
+    if (S > 65535) return VLSA_EUNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid(unsigned((max_n + 1023) / 1024), unsigned(S));
+    adam_step_kernel<<<grid, 256, 0, st>>>(static_cast<const AdamSeg*>(segments), grads_flat, exp_avg, exp_avg_sq, step_count,
+                                           flags, beta1, beta2, eps);
+    adam_count_kernel<<<(S + 127) / 128, 128, 0, st>>>(step_count, flags, S);
+    return static_cast<int>(cudaGetLastError());
+}
 
 #ifdef VLSA_WD_DEBUG
 int vlsa_debug_read_wd(unsigned int* out_host, int reset) {          // development builds only

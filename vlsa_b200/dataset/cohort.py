@@ -18,6 +18,7 @@ from __future__ import annotations
 
 from typing import Hashable, Iterable, Sequence
 
+import numpy as np
 import torch
 
 from .. import ops
@@ -87,8 +88,8 @@ class DeviceCohort:
     def plan(self, keys: Sequence[Hashable]) -> "ops.BagPlan":
         """Row-range plan of the step made of the bags ``keys`` (any order, repeats allowed).  Use it with ``self.X``:
         ``net.forward_packed(cohort.X, cohort.plan(keys))``."""
-        spans = [self.index[k] for k in keys]
-        return ops.make_plan_ranges([s[0] for s in spans], [s[1] for s in spans], self.X.shape[0], self.device)
+        spans = np.array([self.index[k] for k in keys], dtype=np.int64).reshape(-1, 2)
+        return ops.make_plan_ranges(spans[:, 0], spans[:, 1], self.X.shape[0], self.device)
 
     @property
     def nbytes(self) -> int:

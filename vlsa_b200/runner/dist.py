@@ -52,14 +52,21 @@ class FlatBucket:
     it, `zero()` clears all gradients with one memset, and pack / unpack copy nothing (a step on small bags is
     launch-bound: this removes a dozen tiny kernels per step)."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 1):
+    def __init__(self, params: Iterable[torch.nn.Parameter], extra: int = 1, align: int = 1):
         self.params = [p for p in params if p.requires_grad]
         self.sizes = [p.numel() for p in self.params]
         self.extra = extra
+        # `align` (in floats): every segment starts at a multiple of it, so that kernels may write gradients straight into the
+        # attached views with 128-bit stores (the handler asks for 4); the padding floats stay zero and ride the all-reduce
+        self.offsets, at = [], 0
+        for n in self.sizes:
+            self.offsets.append(at)
+            at += -(-n // align) * align
+        self._grad_floats = at
         # tail = `extra` caller scalars, then one "received a gradient this step" flag per parameter (summed over the
         # ranks by the same all-reduce): a parameter nobody touched keeps grad = None for the optimizer, as after the
         # reference's zero_grad(set_to_none) — Adam must not decay its moments or apply weight decay to it
-        total = sum(self.sizes) + extra + len(self.params)
+        total = self._grad_floats + extra + len(self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self._touched = [False] * len(self.params)
@@ -67,6 +74,8 @@ class FlatBucket:
         self._flag_stage = torch.zeros(len(self.params), dtype=torch.float32)
         if dev.type == "cuda":
             self._flag_stage = self._flag_stage.pin_memory()
+        self._flag_cache: dict[tuple, torch.Tensor] = {}     # touched pattern -> its flags on the device (attached buckets)
+        self._index = {id(p): i for i, p in enumerate(self.params)}
 
     @property
     def tail(self) -> torch.Tensor:
@@ -79,10 +88,20 @@ class FlatBucket:
         return self.flat[len(self.flat) - len(self.params):]
 
     def _views(self):
-        at = 0
-        for p, n in zip(self.params, self.sizes):
+        for p, n, at in zip(self.params, self.sizes, self.offsets):
             yield p, self.flat[at:at + n]
-            at += n
+
+    def mark_touched(self, *params: torch.nn.Parameter) -> None:
+        """A kernel wrote this step's gradient of `params` straight into their attached views (no autograd hook fired)."""
+        for p in params:
+            i = self._index.get(id(p))
+            if i is not None:
+                self._touched[i] = True
+
+    def attached(self) -> bool:
+        """True when every parameter's .grad is (still) its view of the bucket."""
+        return bool(self._hooks) and all(p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * at
+                                         for p, at in zip(self.params, self.offsets))
 
     def attach(self) -> None:
         """Make every parameter's .grad a view of the bucket (keeps the current gradient values, if any)."""
@@ -99,11 +118,11 @@ class FlatBucket:
         """Zero all gradients.  Attached: one memset of the bucket (parameters detached by `drop_untouched` are
         re-attached); otherwise `grad = None` like zero_grad()."""
         self._touched = [False] * len(self.params)
-        if self._hooks:
+        if self._hooks and not self.attached():
             for p, seg in self._views():
                 if p.grad is None or p.grad.data_ptr() != seg.data_ptr():
                     p.grad = seg.view_as(p)
-        if all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views()):
+        if self.attached() or (not self._hooks and all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views())):
             self.flat.zero_()
         else:
             for p in self.params:
@@ -119,7 +138,25 @@ class FlatBucket:
                 n += 1
         return n
 
-    def pack(self, extra_values: torch.Tensor | None = None) -> None:
+    def pack(self, extra_values: torch.Tensor | None = None, extra_in_place: bool = False) -> None:
+        """`extra_in_place`: the caller's scalars were already written into `tail` (by a kernel)."""
+        if self._hooks and self.attached():
+            # gradients already live here; the flags of a touched pattern are uploaded once and copied on the device after that
+            if self.extra and not extra_in_place:
+                if extra_values is None:
+                    self.tail.zero_()
+                else:
+                    vals = extra_values.reshape(-1).to(self.flat.dtype)
+                    self.tail.zero_() if vals.numel() < self.extra else None
+                    self.tail[: vals.numel()].copy_(vals)
+            if self.params:
+                key = tuple(self._touched)
+                dev_flags = self._flag_cache.get(key)
+                if dev_flags is None:
+                    dev_flags = torch.tensor(key, dtype=torch.float32).to(self.flat.device)
+                    self._flag_cache[key] = dev_flags
+                self.flags.copy_(dev_flags, non_blocking=True)
+            return
         for p, seg in self._views():
             if p.grad is None:
                 seg.zero_()
@@ -129,7 +166,9 @@ class FlatBucket:
             if extra_values is None:
                 self.tail.zero_()
             else:
-                self.tail.copy_(extra_values.reshape(-1).to(self.flat.dtype))
+                vals = extra_values.reshape(-1).to(self.flat.dtype)
+                self.tail.zero_() if vals.numel() < self.extra else None
+                self.tail[: vals.numel()].copy_(vals)
         if self.params:
             if self._hooks:
                 self._flag_stage.copy_(torch.tensor(self._touched, dtype=torch.float32))
@@ -142,6 +181,8 @@ class FlatBucket:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
     def unpack(self) -> None:
+        if self._hooks and self.attached():
+            return
         for p, seg in self._views():
             g = seg.view_as(p)
             if p.grad is None:

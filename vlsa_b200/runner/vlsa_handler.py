@@ -23,8 +23,9 @@ import torch.nn.functional as F
 from .. import ops
 from ..dataset.loader import pack_bags
 from ..loss import SurvObjective
-from ..model import VLSA
+from ..model import VLSA, PromptAdapter, deepmil
 from . import dist as vdist
+from .optim import BucketAdam
 
 
 def fetch_kws(d: dict, prefix: str = "") -> dict:
@@ -98,13 +99,22 @@ class VLSAHandler:
                                        eps=float(cfg.get("loss_survifmle_eps", 1e-7)))
         self.output_converter = create_output_converter(cfg.get("net_output_converter", "softmax"))
         assert cfg.get("opt_name", "adam") == "adam", "only Adam is wired (cfg_vlsa_conch.yaml:111)"
-        self.optimizer = torch.optim.Adam(param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5))),
-                                          lr=float(cfg.get("opt_lr", 2e-4)), fused=self.device.type == "cuda")
         self.rank, self.world_size = vdist.world()
         vdist.broadcast_module(self.net)          # identical replicas before the first step
         self.balance_shards = balance_shards
-        self.bucket = vdist.FlatBucket(self.net.parameters(), extra=1)
+        # tail = (total, ifmle, emd): the loss kernel of the fused step writes its three values there; segments 16-byte aligned
+        # so that the backward kernels write W / bias / logit_scale gradients straight into the bucket
+        self.bucket = vdist.FlatBucket(self.net.parameters(), extra=3, align=4)
         self.bucket.attach()                      # gradients live in the all-reduce bucket: no pack / unpack copies
+        groups = param_groups_weight_decay(self.net, float(cfg.get("opt_weight_decay", 1e-5)))
+        if self.device.type == "cuda" and cfg.get("vlsa_bucket_adam", True):
+            # one launch over the bucket, untouched parameters skipped on the device (runner/optim.py)
+            self.optimizer = BucketAdam(groups, self.bucket, lr=float(cfg.get("opt_lr", 2e-4)))
+        else:
+            self.optimizer = torch.optim.Adam(groups, lr=float(cfg.get("opt_lr", 2e-4)), fused=self.device.type == "cuda")
+        self.fused_step = bool(cfg.get("vlsa_fused_step", True))
+        self._fused = ops.FusedTrainStep()
+        self._flags_known = None                  # (this rank's touched pattern, reduced flags) of the last synchronous step
 
     # ------------------------------------------------------------------------------------------------
     def calc_objective_loss(self, raw_pred, label, norm: int | None = None):
@@ -136,23 +146,55 @@ class VLSAHandler:
             X = torch.empty(0, ops.D_FEAT, device=self.device)
         return X, ops.make_plan(sizes, self.device)
 
-    def _update_network(self, xs, ys, sizes: Sequence[int] | None = None):
+    def _labels(self, ys, mine: Sequence[int] | None = None) -> torch.Tensor:
+        """Labels of this rank's bags as [2, B_local] int64 on the device: row 0 = time bin, row 1 = event indicator
+        (selected and converted where the labels live: one small copy)."""
+        if isinstance(ys, torch.Tensor):
+            lab = ys.reshape(-1, 2)
+            if mine is not None and len(mine) != lab.shape[0]:
+                lab = lab[torch.as_tensor(list(mine), device=lab.device, dtype=torch.long)]
+        else:
+            picked = ys if mine is None or len(mine) == len(ys) else [ys[i] for i in mine]
+            lab = torch.cat(list(picked), dim=0).reshape(-1, 2) if len(picked) else torch.zeros(0, 2)
+        if lab.is_cuda or self.device.type != "cuda":
+            return lab.t().to(torch.int64).contiguous().to(self.device, non_blocking=True)
+        # host labels: through the pinned ring (a copy from pageable memory would synchronise the stream)
+        host = lab.t().to(torch.int64).contiguous().numpy()
+        n = host.shape[1]
+        return ops.upload_small(lambda st: st.__setitem__(slice(None), host.reshape(-1)), 2 * n, self.device).view(2, n)
+
+    def step_packed(self, X: torch.Tensor, plan: "ops.BagPlan", labels: torch.Tensor, n_sample: int | None = None):
+        """One optimizer step on this rank's bags, already packed on the device (`X`, `plan`), with their labels [B, 2] (or the
+        [2, B] int64 of `_labels`); `n_sample` = bags of the step over ALL ranks (default: this rank's).  No host
+        synchronisation: returns (loss, raw predictions of the local bags) as device tensors."""
+        B = plan.num_bags
+        if not (labels.dtype == torch.int64 and labels.dim() == 2 and labels.shape[0] == 2 and labels.is_cuda):
+            labels = self._labels(labels)
+        mine = list(range(B))
+        if n_sample is None or (self.world_size == 1 and n_sample == B):
+            return self._step(X, plan, labels, mine, B, sync=False)
+        loss, _ = self._step(X, plan, labels, mine, n_sample, sync=False, gather_preds=False)
+        return loss, None
+
+    def _update_network(self, xs, ys, sizes: Sequence[int] | None = None, sync: bool = True):
         """One optimizer step on the bags `xs` (list of [1,N_i,512]) with labels `ys` (list of [1,2]).
 
         `xs[i]` may also be a zero-argument callable returning the bag (then `sizes` gives the N_i): only the bags of
-        this rank's shard are fetched, so with a lazy dataset every rank reads 1/world of the step from storage."""
+        this rank's shard are fetched, so with a lazy dataset every rank reads 1/world of the step from storage.
+        Returns (batch loss, raw predictions [n, R]) — a float and a host tensor as in the reference
+        (runner/vlsa_handler.py:262-289), or with `sync=False` two DEVICE tensors and no host synchronisation in the step
+        (the epoch loop converts them once, at its end)."""
         n_sample = len(xs)
         if sizes is None:
             sizes = [int(x.shape[-2]) for x in xs]
         mine = vdist.shard_indices(sizes, self.rank, self.world_size, self.balance_shards)
-        bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
         X = plan = None
         if mine:
             local = {i: (xs[i]() if callable(xs[i]) else xs[i]) for i in mine}
             X, plan = self._pack_local(local, mine)
-        return self._step(X, plan, bag_label, mine, n_sample)
+        return self._step(X, plan, self._labels(ys, mine), mine, n_sample, sync)
 
-    def update_network_cached(self, cohort, keys: Sequence, ys):
+    def update_network_cached(self, cohort, keys: Sequence, ys, sync: bool = True):
         """`_update_network` on bags that are already resident in a `DeviceCohort` (keys = their cohort keys, e.g. the
         dataset indices): no staging, no H2D of rows — the step's plan points into the cohort buffer.  With several
         ranks the cohort is partitioned STATICALLY (every bag lives in exactly one rank's cohort, e.g. key % world ==
@@ -161,31 +203,103 @@ class VLSAHandler:
         mine = [i for i, k in enumerate(keys) if k in cohort]
         if self.world_size == 1 and len(mine) != n_sample:
             raise KeyError("update_network_cached: a bag of the step is not in the cohort")
-        bag_label = torch.cat([y.reshape(1, 2) for y in ys], dim=0).to(self.device)
         plan = cohort.plan([keys[i] for i in mine]) if mine else None
-        return self._step(cohort.X if mine else None, plan, bag_label, mine, n_sample)
+        return self._step(cohort.X if mine else None, plan, self._labels(ys, mine), mine, n_sample, sync)
 
-    def _step(self, X, plan, bag_label, mine, n_sample):
-        self.bucket.zero()
-        if mine:
-            logits, _, _, _ = self.net.forward_packed(X, plan)                       # [B_local, R]
-            sel = torch.as_tensor(mine, device=self.device)
-            pred_loss = self.calc_objective_loss(logits, bag_label[sel], norm=n_sample)   # sum_local / n_sample
-            pred_loss.backward()
-            local_loss, local_pred = pred_loss.detach(), logits.detach()
+    def _fused_ok(self) -> bool:
+        """The step can run as three C calls (ops.FusedTrainStep): shipped VLFAN shape (mean over P + Linear adapter, raw rows
+        in) and gradients attached to the bucket.  Everything else takes the autograd path."""
+        enc = self.net.mil_encoder
+        return (self.fused_step and self.device.type == "cuda" and isinstance(enc, deepmil.VLFAN) and enc.fused_tail and self.bucket.attached()
+                and not (self.objective.w_ifmle == 0.0 and self.objective.w_emd == 0.0))
+
+    def _fused_local_step(self, X, plan, t, e, n_sample):
+        """forward + loss + backward of this rank's bags; the three loss values land in the bucket tail."""
+        net, enc, bk = self.net, self.net.mil_encoder, self.bucket
+        adapter = enc.Q if isinstance(enc.Q, PromptAdapter) else None
+        res = adapter.residual_features if adapter is not None and adapter.method == "TaskRes" and not enc.gated_query else None
+        if res is not None and res.requires_grad and res.grad is not None:
+            # plain TaskRes rows (prompt_adapter.py:125-126): Q = ratio * residual + prompt, so d residual = ratio * dQ — one
+            # kernel into the attached view instead of a trip through the autograd engine (same arithmetic, same bits)
+            with torch.no_grad():
+                Qd, prenorm = enc.query_directions()
         else:
-            local_loss = torch.zeros((), device=self.device)
+            res = None
+            Qd, prenorm = enc.query_directions()               # small autograd graph over the prompt adapter (grad mode is on)
+        T = net._text_features_for_kernels()
+        W, bias, ls = enc.visual_adapter.weight, enc.visual_adapter.bias, net.logit_scale
+        leaves = {"W": W, "bias": bias, "logit_scale": ls}
+        out = self._fused(X, plan, Qd, W, bias, T, ls, t, e, w_ifmle=self.objective.w_ifmle, w_emd=self.objective.w_emd,
+                          alpha=self.objective.alpha, eps=self.objective.eps, norm=n_sample, scale=enc.coattn_scale_float(),
+                          q_prenorm=prenorm, grad_out={k: p.grad for k, p in leaves.items() if p.requires_grad},
+                          loss_out=bk.tail)
+        for k, buf in (("W", out["dW"]), ("bias", out["db"]), ("logit_scale", out["dls"])):
+            p = leaves[k]
+            if not p.requires_grad:
+                continue
+            if out["wrote"][k]:
+                bk.mark_touched(p)                             # written in place of the zeroed view
+            else:
+                p.grad.add_(buf.reshape(-1)[: p.numel()].view_as(p))
+                bk.mark_touched(p)
+        if res is not None:
+            torch.mul(out["dQ"], float(adapter.res_ratio), out=res.grad)
+            bk.mark_touched(res)
+        roots = [(z, g) for z, g in ((Qd, out["dQ"]), (T, out["dT"])) if z.requires_grad]
+        if roots:
+            torch.autograd.backward([z for z, _ in roots], [g for _, g in roots])
+        return out["logits"], out["loss"] is not None and out["loss"].data_ptr() == bk.tail.data_ptr()
+
+    def _step(self, X, plan, lab, mine, n_sample, sync: bool = True, gather_preds: bool = True):
+        """`lab`: labels of the local bags, [2, len(mine)] int64 on the device (`_labels`); `mine`: their positions among the
+        `n_sample` bags of the step."""
+        self.bucket.zero()
+        loss_in_tail = False
+        local_loss = None
+        if mine:
+            if self._fused_ok():
+                with torch.enable_grad():
+                    local_pred, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample)
+            else:
+                logits, _, _, _ = self.net.forward_packed(X, plan)                   # [B_local, R]
+                pred_loss = self.calc_objective_loss(logits, lab.t(), norm=n_sample)  # sum_local / n_sample
+                pred_loss.backward()
+                local_loss, local_pred = pred_loss.detach().reshape(1), logits.detach()
+        else:
             local_pred = torch.zeros(0, self.net.forward_text_only().shape[0], device=self.device)
-        # the one exchange of the step: gradients + loss in one flat bucket
-        self.bucket.pack(local_loss.reshape(1))
+        # the one exchange of the step: gradients + losses in one flat bucket
+        self.bucket.pack(local_loss, extra_in_place=loss_in_tail)
         self.bucket.all_reduce()
         self.bucket.unpack()
-        tail = self.bucket.flat[-(1 + len(self.bucket.params)):].cpu()         # loss + per-parameter "touched" flags
-        self.bucket.drop_untouched(tail[1:])
-        self.optimizer.step()
-        val_loss = float(tail[0])
-        val_preds = vdist.all_reduce_rows(local_pred, mine, n_sample).cpu()
-        return val_loss, val_preds
+        n_par = len(self.bucket.params)
+        if isinstance(self.optimizer, BucketAdam):
+            # the kernel reads the reduced flags itself: untouched parameters are skipped on the device
+            self.optimizer.step()
+            loss_dev = self.bucket.tail[0].clone()
+        else:
+            pattern = (tuple(self.bucket._touched), bool(mine))
+            known = self._flags_known
+            if not sync and known is not None and known[0] == pattern and mine:
+                # which parameters a step reaches is a property of the model, not of the step: with the same local pattern as
+                # the last synchronous step (and bags on this rank) the reduced flags are the same — no device -> host read
+                flags = known[1]
+                loss_dev = self.bucket.tail[0].clone()
+            else:
+                tail = self.bucket.flat[-(3 + n_par):].cpu()            # losses + per-parameter "touched" flags
+                flags = tail[3:]
+                self._flags_known = (pattern, flags)
+                loss_dev = tail[0]
+            self.bucket.drop_untouched(flags)
+            self.optimizer.step()
+        if not gather_preds:
+            preds = None
+        elif self.world_size == 1 and len(mine) == n_sample:
+            preds = local_pred
+        else:
+            preds = vdist.all_reduce_rows(local_pred, mine, n_sample)
+        if sync:
+            return float(loss_dev), (preds.cpu() if preds is not None else None)
+        return loss_dev, preds
 
     def _train_each_epoch(self, epoch, train_loader, name_loader="train"):
         self.net.train()
@@ -198,13 +312,14 @@ class VLSAHandler:
             y_c.append(data_y)
             idx_c.append(data_idx)
             if i_batch % bp_every_batch == 0 or i_batch == num_samples:
-                batch_loss, batch_pred = self._update_network(x_c, y_c)
+                batch_loss, batch_pred = self._update_network(x_c, y_c, sync=False)   # device tensors: one sync per epoch
                 losses.append(batch_loss)
                 all_raw_pred.append(batch_pred)
                 all_gt.append(torch.cat([y.reshape(1, 2) for y in y_c], dim=0).cpu())
                 all_idx.append(torch.cat([i.reshape(-1) for i in idx_c], dim=0).cpu())
                 idx_c, x_c, y_c = [], [], []
-        raw = torch.cat(all_raw_pred, 0)
+        raw = torch.cat(all_raw_pred, 0).cpu()
+        losses = torch.stack([torch.as_tensor(l, dtype=torch.float32).reshape(()).to(raw.device) for l in losses]).tolist() if losses else []
         return {"pred": {"y": torch.cat(all_gt, 0), "raw_y_hat": raw, "y_hat": self.output_converter(raw),
                          "uid": torch.cat(all_idx, 0)}, "loss": losses}
 
