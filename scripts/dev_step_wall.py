@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 out = {}
 n_pat, bs = 128, 32
 sizes = np.exp(np.random.default_rng(0).uniform(np.log(1000), np.log(20000), n_pat)).astype(int)
-for P, layout in ((12, "split16"), (4, "rows"), (12, "rows")):
+for P, layout in (() if "single" in sys.argv else ((12, "split16"), (4, "rows"), (12, "rows"))):
     cohort = DeviceCohort(dev, int(sum((n + 15) // 16 * 16 for n in sizes)), layout=layout)
     for i, n in enumerate(sizes):
         cohort.add(i, torch.randn(int(n), 512, device=dev) * 1.1 + 0.7)

@@ -394,11 +394,9 @@ int vlsa_agg_fwd(const void* X, int x_dtype, int64_t total_rows, const int64_t* 
                                                                 ws.l2_m, ws.l2_l, ws.l2_O);
         VLSA_CUDA(cudaGetLastError());
     }
-    VLSA_DISPATCH_P(P, {
-        merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
-                                                                     S > 0 ? ws.l2_O : ws.part_O, chunk_start, S,
-                                                                     out_ml, out_O, out_v);
-    });
+    merge_fwd_kernel<<<dim3(B, VLSA_D / 64), dim3(64, P), 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
+                                                                   S > 0 ? ws.l2_O : ws.part_O, chunk_start, P, S,
+                                                                   out_ml, out_O, out_v);
     VLSA_CUDA(cudaGetLastError());
     adapter_fwd_kernel<<<VLSA_D / 4, 128, 0, st>>>(W, bias, out_v, B, out_f);
     VLSA_CUDA(cudaGetLastError());
@@ -528,11 +526,9 @@ int vlsa_agg_pooled_fwd(const void* X, int x_dtype, int64_t total_rows, const in
                                                                 ws.l2_m, ws.l2_l, ws.l2_O);
         VLSA_CUDA(cudaGetLastError());
     }
-    VLSA_DISPATCH_P(P, {
-        merge_fwd_kernel<kP><<<dim3(B, VLSA_D / 128), 128, 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
-                                                                     S > 0 ? ws.l2_O : ws.part_O, chunk_start, S,
-                                                                     out_ml, out_O, nullptr);
-    });
+    merge_fwd_kernel<<<dim3(B, VLSA_D / 64), dim3(64, P), 0, st>>>(S > 0 ? ws.l2_m : ws.part_m, S > 0 ? ws.l2_l : ws.part_l,
+                                                                   S > 0 ? ws.l2_O : ws.part_O, chunk_start, P, S,
+                                                                   out_ml, out_O, nullptr);
     VLSA_CUDA(cudaGetLastError());
     return 0;
 }

@@ -9,76 +9,64 @@ namespace vlsa {
 // ------------------------------------------------------------------------------------------------
 // merge of the per-chunk online-softmax partials of one bag (flash-decoding style, fixed order):
 //   m = max_c m_c ; l = sum_c l_c e^{m_c-m} ; O_p = sum_c e^{m_c-m} O_c,p / l ; v = mean_p O_p
-// grid (B, D/128), 128 threads, thread = one feature column.
+// grid (B, D/64), block (64, P): thread (x, y) = (feature column, prototype) folds the bag's entries in order — the loads of
+// different entries are independent, so a thread keeps many in flight; the mean over P goes through shared memory in
+// prototype order.  (The first version gave a thread all P prototypes of its column on a (B, 4) grid: one bag per call left
+// 4 CTAs walking P x S dependent-latency loads, 20-40 us for work that is 3 us here.)
 // With S > 0 the inputs are the level-1 partials of merge_fwd_split_kernel: bag b owns entries [b S, b S + S)
 // (unused entries carry m = -inf, l = 0, O = 0); chunk_start then only tells whether the bag is empty.
-template <int P>
-__global__ void __launch_bounds__(128) merge_fwd_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
-                                                        const float* __restrict__ part_O, const int* __restrict__ chunk_start,
-                                                        int S, float* __restrict__ out_ml, float* __restrict__ out_O,
-                                                        float* __restrict__ out_v) {
-    constexpr int D = VLSA_D, CB = 32;                 // chunks per batch
-    __shared__ float s_mx[P];
-    __shared__ float s_sf[CB][P];
-    __shared__ float s_red[4][P];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = blockIdx.y * 128 + tid;
+__global__ void __launch_bounds__(64 * VLSA_MAX_P) merge_fwd_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                                                     const float* __restrict__ part_O, const int* __restrict__ chunk_start,
+                                                                     int P, int S, float* __restrict__ out_ml, float* __restrict__ out_O,
+                                                                     float* __restrict__ out_v) {
+    constexpr int D = VLSA_D;
+    __shared__ float s_o[VLSA_MAX_P][64];
+    const int b = blockIdx.x, col = threadIdx.x, p = threadIdx.y;
+    const int d = blockIdx.y * 64 + col;
     const bool bag_empty = chunk_start[b + 1] == chunk_start[b];
     const int c0 = S > 0 ? b * S : chunk_start[b], c1 = S > 0 ? c0 + (bag_empty ? 0 : S) : chunk_start[b + 1];
 
-    // pass 1: global max per p over the bag's chunks
-    float mx[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) mx[p] = -INFINITY;
-    for (int c = c0 + tid; c < c1; c += 128)
-#pragma unroll
-        for (int p = 0; p < P; ++p) mx[p] = fmaxf(mx[p], part_m[size_t(c) * P + p]);
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const float v = warp_max(mx[p]);
-        if (lane == 0) s_red[warp][p] = v;
-    }
-    __syncthreads();
-    if (tid < P) s_mx[tid] = fmaxf(fmaxf(s_red[0][tid], s_red[1][tid]), fmaxf(s_red[2][tid], s_red[3][tid]));
-    __syncthreads();
-
-    float o[P], l[P];
-#pragma unroll
-    for (int p = 0; p < P; ++p) { o[p] = 0.f; l[p] = 0.f; }
-    for (int cb = c0; cb < c1; cb += CB) {
-        const int nb = (c1 - cb) < CB ? (c1 - cb) : CB;
-        __syncthreads();
-        for (int i = tid; i < nb * P; i += 128) {
-            const int c = i / P, p = i % P;
-            const float mc = part_m[size_t(cb + c) * P + p];
-            s_sf[c][p] = mc == -INFINITY ? 0.f : expf(mc - s_mx[p]);
+    // a warp = 32 consecutive columns of ONE prototype: its lanes share the per-entry scalars (m, l, the scale factor), so each
+    // lane fetches / computes them for one entry in 32 and they travel by shuffle; the O loads of eight entries are issued
+    // together, the fold itself stays in entry order (bit-stable, and the same bits as a plain sequential loop)
+    const int lane = col & 31;
+    float mx = -INFINITY;
+    for (int c = c0 + lane; c < c1; c += 32) mx = fmaxf(mx, __ldg(part_m + size_t(c) * P + p));
+    mx = warp_max(mx);
+    float o = 0.f, l = 0.f;
+    for (int cb = c0; cb < c1; cb += 32) {
+        const int c = cb + lane;
+        float sf_mine = 0.f, l_mine = 0.f;
+        if (c < c1) {
+            const float mc = __ldg(part_m + size_t(c) * P + p);
+            sf_mine = mc == -INFINITY ? 0.f : expf(mc - mx);
+            l_mine = __ldg(part_l + size_t(c) * P + p);
         }
-        __syncthreads();
-        for (int c = 0; c < nb; ++c) {
-            const float* po = part_O + size_t(cb + c) * P * D + d;
-            const float* pl = part_l + size_t(cb + c) * P;
+        const int nb = (c1 - cb) < 32 ? (c1 - cb) : 32;
+        for (int k0 = 0; k0 < nb; k0 += 8) {
+            float ov[8];
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float sf = s_sf[c][p];
-                o[p] += sf * po[size_t(p) * D];
-                l[p] += sf * pl[p];
+            for (int k = 0; k < 8; ++k) ov[k] = (k0 + k < nb) ? part_O[(size_t(cb + k0 + k) * P + p) * D + d] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float sf = __shfl_sync(0xffffffffu, sf_mine, k0 + k), lv = __shfl_sync(0xffffffffu, l_mine, k0 + k);
+                o = fmaf(sf, ov[k], o);
+                l = fmaf(sf, lv, l);
             }
         }
     }
-    float vs = 0.f;
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-        const float op = (c1 > c0) ? o[p] / l[p] : 0.f;      // empty bag: matmul over an empty N gives zeros
-        if (out_O) out_O[(size_t(b) * P + p) * D + d] = op;
-        vs += op;
+    const float op = (c1 > c0) ? o / l : 0.f;                 // empty bag: matmul over an empty N gives zeros
+    if (out_O) out_O[(size_t(b) * P + p) * D + d] = op;
+    s_o[p][col] = op;
+    __syncthreads();
+    if (p == 0 && out_v) {
+        float vs = 0.f;
+        for (int q = 0; q < P; ++q) vs += s_o[q][col];
+        out_v[size_t(b) * D + d] = vs / float(P);             // torch.mean over P (deepmil.py:136)
     }
-    if (out_v) out_v[size_t(b) * D + d] = vs / float(P);    // torch.mean over P (deepmil.py:136)
-    if (blockIdx.y == 0 && tid < P) {
-        out_ml[(size_t(b) * P + tid) * 2 + 0] = s_mx[tid];
-        float lt = 0.f;
-#pragma unroll
-        for (int p = 0; p < P; ++p) if (p == tid) lt = l[p];
-        out_ml[(size_t(b) * P + tid) * 2 + 1] = lt;
+    if (blockIdx.y == 0 && col == 0) {
+        out_ml[(size_t(b) * P + p) * 2 + 0] = mx;
+        out_ml[(size_t(b) * P + p) * 2 + 1] = l;
     }
 }
 

@@ -189,6 +189,30 @@ class VLFAN(nn.Module):
         Qn = F.normalize(Q, dim=-1)
         return Qn[:-1] - Qn[-1:], True
 
+    def query_directions_cached(self):
+        """`query_directions()` for calls that need no gradient, evaluated once per state of the query network: the prompt
+        adapter is a few [P, 512] tensor ops (~10 us of launches per call) whose inputs only change at optimizer steps.  The
+        cache key is the version counter of every parameter and buffer behind Q (in-place updates bump it) and the
+        train / eval mode (dropout in the FC adapter)."""
+        Q = self.Q
+        if isinstance(Q, nn.Module):
+            key = (Q.training, tuple((id(t), t._version) for t in Q.parameters()), tuple((id(t), t._version) for t in Q.buffers()))
+            if Q.training and any(isinstance(m, nn.Dropout) and m.p > 0 for m in Q.modules()):
+                key = None
+        elif isinstance(Q, torch.Tensor):
+            key = (id(Q), Q._version)
+        else:
+            key = None
+        hit = getattr(self, "_qdir_cache", None)
+        if key is not None and hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            Qd, prenorm = self.query_directions()
+            Qd = Qd.contiguous()
+        if key is not None:
+            self._qdir_cache = (key, Qd, prenorm)
+        return Qd, prenorm
+
     def get_query(self):
         assert self.Q is not None, f"You have to call `reset_query` to reset query for query_type ({self.query_type})."
         return self.Q() if callable(self.Q) else self.Q

@@ -112,6 +112,9 @@ class VLSA(nn.Module):
             feats = ops.row_normalize(Xp) if getattr(self, "zero_shot_image_features", True) else None
             return pooled, feats, Tn
         plan = ops.make_plan([Xp.shape[0]], Xp.device)
+        lean = self._infer(Xp, plan, text_features, want_if=False)
+        if lean is not None:
+            return lean[:3]
         logits, g, Tn, _, _ = self._fused(Xp, plan, text_features)
         return logits, g, Tn
 
@@ -130,10 +133,30 @@ class VLSA(nn.Module):
         return ops.aggregate(Xp, plan, Qd, enc.visual_adapter.weight, enc.visual_adapter.bias,
                              text_features, self.logit_scale, enc.coattn_scale_float(), prenorm)
 
+    def _infer(self, Xp, plan, text_features, want_if: bool):
+        """The fused forward when nothing asks for a gradient (eval loops, `torch.no_grad()`): the lean call
+        (``ops.aggregate_infer``) with the query rows cached across calls.  None when autograd has to see the call."""
+        enc = self.mil_encoder
+        if not enc.fused_tail:
+            return None
+        W, b, ls = enc.visual_adapter.weight, enc.visual_adapter.bias, self.logit_scale
+        grad = torch.is_grad_enabled()
+        if grad and (W.requires_grad or b.requires_grad or ls.requires_grad or text_features.requires_grad):
+            return None
+        Qd, prenorm = enc.query_directions_cached() if not grad else enc.query_directions()
+        if grad and Qd.requires_grad:
+            return None
+        if not (Qd.is_contiguous() and text_features.is_contiguous() and W.is_contiguous()):
+            return None
+        return ops.aggregate_infer(Xp, plan, Qd, W, b, text_features, ls, enc.coattn_scale_float(), prenorm, want_if)
+
     def forward_packed(self, X_packed: torch.Tensor, plan: "ops.BagPlan", text_features: torch.Tensor | None = None):
         """All bags of one step in one launch: X_packed [sum N_i, 512] + plan -> (logits [B,R], g [B,512], Tn,
         incidence [B,R]).  Numerically identical to looping ``forward`` over the bags."""
         if text_features is None:
             text_features = self._text_features_for_kernels()
+        lean = self._infer(X_packed, plan, text_features, want_if=True)
+        if lean is not None:
+            return lean
         logits, g, Tn, inc, _ = self._fused(X_packed, plan, text_features)
         return logits, g, Tn, inc

@@ -119,8 +119,11 @@ def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
     if hit is not None:
         _PLAN_CACHE.move_to_end(key)
         plan, uploaded = hit
-        if uploaded is not None and not uploaded.query():
-            torch.cuda.current_stream(dev).wait_event(uploaded)
+        if uploaded is not None:
+            if uploaded.query():
+                _PLAN_CACHE[key] = (plan, None)            # the upload has completed: later hits skip the query
+            else:
+                torch.cuda.current_stream(dev).wait_event(uploaded)
         return plan
     plan = _build_plan(sizes_t, dev, sms)
     uploaded = None
@@ -315,6 +318,56 @@ def aggregate_forward_raw(X, plan: BagPlan, Q, W, bias, T, logit_scale, need_bwd
     _lib.check(rc, "vlsa_agg_fwd")
     out["_workspace"] = ws
     return out
+
+
+_WS_BYTES: dict[tuple, int] = {}
+
+
+def aggregate_infer(X, plan: BagPlan, Q, W, bias, T, logit_scale, scale: float | None = None, q_prenorm: bool = False,
+                    want_if: bool = True):
+    """The inference call of ``VLSA.forward`` / ``forward_packed`` with as little host work as the contract allows: the same
+    launches as ``aggregate_forward_raw(need_bwd=False)``, but the workspace and the by-products nobody reads (v, f, the
+    softmax statistics) share ONE allocation and the parameters are taken as they are (no detach / contiguous copies).
+    At one bag of a few thousand rows per call the GPU work is ~25 us and every allocator call ~3 us.
+    Returns (logits [B,R], g [B,512], Tn [R,512], incidence [B,R] or None)."""
+    L = _lib.lib()
+    B, P, R = plan.num_bags, Q.shape[0], T.shape[0]
+    if X.dim() != 2 or (X.shape[1] != D_FEAT and not _is_split16(X)) or X.shape[0] != plan.total_rows:
+        raise ValueError(f"packed X {tuple(X.shape)} does not go with a plan over {plan.total_rows} rows of {D_FEAT}")
+    if _is_split16(X) and not plan.ranges:
+        raise ValueError("a pre-split cohort image goes with a row-range plan (DeviceCohort.plan)")
+    if not (1 <= P <= MAX_P and 1 <= R <= MAX_R):
+        raise ValueError(f"P={P} / R={R} outside 1..{MAX_P} / 1..{MAX_R}")
+    _check_cuda(X, "X", None)
+    for name, z in (("Q", Q), ("W", W), ("bias", bias), ("T", T), ("logit_scale", logit_scale)):
+        _check_cuda(z, name)
+    if Q.shape[1] != D_FEAT or T.shape[1] != D_FEAT or W.shape[0] != D_FEAT or W.shape[1] != D_FEAT or bias.numel() != D_FEAT:
+        raise ValueError("parameter shapes do not match D=512")
+    key = (plan.total_chunks, B, P)
+    ws_bytes = _WS_BYTES.get(key)
+    if ws_bytes is None:
+        ws_bytes = (max(int(L.vlsa_agg_workspace_bytes(plan.total_chunks, B, P)), 256) + 255) // 256 * 256
+        if len(_WS_BYTES) > 4096:
+            _WS_BYTES.clear()
+        _WS_BYTES[key] = ws_bytes
+    dev = X.device
+    side = B * (2 * D_FEAT + 2 * P)                       # v | f | ml, fp32
+    scratch = torch.empty(ws_bytes + 4 * side, dtype=torch.uint8, device=dev)
+    logits = torch.empty(B, R, dtype=torch.float32, device=dev)
+    g = torch.empty(B, D_FEAT, dtype=torch.float32, device=dev)
+    Tn = torch.empty(R, D_FEAT, dtype=torch.float32, device=dev)
+    inc = torch.empty(B, R, dtype=torch.float32, device=dev) if want_if else None
+    base = scratch.data_ptr()
+    v_ptr = base + ws_bytes
+    f_ptr = v_ptr + 4 * B * D_FEAT
+    ml_ptr = f_ptr + 4 * B * D_FEAT
+    rc = L.vlsa_agg_fwd(X.data_ptr(), _agg_dtype_code(X, plan), plan.total_rows, plan.cu_rows.data_ptr(), plan.chunk_start.data_ptr(),
+                        B, plan.chunk_rows, plan.total_chunks, Q.data_ptr(), P, int(bool(q_prenorm)),
+                        coattn_scale() if scale is None else float(scale), W.data_ptr(), bias.data_ptr(), T.data_ptr(), R,
+                        logit_scale.data_ptr(), base, ws_bytes, v_ptr, f_ptr, g.data_ptr(), logits.data_ptr(),
+                        None if inc is None else inc.data_ptr(), ml_ptr, None, Tn.data_ptr(), _stream())
+    _lib.check(rc, "vlsa_agg_fwd")
+    return logits, g, Tn, inc
 
 
 def aggregate_partial_only(X, plan: BagPlan, Q, workspace: torch.Tensor, scale: float | None = None) -> None:
