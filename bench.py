@@ -494,6 +494,56 @@ def main():
             if (P, R) == (12, 12):
                 break
 
+    # ---- optimizer steps on TCGA-sized bags drawn from a device cohort (BASELINE configs[2]: what a training epoch of the
+    #      reference's loop looks like from epoch 2 on): wall clock, host work included -------------------------------------
+    tcga = None
+    if not args.no_train and not args.no_ragged:
+        from vlsa_b200.dataset import DeviceCohort
+        from vlsa_b200.runner import VLSAHandler
+        rs_t = np.random.RandomState(99 + rank)
+        n_pat = 4 * nb
+        t_sizes = [int(v) for v in np.exp(rs_t.uniform(np.log(1e3), np.log(2e4), n_pat))]
+        tcga = {"bags": n_pat, "bags_per_step": nb, "rows_min_max_mean": [min(t_sizes), max(t_sizes), float(np.mean(t_sizes))],
+                "what": "VLSAHandler.step_packed on shuffled steps of 32 bags with N_i ~ LogUniform(1k, 20k) drawn from a DeviceCohort "
+                        "(row-range plans): forward + SurvIFMLE/SurvEMD + backward + flat-bucket all-reduce + Adam, WALL clock over "
+                        "whole epochs (plan upload, labels and every launch included), one synchronisation per epoch"}
+        for (p_, layout) in ((P, "rows"), (12, "split16")):
+            if args.dtype != "fp32" and layout == "split16":
+                continue
+            coh = DeviceCohort(dev, sum((n + 15) // 16 * 16 for n in t_sizes), dtype=xdtype if layout == "rows" else torch.float32,
+                               layout=layout)
+            at = 0
+            for i, n in enumerate(t_sizes):                     # rows taken from the resident synthetic batches
+                src = batches[0][at:at + n]
+                coh.add(i, src if layout == "rows" else src.float())
+                at += n
+            net_t = build_net(p_, p_, dev).train()
+            h_t = VLSAHandler({"task": "vlsa", "arch": "VLSA", "loss_type": "SurvIFMLE-SurvEMD", "opt_name": "adam", "opt_lr": 2e-4},
+                              net=net_t, device=dev)
+            tl, el = synth.make_labels(n_pat, p_, 5 + rank)
+            lab_all = torch.stack([tl, el], 1)
+
+            def epochs(n_ep):
+                for _ in range(n_ep):
+                    order = rs_t.permutation(n_pat)
+                    for s0 in range(0, n_pat, nb):
+                        ids = order[s0:s0 + nb].tolist()
+                        h_t.step_packed(coh.X, coh.plan(ids), lab_all[ids], nb * world)
+                torch.cuda.synchronize(dev)
+
+            epochs(2)
+            sync_all()
+            t0 = time.perf_counter()
+            n_ep = 8
+            epochs(n_ep)
+            tt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            n_steps = n_ep * (n_pat // nb)
+            tcga[f"P{p_}_{layout}"] = {"value": n_steps * nb * world / float(tt.item()), "unit": "WSI/s",
+                                       "ms_per_step": 1e3 * float(tt.item()) / n_steps, "steps": n_steps}
+            del coh, h_t, net_t
+
     # ---- the reference's eager-torch op sequence on the SAME GPU (BASELINE configs[1]) ----------------
     torch_gpu = None
     if not args.no_torch_gpu and rank == 0:
@@ -628,7 +678,7 @@ def main():
                                                  "of the same 3.28 GB (profiles/readbw_r01.txt)"},
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps, "e2e": e2e, "e2e_cached": e2e_cached,
         "train_step": main_rec.get("train_step"), "shipped_shape": shipped, "ragged": ragged,
-        "torch_gpu_baseline": torch_gpu,
+        "tcga_sized_training": tcga, "torch_gpu_baseline": torch_gpu,
     }
     # DRAM traffic of the dominant kernel from the committed ncu capture of THIS build (null when the kernels changed since)
     traffic_file = os.path.join(ROOT, "profiles", "traffic_r02.json")

@@ -53,6 +53,9 @@ def main():
     ap.add_argument("--gated-query", action="store_true")
     ap.add_argument("--query-pooling", default="mean", choices=["mean", "max", "weight", "attention", "gated_attention"])
     ap.add_argument("--feat-proj", action="store_true")
+    ap.add_argument("--autograd-step", action="store_true",
+                    help="run every optimizer step through torch autograd and torch.optim.Adam instead of the fused C-call step "
+                         "and the bucket Adam kernel (same kernels underneath; for cross-checking the two)")
     ap.add_argument("--cohort", default="none", choices=["none", "rows", "split16"],
                     help="keep every bag of this rank's shard resident in HBM after epoch 0 (DeviceCohort): 'rows' = fp32 rows, "
                          "'split16' = pre-split tile records (the tensor-core kernel then converts nothing per epoch)")
@@ -119,6 +122,10 @@ def main():
                query_prompt_features=pr["prompt_features"], vlsa_api="CONCH", path_clip_model=None,
                query_neg_prompt_features=torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1)
                if args.gated_query else None)
+    if args.autograd_step:
+        # (torch's foreach Adam is the implementation the bucket kernel follows to the last bit or two; its fused=True variant
+        # drifts from both by ~lr within a handful of steps on this model)
+        cfg.update(vlsa_fused_step=False, vlsa_bucket_adam=False, vlsa_torch_adam_fused=False)
     handler = VLSAHandler(cfg, net=net, device=dev)
     loader = OneBagLoader()
     bs = cfg["bp_every_batch"]

@@ -111,7 +111,8 @@ class VLSAHandler:
             # one launch over the bucket, untouched parameters skipped on the device (runner/optim.py)
             self.optimizer = BucketAdam(groups, self.bucket, lr=float(cfg.get("opt_lr", 2e-4)))
         else:
-            self.optimizer = torch.optim.Adam(groups, lr=float(cfg.get("opt_lr", 2e-4)), fused=self.device.type == "cuda")
+            self.optimizer = torch.optim.Adam(groups, lr=float(cfg.get("opt_lr", 2e-4)),
+                                              fused=self.device.type == "cuda" and bool(cfg.get("vlsa_torch_adam_fused", True)))
         self.fused_step = bool(cfg.get("vlsa_fused_step", True))
         self._fused = ops.FusedTrainStep()
         self._flags_known = None                  # (this rank's touched pattern, reduced flags) of the last synchronous step
