@@ -522,6 +522,10 @@ def test_fused_train_step_equals_the_autograd_step(P, gated, dev):
 
     for train_text in (False, True):
         ha, hb = make(True, train_text), make(False, train_text)
+        ha.net.eval()
+        with torch.no_grad():                        # an evaluation BEFORE the steps fills the query-row cache
+            ha.net.forward_packed(torch.cat(bags, 0).to(dev), ops.make_plan(sizes, dev))
+        ha.net.train()
         for step in range(2):
             la, pa = ha._update_network(xs, ys)
             lb, pb = hb._update_network(xs, ys)
@@ -531,6 +535,17 @@ def test_fused_train_step_equals_the_autograd_step(P, gated, dev):
         if train_text:
             assert torch.equal(ha.net._text_param, hb.net._text_param)
             assert not torch.equal(ha.net._text_param, pr["text_features"].to(dev))
+        # the optimizer kernel writes through raw pointers: version counters must still move (caches keyed on them, e.g. the
+        # query rows of the lean inference call, would otherwise serve the weights of before the step)
+        ha.net.eval()
+        with torch.no_grad():
+            eval_a = ha.net.forward_packed(torch.cat(bags, 0).to(dev), ops.make_plan(sizes, dev))[0]
+            eval_b = ops.aggregate(torch.cat(bags, 0).to(dev), ops.make_plan(sizes, dev), *ha.net.mil_encoder.query_directions()[:1],
+                                   ha.net.mil_encoder.visual_adapter.weight, ha.net.mil_encoder.visual_adapter.bias,
+                                   ha.net._text_features_for_kernels(), ha.net.logit_scale,
+                                   q_prenorm=ha.net.mil_encoder.query_directions()[1])[0]
+        assert torch.equal(eval_a, eval_b)
+        ha.net.train()
         # no-sync entry points: device tensors back, same numbers; component losses ride the bucket tail
         X = torch.cat(bags, 0).to(dev)
         plan = ops.make_plan(sizes, dev)

@@ -80,6 +80,9 @@ class BucketAdam:
                                        bk.flags.data_ptr() if use_flags else None, float(g0["betas"][0]), float(g0["betas"][1]),
                                        float(g0["eps"]), torch.cuda.current_stream(bk.flat.device).cuda_stream)
         _lib.check(rc, "vlsa_adam_step")
+        # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on a tensor's version
+        # counter, e.g. VLFAN.query_directions_cached) that they changed, as an in-place torch op would
+        torch.autograd.graph.increment_version(bk.params)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.bucket.zero()
