@@ -18,6 +18,7 @@ Xf = torch.cat(bags, 0).to(dev)
 cohort = DeviceCohort(dev, sum((n + 15) // 16 * 16 for n in sizes), layout="split16")
 for i, b in enumerate(bags):
     cohort.add(i, b)
+only = os.environ.get("DEV_ONLY")
 cases = {"fp32 rows (agg_tc)": (Xf, ops.make_plan(sizes, dev)), "bf16 rows (agg_bf16)": (Xf.to(torch.bfloat16), ops.make_plan(sizes, dev)),
          "split16 cohort (agg_split)": (cohort.X, cohort.plan(list(range(len(sizes)))))}
 
@@ -34,6 +35,8 @@ def once(X, plan):
 
 ops.set_agg_variant("tc")
 for name, (X, plan) in cases.items():
+    if only and only not in name:
+        continue
     ref = once(X, plan)
     bad = 0
     for _ in range(iters):
