@@ -393,3 +393,33 @@ def test_gated_query_directions_reproduce_the_reference_scores():
     g2, = torch.autograd.grad(f_ref.sum(), enc.Q)
     torch.testing.assert_close(g1, g2, rtol=1e-8, atol=1e-12)
     assert g1[-1].abs().max() > 0
+
+
+def test_flat_bucket_aligned_segments_and_direct_writes():
+    """FlatBucket(align=4): every segment starts at a multiple of four floats (kernels write gradients straight into the attached
+    views with 128-bit stores), the padding rides the all-reduce as zeros, `mark_touched` stands in for the autograd hook when a
+    kernel wrote a gradient, and `pack(extra_in_place=True)` leaves the tail a kernel filled alone."""
+    import torch
+    from vlsa_b200.runner.dist import FlatBucket
+    ps = [torch.nn.Parameter(torch.randn(())), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(3, 3)),
+          torch.nn.Parameter(torch.randn(2), requires_grad=False)]
+    bk = FlatBucket(ps, extra=3, align=4)
+    assert bk.offsets == [0, 4, 12] and bk.sizes == [1, 5, 9]
+    assert bk.flat.numel() == 4 + 8 + 12 + 3 + 3                      # padded segments | 3 extras | one flag per trainable tensor
+    bk.attach()
+    assert bk.attached() and all(p.grad.data_ptr() % 16 == bk.flat.data_ptr() % 16 for p in ps[:3])
+    bk.zero()
+    ps[1].grad.copy_(torch.arange(5.0))                               # "a kernel wrote this gradient"
+    bk.mark_touched(ps[1])
+    (ps[2] ** 2).sum().backward()                                     # autograd accumulates into the view, its hook marks it
+    bk.tail.copy_(torch.tensor([1.5, 0.5, 1.0]))                      # "the loss kernel wrote (total, ifmle, emd)"
+    bk.pack(None, extra_in_place=True)
+    bk.all_reduce(); bk.unpack()
+    assert bk.tail.tolist() == [1.5, 0.5, 1.0] and bk.flags.tolist() == [0.0, 1.0, 1.0]
+    assert torch.equal(bk.flat[4:9], torch.arange(5.0)) and float(bk.flat[9:12].abs().sum()) == 0.0     # padding stays zero
+    assert torch.allclose(ps[2].grad, 2 * ps[2].detach())
+    # a caller that replaces a gradient tensor detaches the bucket; zero() re-attaches it
+    ps[1].grad = torch.ones(5)
+    assert not bk.attached()
+    bk.zero()
+    assert bk.attached() and float(bk.flat.abs().sum()) == 0.0

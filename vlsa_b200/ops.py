@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import functools
 import math
+import threading
 from collections import OrderedDict
 from dataclasses import dataclass
 
@@ -166,15 +167,24 @@ class _PinnedRing:
         return out
 
 
-_RING: _PinnedRing | None = None
+_RINGS: dict[int, _PinnedRing] = {}          # one ring per device: a slot's event belongs to the device it was recorded on
+_RING_LOCK = threading.Lock()
 
 
 def upload_small(fill, n_words: int, device) -> torch.Tensor:
-    """n_words int64 words written by `fill` into pinned staging -> device tensor, asynchronously on the current stream."""
-    global _RING
-    if _RING is None:
-        _RING = _PinnedRing()
-    return _RING.upload(fill, n_words, device)
+    """n_words int64 words written by `fill` into pinned staging -> device tensor, asynchronously on the current stream of
+    `device`.  Serialised by a lock: loader threads and the training thread share the rings."""
+    dev = torch.device(device)
+    cur = torch.cuda.current_device()
+    idx = dev.index if dev.index is not None else cur
+    with _RING_LOCK:
+        ring = _RINGS.get(idx)
+        if ring is None:
+            ring = _RINGS[idx] = _PinnedRing()
+        if idx == cur:
+            return ring.upload(fill, n_words, dev)
+        with torch.cuda.device(idx):                      # the slot's event is recorded on a stream of ITS device
+            return ring.upload(fill, n_words, dev)
 
 
 def _chunk_schedule(sizes: np.ndarray, sms: int):
