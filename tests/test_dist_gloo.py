@@ -153,3 +153,29 @@ def test_handler_broadcasts_rank0_parameters(tmp_path):
     for k in b0["state"]:
         assert torch.equal(b0["state"][k], b1["state"][k]), k
     assert torch.equal(b0["state"]["mil_encoder.visual_adapter.weight"], b0["before"])   # rank 0 is the source
+
+
+@pytest.mark.timeout(600)
+def test_train_each_epoch_groups_steps_and_reads_back_once():
+    """`_train_each_epoch` (runner/vlsa_handler.py:189-239 of the reference): bags grouped `bp_every_batch` at a time, one optimizer
+    step per group through the no-synchronisation path, losses and raw predictions converted once at the end of the epoch —
+    against a twin handler stepping the same groups one `_update_network` call at a time."""
+    torch.set_num_threads(4)
+    ha, hb = _make_handler(), _make_handler()
+    ha.cfg["bp_every_batch"] = 3
+    xs, ys = _batch()
+    loader = [(torch.tensor([[10 + i]]), (xs[i], torch.zeros(1)), ys[i]) for i in range(len(xs))]
+    out = ha._train_each_epoch(0, loader)
+    groups = [list(range(0, 3)), list(range(3, 6)), list(range(6, 8))]
+    ref_loss, ref_pred = [], []
+    for g in groups:
+        l, p = hb._update_network([xs[i] for i in g], [ys[i] for i in g])
+        ref_loss.append(l); ref_pred.append(p)
+    assert isinstance(out["loss"], list) and len(out["loss"]) == 3 and all(isinstance(v, float) for v in out["loss"])
+    np.testing.assert_allclose(out["loss"], ref_loss, rtol=1e-6)
+    torch.testing.assert_close(out["pred"]["raw_y_hat"], torch.cat(ref_pred, 0), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out["pred"]["y_hat"], torch.softmax(torch.cat(ref_pred, 0), -1), rtol=1e-6, atol=1e-6)
+    assert out["pred"]["uid"].tolist() == [10 + i for i in range(len(xs))]
+    torch.testing.assert_close(out["pred"]["y"], torch.cat([y.reshape(1, 2) for y in ys], 0))
+    for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
+        torch.testing.assert_close(va, vb, rtol=1e-6, atol=1e-8, msg=k)

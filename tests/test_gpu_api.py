@@ -621,3 +621,31 @@ def test_bucket_adam_follows_torch_adam(dev):
         one_step(step)
     for a, b in zip(pa, pb):
         torch.testing.assert_close(b, a, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.gpu
+def test_train_each_epoch_on_the_device(dev):
+    """`VLSAHandler._train_each_epoch` with the real kernels: groups of `bp_every_batch` bags, one fused step each with no host
+    synchronisation inside the epoch, one read-back at its end — same losses, predictions and weights as a twin handler stepping
+    the same groups with synchronous `_update_network` calls."""
+    from vlsa_b200 import synth
+    from vlsa_b200.runner import VLSAHandler
+    P = 12
+    sizes = [1000, 37, 2798, 1, 513, 64, 4096, 255]
+    bags = [synth.make_bag("g1", n, 900 + i) for i, n in enumerate(sizes)]          # host bags, as a DataLoader yields them
+    pr = synth.make_params(P, P, 33)
+    t, e = synth.make_labels(len(sizes), P, 5)
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(sizes))]
+    cfg = dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4, bp_every_batch=3)
+    ha, hb = VLSAHandler(cfg, build_net(pr, P, P, dev), device=dev), VLSAHandler(cfg, build_net(pr, P, P, dev), device=dev)
+    loader = [(torch.tensor([[10 + i]]), (bags[i].unsqueeze(0), torch.zeros(1)), ys[i]) for i in range(len(bags))]
+    out = ha._train_each_epoch(0, loader)
+    ref_loss, ref_pred = [], []
+    for g in ([0, 1, 2], [3, 4, 5], [6, 7]):
+        l, p = hb._update_network([bags[i].unsqueeze(0) for i in g], [ys[i] for i in g])
+        ref_loss.append(l); ref_pred.append(p)
+    assert len(out["loss"]) == 3 and all(isinstance(v, float) for v in out["loss"]) and out["loss"] == ref_loss
+    assert not out["pred"]["raw_y_hat"].is_cuda and torch.equal(out["pred"]["raw_y_hat"], torch.cat(ref_pred, 0))
+    assert out["pred"]["uid"].tolist() == [10 + i for i in range(len(bags))]
+    for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
+        assert torch.equal(va, vb), k

@@ -286,7 +286,8 @@ class VLSAHandler:
                 flags = known[1]
                 loss_dev = self.bucket.tail[0].clone()
             else:
-                tail = self.bucket.flat[-(3 + n_par):].cpu()            # losses + per-parameter "touched" flags
+                # losses + per-parameter "touched" flags; a real copy (on a CPU device `.cpu()` would alias the live bucket)
+                tail = self.bucket.flat[-(3 + n_par):].detach().to("cpu", copy=True)
                 flags = tail[3:]
                 self._flags_known = (pattern, flags)
                 loss_dev = tail[0]
