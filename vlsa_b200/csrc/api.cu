@@ -97,9 +97,13 @@ static int merge_fwd_splits(int total_chunks, int B, int P) {
     if (S > 64) S = 64;
     return S < 1 ? 1 : S;
 }
+// Level 1 (S x P CTAs) folds total_chunks / S partials per thread two at a time, level 2 (P CTAs) folds S entries four at a
+// time: both are chains of dependent-latency rounds, shortest in sum at S ~ sqrt(2 total_chunks) (the first version maximised
+// the CTAs of level 1 — S = 1184 / P — and left level 2 walking 296 entries on 4 CTAs at P = 4: 25 us of the step).
 static int merge_bwd_splits(int total_chunks, int P) {
     if (total_chunks < 16) return 0;
-    int S = 1184 / P;
+    int S = int(sqrtf(2.f * float(total_chunks)) + 0.5f);
+    if (S > 1184 / P) S = 1184 / P;
     if (S > total_chunks / 4) S = total_chunks / 4;
     return S < 1 ? 1 : S;
 }
