@@ -649,3 +649,35 @@ def test_train_each_epoch_on_the_device(dev):
     assert out["pred"]["uid"].tolist() == [10 + i for i in range(len(bags))]
     for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
         assert torch.equal(va, vb), k
+
+
+@pytest.mark.gpu
+def test_query_div_regulariser_rides_the_fused_step(dev):
+    """loss_type 'SurvIFMLE-SurvEMD-QueryDiv' (runner/vlsa_handler.py:181-187,255-256: weight * VLFAN.query_div_loss() added once per
+    optimizer step): the loss of a step is the survival objective plus the weighted regulariser, and the fused step (kernels write
+    d residual, autograd adds the regulariser's share on top) leaves the same weights as the autograd path."""
+    from vlsa_b200 import ops, synth
+    from vlsa_b200.runner import VLSAHandler
+    P = 12
+    sizes = [1000, 37, 2798, 513]
+    bags = [synth.make_bag("g1", n, 70 + i).to(dev) for i, n in enumerate(sizes)]
+    pr = synth.make_params(P, P, 44)
+    t, e = synth.make_labels(len(sizes), P, 5)
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(sizes))]
+    xs = [b.unsqueeze(0) for b in bags]
+    base = dict(task="vlsa", arch="VLSA", opt_name="adam", opt_lr=2e-4)
+    h0 = VLSAHandler(dict(base, loss_type="SurvIFMLE-SurvEMD"), build_net(pr, P, P, dev), device=dev)
+    ha = VLSAHandler(dict(base, loss_type="SurvIFMLE-SurvEMD-QueryDiv", loss_querydiv_weight=0.5), build_net(pr, P, P, dev), device=dev)
+    hb = VLSAHandler(dict(base, loss_type="SurvIFMLE-SurvEMD-QueryDiv", loss_querydiv_weight=0.5, vlsa_fused_step=False),
+                     build_net(pr, P, P, dev), device=dev)
+    assert ha._fused_ok() and not hb._fused_ok()
+    with torch.no_grad():
+        reg = float(ha.net.mil_encoder.query_div_loss())
+    l0, _ = h0._update_network(xs, ys)
+    la, pa = ha._update_network(xs, ys)
+    lb, pb = hb._update_network(xs, ys)
+    assert abs(la - (l0 + 0.5 * reg)) <= 1e-5 * abs(la) and reg > 0
+    assert la == lb and torch.equal(pa, pb)
+    for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
+        assert torch.equal(va, vb), k
+    assert not torch.equal(ha.net.mil_encoder.Q.residual_features, h0.net.mil_encoder.Q.residual_features)

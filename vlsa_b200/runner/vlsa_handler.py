@@ -84,9 +84,13 @@ class VLSAHandler:
         # losses: 'SurvIFMLE-SurvEMD' with per-loss weights (cfg_vlsa_conch.yaml:102-105)
         names = [n for n in str(cfg.get("loss_type", "SurvIFMLE-SurvEMD")).split("-") if n]
         for n in names:
-            if n not in ("SurvIFMLE", "SurvEMD"):
+            if n not in ("SurvIFMLE", "SurvEMD", "QueryDiv"):
                 raise NotImplementedError(f"loss {n} is not part of the accelerated VLSA path")
         self.loss_weight = {n: float(cfg.get(f"loss_{n.lower()}_weight", 1.0)) for n in names}
+        # 'QueryDiv' (runner/vlsa_handler.py:181-187,255-256 + model/deepmil.py:157-168): a regulariser on the P query rows alone,
+        # once per optimizer step — N-independent, so it stays a [P, 512] torch expression next to the fused step
+        self.query_div_kws = ({k: v for k, v in fetch_kws(cfg, "loss_querydiv").items() if k != "weight"}
+                              if "QueryDiv" in names else None)
         # loss options the fused kernel does not implement must not be ignored silently (loss/loss_surv_ext.py:58-69,
         # loss/loss_surv.py:127-143): the shipped configs use p = 2, raw distance, mean reduction, eps 1e-7
         for key, ok in (("loss_survemd_p", lambda v: int(v) == 2), ("loss_survemd_raw_distance", lambda v: bool(v)),
@@ -249,7 +253,15 @@ class VLSAHandler:
         roots = [(z, g) for z, g in ((Qd, out["dQ"]), (T, out["dT"])) if z.requires_grad]
         if roots:
             torch.autograd.backward([z for z, _ in roots], [g for _, g in roots])
-        return out["logits"], out["loss"] is not None and out["loss"].data_ptr() == bk.tail.data_ptr()
+        in_tail = out["loss"].data_ptr() == bk.tail.data_ptr()
+        return out["logits"], (None if in_tail else out["loss"][:3].clone()), in_tail
+
+    def _query_div_term(self):
+        """weight * query_div_loss() of this step, split evenly over the ranks (the bucket all-reduce sums it back)."""
+        if self.query_div_kws is None or self.loss_weight.get("QueryDiv", 0.0) == 0.0:
+            return None
+        with torch.enable_grad():
+            return (self.loss_weight["QueryDiv"] / self.world_size) * self.net.mil_encoder.query_div_loss(**self.query_div_kws)
 
     def _step(self, X, plan, lab, mine, n_sample, sync: bool = True, gather_preds: bool = True):
         """`lab`: labels of the local bags, [2, len(mine)] int64 on the device (`_labels`); `mine`: their positions among the
@@ -257,17 +269,28 @@ class VLSAHandler:
         self.bucket.zero()
         loss_in_tail = False
         local_loss = None
+        extra = self._query_div_term()
         if mine:
             if self._fused_ok():
                 with torch.enable_grad():
-                    local_pred, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample)
+                    local_pred, local_loss, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample)
+                if extra is not None:
+                    extra.backward()                               # accumulates on top of what the kernels wrote
+                    (self.bucket.tail if loss_in_tail else local_loss)[0:1].add_(extra.detach().reshape(1))
+                    extra = None
             else:
                 logits, _, _, _ = self.net.forward_packed(X, plan)                   # [B_local, R]
                 pred_loss = self.calc_objective_loss(logits, lab.t(), norm=n_sample)  # sum_local / n_sample
+                if extra is not None:
+                    pred_loss = pred_loss + extra
+                    extra = None
                 pred_loss.backward()
                 local_loss, local_pred = pred_loss.detach().reshape(1), logits.detach()
         else:
             local_pred = torch.zeros(0, self.net.forward_text_only().shape[0], device=self.device)
+        if extra is not None:                                      # a rank without bags still owes its share of the regulariser
+            extra.backward()
+            local_loss = extra.detach().reshape(1)
         # the one exchange of the step: gradients + losses in one flat bucket
         self.bucket.pack(local_loss, extra_in_place=loss_in_tail)
         self.bucket.all_reduce()
