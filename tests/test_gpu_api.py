@@ -681,3 +681,35 @@ def test_query_div_regulariser_rides_the_fused_step(dev):
     for (k, va), (_, vb) in zip(ha.net.state_dict().items(), hb.net.state_dict().items()):
         assert torch.equal(va, vb), k
     assert not torch.equal(ha.net.mil_encoder.Q.residual_features, h0.net.mil_encoder.Q.residual_features)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,dtype", [(4, torch.float32), (12, torch.float32), (12, torch.bfloat16)])
+def test_graphed_forward_replays_the_same_call(P, dtype, dev):
+    """`VLSA.graphed(N)` (CUDA-graph replay of `VLSA.forward` for bags of one size): bit-identical to the eager call for every
+    bag, sees in-place weight updates, re-captures when the prompt adapter's tensors change, rejects other shapes."""
+    from vlsa_b200 import synth
+    N = 2798
+    pr = synth.make_params(P, P, 50 + P)
+    net = build_net(pr, P, P, dev).eval()
+    gf = net.graphed(N, dtype)
+    bags = [synth.make_bag("g1", N, 400 + i).to(dev).to(dtype).unsqueeze(0) for i in range(3)]
+    with torch.no_grad():
+        for X in bags:
+            want = [z.clone() for z in net(X)]
+            got = gf(X)
+            assert all(torch.equal(a, b) for a, b in zip(want, got))
+        # the caller may land a bag in `.input` itself (e.g. as the target of its H2D copy) and replay
+        gf.input.copy_(bags[1])
+        assert torch.equal(gf.replay()[0], net(bags[1])[0])
+        # in-place weight updates are seen through the pointers; a changed residual re-captures (new query rows)
+        net.mil_encoder.visual_adapter.weight.mul_(1.01)
+        net.logit_scale.add_(0.05)
+        assert torch.equal(gf(bags[0])[0], net(bags[0])[0])
+        net.mil_encoder.Q.residual_features.add_(0.01)
+        assert torch.equal(gf(bags[2])[0], net(bags[2])[0])
+        with pytest.raises(ValueError):
+            gf(bags[0][:, :100])
+    net.train()
+    with pytest.raises(RuntimeError):
+        gf(bags[0])

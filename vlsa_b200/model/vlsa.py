@@ -118,6 +118,11 @@ class VLSA(nn.Module):
         logits, g, Tn, _, _ = self._fused(Xp, plan, text_features)
         return logits, g, Tn
 
+    def graphed(self, n_rows: int, dtype: torch.dtype = torch.float32):
+        """CUDA-graph replay of ``forward`` for bags of ``n_rows`` rows (model/graphed.py): one ``cudaGraphLaunch`` per call."""
+        from .graphed import GraphedForward
+        return GraphedForward(self, n_rows, dtype)
+
     # ---- batched entry (SURVEY §8 f1) -------------------------------------------------------------
     def _fused(self, Xp, plan, text_features):
         enc = self.mil_encoder
