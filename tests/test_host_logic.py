@@ -423,3 +423,33 @@ def test_flat_bucket_aligned_segments_and_direct_writes():
     assert not bk.attached()
     bk.zero()
     assert bk.attached() and float(bk.flat.abs().sum()) == 0.0
+
+
+def test_query_rows_cache_follows_the_adapter():
+    """`VLFAN.query_directions_cached()` (the rows the lean inference call and the graph replay use): evaluated once per state of the
+    prompt adapter — an in-place update or a bumped version counter (what `BucketAdam` does after its kernel wrote the weights
+    through raw pointers) invalidates it; the gated query's difference rows are cached the same way."""
+    import torch
+    from vlsa_b200.model import VLSA
+    nets = [_net(P=4, R=4)[0]]
+    pr = synth.make_params(4, 4, 3)
+    nets.append(VLSA({"name": "mahmoodlab/conch"},
+                     dict(name="VLFAN", dim_in=512, use_feat_proj=False, query="Text", num_query=4, gated_query=True,
+                          query_text_method="TaskRes"),
+                     {"name": "CoOp"}, text_features=pr["text_features"], query_prompt_features=pr["prompt_features"],
+                     query_neg_prompt_features=torch.randn(1, 512)))
+    for net in nets:
+        enc = net.mil_encoder
+        a, pre = enc.query_directions_cached()
+        b, _ = enc.query_directions_cached()
+        assert a is b and not a.requires_grad and bool(pre) == bool(enc.gated_query) and a.shape == (4, 512)
+        with torch.no_grad():
+            want, _ = enc.query_directions()
+        assert torch.equal(a, want)
+        with torch.no_grad():
+            enc.Q.residual_features.add_(0.25)                      # in-place update: the version counter moves
+        c, _ = enc.query_directions_cached()
+        assert c is not a and torch.equal(c, enc.query_directions()[0].detach()) and not torch.equal(c, a)
+        torch.autograd.graph.increment_version(enc.Q.residual_features)     # what a raw-pointer writer does after its kernel
+        d, _ = enc.query_directions_cached()
+        assert d is not c and torch.equal(d, c)
