@@ -53,6 +53,10 @@ def main():
     ap.add_argument("--gated-query", action="store_true")
     ap.add_argument("--query-pooling", default="mean", choices=["mean", "max", "weight", "attention", "gated_attention"])
     ap.add_argument("--feat-proj", action="store_true")
+    ap.add_argument("--handler-loop", action="store_true",
+                    help="run every epoch through VLSAHandler._train_each_epoch(loader) — the reference's own loop "
+                         "(runner/vlsa_handler.py:189-239) — with cfg vlsa_device_cohort = --cohort: the handler keeps the bags it "
+                         "has seen resident in HBM and the dataset stops reading them after the first epoch (1 GPU)")
     ap.add_argument("--autograd-step", action="store_true",
                     help="run every optimizer step through torch autograd and torch.optim.Adam instead of the fused C-call step "
                          "and the bucket Adam kernel (same kernels underneath; for cross-checking the two)")
@@ -106,6 +110,7 @@ def main():
     ds = WSIPatchSurvStore(store, pids, pid2sids, pid2label)
 
     class OneBagLoader:            # DataLoader(batch_size=1) of the reference: (idx [1], (feats [1,N,512], extra), label [1,2])
+        dataset = ds
         def __len__(self): return len(ds)
         def __iter__(self):
             for i in range(len(ds)):
@@ -126,6 +131,8 @@ def main():
         # (torch's foreach Adam is the implementation the bucket kernel follows to the last bit or two; its fused=True variant
         # drifts from both by ~lr within a handful of steps on this model)
         cfg.update(vlsa_fused_step=False, vlsa_bucket_adam=False, vlsa_torch_adam_fused=False)
+    if args.handler_loop and args.cohort != "none":
+        cfg["vlsa_device_cohort"] = args.cohort
     handler = VLSAHandler(cfg, net=net, device=dev)
     loader = OneBagLoader()
     bs = cfg["bp_every_batch"]
@@ -140,6 +147,20 @@ def main():
         torch.cuda.synchronize(); t0 = time.time()
         handler.net.train()
         losses = []
+        if args.handler_loop:
+            assert world == 1, "--handler-loop is the single-process loop of the reference"
+            losses = handler._train_each_epoch(epoch, loader)["loss"]
+            torch.cuda.synchronize(); dt = time.time() - t0
+            ds.skip_features(())                                # evaluation below reads every bag again
+            pred = handler.test_model(handler.net, loader)["pred"]
+            if handler.cohort is not None:
+                ds.skip_features(handler.cohort.index.keys())
+            inc = pred["y_hat"].numpy()
+            score = (inc * np.arange(R)[None, :]).sum(1)
+            c = concordance_index(-score, pred["y"][:, 0].numpy(), pred["y"][:, 1].numpy())
+            print(f"[epoch {epoch}] loss {np.mean(losses):.4f}  C-index {c:.3f}  train {dt:.3f} s "
+                  f"({args.patients / dt:.0f} bags/s through VLSAHandler._train_each_epoch, cohort {cfg.get('vlsa_device_cohort')})", flush=True)
+            continue
         if cohort is not None and epoch == 0:
             for i in mine_all:                               # the one upload of the run (epoch 0 pays the store reads and H2D)
                 cohort.add(i, ds[i][1][0])

@@ -713,3 +713,48 @@ def test_graphed_forward_replays_the_same_call(P, dtype, dev):
     net.train()
     with pytest.raises(RuntimeError):
         gf(bags[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["rows", "split16"])
+def test_train_each_epoch_with_an_automatic_device_cohort(layout, dev):
+    """cfg `vlsa_device_cohort`: `_train_each_epoch` uploads every bag once, steps from the resident buffer by row-range plans, and
+    tells a cooperating dataset to stop reading what is resident (`skip_features`): the second epoch sees empty feature tensors
+    and trains all the same.  'rows' must match the plain handler bit for bit; 'split16' (pre-split tensor-core records, another
+    summation order in the backward) to 1e-4."""
+    from vlsa_b200 import synth
+    from vlsa_b200.runner import VLSAHandler
+    P = 12
+    sizes = [1000, 37, 2798, 1, 513, 64, 4096, 255]
+    bags = [synth.make_bag("g1", n, 600 + i) for i, n in enumerate(sizes)]
+    pr = synth.make_params(P, P, 21)
+    t, e = synth.make_labels(len(sizes), P, 5)
+    ys = [torch.stack([t[i], e[i]]).float().reshape(1, 2) for i in range(len(sizes))]
+
+    class DS:
+        def __init__(self): self.skip, self.reads = set(), 0
+        def skip_features(self, idx): self.skip = set(int(i) for i in idx)
+        def item(self, i):
+            if i in self.skip:
+                return torch.tensor([[i]]), (torch.empty(1, 0, 512),), ys[i]
+            self.reads += 1
+            return torch.tensor([[i]]), (bags[i].unsqueeze(0),), ys[i]
+
+    class Loader:
+        def __init__(self, ds): self.dataset = ds
+        def __len__(self): return len(bags)
+        def __iter__(self): return (self.dataset.item(i) for i in range(len(bags)))
+
+    cfg = dict(task="vlsa", arch="VLSA", loss_type="SurvIFMLE-SurvEMD", opt_name="adam", opt_lr=2e-4, bp_every_batch=3)
+    ha = VLSAHandler(dict(cfg, vlsa_device_cohort=layout, vlsa_device_cohort_rows=2000), build_net(pr, P, P, dev), device=dev)
+    hb = VLSAHandler(cfg, build_net(pr, P, P, dev), device=dev)
+    la, lb = Loader(DS()), Loader(DS())
+    for epoch in range(3):
+        oa, ob = ha._train_each_epoch(epoch, la), hb._train_each_epoch(epoch, lb)
+        if layout == "rows":
+            assert oa["loss"] == ob["loss"] and torch.equal(oa["pred"]["raw_y_hat"], ob["pred"]["raw_y_hat"])
+        else:
+            np.testing.assert_allclose(oa["loss"], ob["loss"], rtol=1e-4)
+            torch.testing.assert_close(oa["pred"]["raw_y_hat"], ob["pred"]["raw_y_hat"], rtol=1e-4, atol=1e-4)
+    assert la.dataset.reads == len(bags) and lb.dataset.reads == 3 * len(bags)        # the cohort's dataset read every bag once
+    assert len(ha.cohort) == len(bags) and ha.cohort.X.shape[0] >= sum(sizes)           # grown from the 2 000 rows it started with

@@ -40,6 +40,17 @@ class DeviceCohort:
         self.rows = 0                                    # rows handed out so far
         self.index: dict[Hashable, tuple[int, int]] = {}   # key -> (first row, one past the last row)
 
+    def grow(self, min_rows: int) -> None:
+        """Make room for at least ``min_rows`` rows in total (at least doubling): one device-to-device copy of what is resident."""
+        if min_rows <= self.X.shape[0]:
+            return
+        cap = max(int(min_rows), 2 * self.X.shape[0])
+        if self.layout == "split16":
+            cap = (cap + 15) // 16 * 16
+        new = torch.empty(cap, self.X.shape[1], dtype=self.X.dtype, device=self.device)
+        new[: self.rows].copy_(self.X[: self.rows])
+        self.X = new
+
     # ---- filling ------------------------------------------------------------------------------------
     def reserve(self, key: Hashable, n_rows: int) -> torch.Tensor:
         """Claim the next ``n_rows`` rows for bag ``key`` and return the view to copy its rows into."""

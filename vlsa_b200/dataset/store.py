@@ -141,9 +141,18 @@ class WSIPatchSurvStore(torch.utils.data.Dataset):
     def __len__(self) -> int:
         return len(self.pids)
 
+    def skip_features(self, indices) -> None:
+        """Items whose rows already live on the device (a ``DeviceCohort`` keyed by item index, e.g. the one
+        ``VLSAHandler._train_each_epoch`` fills with ``vlsa_device_cohort``) come back with an EMPTY feature tensor [0, 512]:
+        from the second epoch on the loader no longer reads or copies a single row for them."""
+        self._skip = set(int(i) for i in indices)
+
     def __getitem__(self, index: int):
         pid = self.pids[index]
-        feats = self.store.read(self.pid2sids[pid]).to(torch.float)
+        if index in getattr(self, "_skip", ()):
+            feats = torch.empty(0, ops.D_FEAT, dtype=torch.float)
+        else:
+            feats = self.store.read(self.pid2sids[pid]).to(torch.float)
         label = torch.Tensor(self.pid2label[pid]).to(torch.float)
         return torch.Tensor([index]).to(torch.int), (feats, torch.Tensor([0])), label
 

@@ -118,6 +118,11 @@ class VLSAHandler:
             self.optimizer = torch.optim.Adam(groups, lr=float(cfg.get("opt_lr", 2e-4)),
                                               fused=self.device.type == "cuda" and bool(cfg.get("vlsa_torch_adam_fused", True)))
         self.fused_step = bool(cfg.get("vlsa_fused_step", True))
+        # 'rows' | 'split16': `_train_each_epoch` keeps every bag it has seen resident in HBM (dataset/cohort.py) and steps from there
+        self.cohort_layout = cfg.get("vlsa_device_cohort") or None
+        if self.cohort_layout not in (None, "rows", "split16"):
+            raise ValueError("vlsa_device_cohort is 'rows' or 'split16'")
+        self.cohort = None
         self._fused = ops.FusedTrainStep()
         self._flags_known = None                  # (this rank's touched pattern, reduced flags) of the last synchronous step
 
@@ -326,6 +331,25 @@ class VLSAHandler:
             return float(loss_dev), (preds.cpu() if preds is not None else None)
         return loss_dev, preds
 
+    def _to_cohort(self, data_idx, x) -> int:
+        """Key of the bag in the handler's device cohort; its rows are uploaded (and, for 'split16', packed) the first time the
+        bag is seen.  A bag that is already resident may arrive with an empty feature tensor (the dataset skipped the read).
+        With several ranks every rank keeps the bags of its own shard only (key % world == rank)."""
+        from ..dataset.cohort import DeviceCohort
+        key = int(data_idx.reshape(-1)[0]) if isinstance(data_idx, torch.Tensor) else int(data_idx)
+        if self.cohort is None:
+            self.cohort = DeviceCohort(self.device, int(self.cfg.get("vlsa_device_cohort_rows", 1 << 20)), layout=self.cohort_layout)
+        if self.world_size > 1 and key % self.world_size != self.rank:
+            return key
+        bag = x[0] if x.dim() == 3 else x
+        if key not in self.cohort:
+            if bag.shape[0] == 0:
+                raise KeyError(f"bag {key} arrived without rows but is not resident in the device cohort")
+            need = self.cohort.rows + (bag.shape[0] + 15) // 16 * 16
+            self.cohort.grow(need)
+            self.cohort.add(key, bag)
+        return key
+
     def _train_each_epoch(self, epoch, train_loader, name_loader="train"):
         self.net.train()
         bp_every_batch = int(self.cfg.get("bp_every_batch", 32))
@@ -333,16 +357,23 @@ class VLSAHandler:
         idx_c, x_c, y_c = [], [], []
         num_samples = len(train_loader)
         for i_batch, (data_idx, data_x, data_y) in enumerate(train_loader, start=1):
-            x_c.append(data_x[0])
+            x_c.append(self._to_cohort(data_idx, data_x[0]) if self.cohort_layout else data_x[0])
             y_c.append(data_y)
             idx_c.append(data_idx)
             if i_batch % bp_every_batch == 0 or i_batch == num_samples:
-                batch_loss, batch_pred = self._update_network(x_c, y_c, sync=False)   # device tensors: one sync per epoch
+                if self.cohort_layout:
+                    # x_c holds cohort keys: the step is a row-range plan into the resident buffer (no staging, no H2D of rows)
+                    batch_loss, batch_pred = self.update_network_cached(self.cohort, x_c, y_c, sync=False)
+                else:
+                    batch_loss, batch_pred = self._update_network(x_c, y_c, sync=False)   # device tensors: one sync per epoch
                 losses.append(batch_loss)
                 all_raw_pred.append(batch_pred)
                 all_gt.append(torch.cat([y.reshape(1, 2) for y in y_c], dim=0).cpu())
                 all_idx.append(torch.cat([i.reshape(-1) for i in idx_c], dim=0).cpu())
                 idx_c, x_c, y_c = [], [], []
+        if self.cohort_layout and hasattr(getattr(train_loader, "dataset", None), "skip_features"):
+            # the dataset may stop reading what is resident now (dataset/store.py: WSIPatchSurvStore.skip_features)
+            train_loader.dataset.skip_features(self.cohort.index.keys())
         raw = torch.cat(all_raw_pred, 0).cpu()
         losses = torch.stack([torch.as_tensor(l, dtype=torch.float32).reshape(()).to(raw.device) for l in losses]).tolist() if losses else []
         return {"pred": {"y": torch.cat(all_gt, 0), "raw_y_hat": raw, "y_hat": self.output_converter(raw),
