@@ -57,6 +57,7 @@ def main():
                     help="run every epoch through VLSAHandler._train_each_epoch(loader) — the reference's own loop "
                          "(runner/vlsa_handler.py:189-239) — with cfg vlsa_device_cohort = --cohort: the handler keeps the bags it "
                          "has seen resident in HBM and the dataset stops reading them after the first epoch (1 GPU)")
+    ap.add_argument("--print-steps", action="store_true", help="print the loss of every optimizer step")
     ap.add_argument("--autograd-step", action="store_true",
                     help="run every optimizer step through torch autograd and torch.optim.Adam instead of the fused C-call step "
                          "and the bucket Adam kernel (same kernels underneath; for cross-checking the two)")
@@ -151,6 +152,8 @@ def main():
             assert world == 1, "--handler-loop is the single-process loop of the reference"
             losses = handler._train_each_epoch(epoch, loader)["loss"]
             torch.cuda.synchronize(); dt = time.time() - t0
+            if args.print_steps and rank == 0:
+                print("   steps", [round(float(l), 6) for l in losses], flush=True)
             ds.skip_features(())                                # evaluation below reads every bag again
             pred = handler.test_model(handler.net, loader)["pred"]
             if handler.cohort is not None:
@@ -177,6 +180,8 @@ def main():
             losses.append(loss)
         torch.cuda.synchronize(); dt = time.time() - t0
         losses = [float(l) for l in losses]
+        if args.print_steps and rank == 0:
+            print("   steps", [round(l, 6) for l in losses], flush=True)
         pred = handler.test_model(handler.net, loader)["pred"]
         inc = pred["y_hat"].numpy()                                            # incidence function [n, R]
         score = (inc * np.arange(R)[None, :]).sum(1)                           # expected time bin: low = high risk
