@@ -139,13 +139,20 @@ def make_plan(bag_sizes, device, sms: int | None = None) -> BagPlan:
 
 class _PinnedRing:
     """Small pinned staging slots for the per-step tables (row ranges, chunk table, labels): a truly asynchronous H2D copy
-    without a pinned allocation per step, and without the stream synchronisation a copy from pageable memory implies.  A slot
-    is reused only after the copy that read it has completed (its event)."""
+    without a pinned allocation per step, and without the stream synchronisation a copy from pageable memory implies.  Slots
+    are protected in GROUPS: one event is recorded after the last slot of a group has been used, and the first slot of a group
+    is reused only after that event (recorded a whole ring cycle earlier) has completed — an event per upload costs more host
+    time than the upload itself."""
 
-    def __init__(self, slots: int = 16, words: int = 4096):
+    GROUP = 16
+
+    def __init__(self, slots: int = 64, words: int = 2048):
+        assert slots % self.GROUP == 0 and slots >= 2 * self.GROUP
         self.words = words
-        self.buf = [torch.empty(words, dtype=torch.int64).pin_memory() for _ in range(slots)]
-        self.ev: list = [None] * slots
+        flat = torch.empty(slots * words, dtype=torch.int64).pin_memory()
+        self.buf = [flat[i * words:(i + 1) * words] for i in range(slots)]
+        self.np = [b.numpy() for b in self.buf]
+        self.ev: list = [None] * (slots // self.GROUP)
         self.at = 0
 
     def upload(self, fill, n_words: int, device) -> torch.Tensor:
@@ -156,18 +163,20 @@ class _PinnedRing:
             return stage.to(device, non_blocking=True)
         i = self.at
         self.at = (i + 1) % len(self.buf)
-        if self.ev[i] is not None:
-            self.ev[i].synchronize()
-        fill(self.buf[i].numpy()[:n_words])
+        g, first, last = i // self.GROUP, i % self.GROUP == 0, i % self.GROUP == self.GROUP - 1
+        if first and self.ev[g] is not None:
+            self.ev[g].synchronize()                  # every copy that read this group's slots in the previous cycle is done
+        fill(self.np[i][:n_words])
         out = torch.empty(n_words, dtype=torch.int64, device=device)
         out.copy_(self.buf[i][:n_words], non_blocking=True)
-        if self.ev[i] is None:
-            self.ev[i] = torch.cuda.Event()
-        self.ev[i].record()
+        if last:
+            if self.ev[g] is None:
+                self.ev[g] = torch.cuda.Event()
+            self.ev[g].record()
         return out
 
 
-_RINGS: dict[int, _PinnedRing] = {}          # one ring per device: a slot's event belongs to the device it was recorded on
+_RINGS: dict[tuple, _PinnedRing] = {}        # one ring per (device, stream)
 _RING_LOCK = threading.Lock()
 
 
@@ -177,14 +186,17 @@ def upload_small(fill, n_words: int, device) -> torch.Tensor:
     dev = torch.device(device)
     cur = torch.cuda.current_device()
     idx = dev.index if dev.index is not None else cur
+    if idx != cur:
+        with torch.cuda.device(idx):                      # events are recorded on the current stream of the ring's device
+            return upload_small(fill, n_words, dev)
+    key = (idx, _stream())                                # one ring per (device, stream): a group's event covers all its copies
     with _RING_LOCK:
-        ring = _RINGS.get(idx)
+        ring = _RINGS.get(key)
         if ring is None:
-            ring = _RINGS[idx] = _PinnedRing()
-        if idx == cur:
-            return ring.upload(fill, n_words, dev)
-        with torch.cuda.device(idx):                      # the slot's event is recorded on a stream of ITS device
-            return ring.upload(fill, n_words, dev)
+            if len(_RINGS) >= 32:
+                _RINGS.clear()                            # streams come and go; a dropped ring's copies have long completed
+            ring = _RINGS[key] = _PinnedRing()
+        return ring.upload(fill, n_words, dev)
 
 
 def _chunk_schedule(sizes: np.ndarray, sms: int):
