@@ -118,11 +118,13 @@ class FlatBucket:
         """Zero all gradients.  Attached: one memset of the bucket (parameters detached by `drop_untouched` are
         re-attached); otherwise `grad = None` like zero_grad()."""
         self._touched = [False] * len(self.params)
-        if self._hooks and not self.attached():
+        att = self.attached()
+        if self._hooks and not att:
             for p, seg in self._views():
                 if p.grad is None or p.grad.data_ptr() != seg.data_ptr():
                     p.grad = seg.view_as(p)
-        if self.attached() or (not self._hooks and all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views())):
+            att = True
+        if att or (not self._hooks and all(p.grad is not None and p.grad.data_ptr() == seg.data_ptr() for p, seg in self._views())):
             self.flat.zero_()
         else:
             for p in self.params:
@@ -138,9 +140,10 @@ class FlatBucket:
                 n += 1
         return n
 
-    def pack(self, extra_values: torch.Tensor | None = None, extra_in_place: bool = False) -> None:
-        """`extra_in_place`: the caller's scalars were already written into `tail` (by a kernel)."""
-        if self._hooks and self.attached():
+    def pack(self, extra_values: torch.Tensor | None = None, extra_in_place: bool = False, attached: bool | None = None) -> None:
+        """`extra_in_place`: the caller's scalars were already written into `tail` (by a kernel).  `attached`: what
+        `self.attached()` returned earlier in this step (the check walks every parameter; a step asks once)."""
+        if self._hooks and (self.attached() if attached is None else attached):
             # gradients already live here; the flags of a touched pattern are uploaded once and copied on the device after that
             if self.extra and not extra_in_place:
                 if extra_values is None:
@@ -180,8 +183,8 @@ class FlatBucket:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
 
-    def unpack(self) -> None:
-        if self._hooks and self.attached():
+    def unpack(self, attached: bool | None = None) -> None:
+        if self._hooks and (self.attached() if attached is None else attached):
             return
         for p, seg in self._views():
             g = seg.view_as(p)

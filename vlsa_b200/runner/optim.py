@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, ops
 from .dist import FlatBucket
 
 
@@ -63,12 +63,13 @@ class BucketAdam:
             self._seg_key = key
         return self._segs
 
-    def step(self, use_flags: bool = True) -> None:
-        """One update from the gradients in the bucket.  ``use_flags``: skip the parameters whose (all-reduced) flag is zero."""
+    def step(self, use_flags: bool = True, attached: bool | None = None) -> None:
+        """One update from the gradients in the bucket.  ``use_flags``: skip the parameters whose (all-reduced) flag is zero.
+        ``attached``: what ``bucket.attached()`` returned earlier in this step."""
         bk = self.bucket
         if not bk.params:
             return
-        if not bk.attached():
+        if not (bk.attached() if attached is None else attached):
             raise RuntimeError("BucketAdam: the parameters' gradients must be attached to the bucket (FlatBucket.attach)")
         g0 = self.param_groups[0]
         for g in self.param_groups[1:]:
@@ -78,7 +79,7 @@ class BucketAdam:
         rc = _lib.lib().vlsa_adam_step(segs.data_ptr(), len(bk.params), self._max_n, bk.flat.data_ptr(), self.exp_avg.data_ptr(),
                                        self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(),
                                        bk.flags.data_ptr() if use_flags else None, float(g0["betas"][0]), float(g0["betas"][1]),
-                                       float(g0["eps"]), torch.cuda.current_stream(bk.flat.device).cuda_stream)
+                                       float(g0["eps"]), ops._stream())
         _lib.check(rc, "vlsa_adam_step")
         # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on a tensor's version
         # counter, e.g. VLFAN.query_directions_cached) that they changed, as an in-place torch op would

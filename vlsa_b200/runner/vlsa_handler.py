@@ -216,11 +216,12 @@ class VLSAHandler:
         plan = cohort.plan([keys[i] for i in mine]) if mine else None
         return self._step(cohort.X if mine else None, plan, self._labels(ys, mine), mine, n_sample, sync)
 
-    def _fused_ok(self) -> bool:
+    def _fused_ok(self, attached: bool | None = None) -> bool:
         """The step can run as three C calls (ops.FusedTrainStep): shipped VLFAN shape (mean over P + Linear adapter, raw rows
         in) and gradients attached to the bucket.  Everything else takes the autograd path."""
         enc = self.net.mil_encoder
-        return (self.fused_step and self.device.type == "cuda" and isinstance(enc, deepmil.VLFAN) and enc.fused_tail and self.bucket.attached()
+        return (self.fused_step and self.device.type == "cuda" and isinstance(enc, deepmil.VLFAN) and enc.fused_tail
+                and (self.bucket.attached() if attached is None else attached)
                 and not (self.objective.w_ifmle == 0.0 and self.objective.w_emd == 0.0))
 
     def _fused_local_step(self, X, plan, t, e, n_sample):
@@ -272,11 +273,12 @@ class VLSAHandler:
         """`lab`: labels of the local bags, [2, len(mine)] int64 on the device (`_labels`); `mine`: their positions among the
         `n_sample` bags of the step."""
         self.bucket.zero()
+        att = self.bucket.attached()                               # asked once per step (the check walks every parameter)
         loss_in_tail = False
         local_loss = None
         extra = self._query_div_term()
         if mine:
-            if self._fused_ok():
+            if self._fused_ok(att):
                 with torch.enable_grad():
                     local_pred, local_loss, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample)
                 if extra is not None:
@@ -297,13 +299,14 @@ class VLSAHandler:
             extra.backward()
             local_loss = extra.detach().reshape(1)
         # the one exchange of the step: gradients + losses in one flat bucket
-        self.bucket.pack(local_loss, extra_in_place=loss_in_tail)
+        att = att and self.bucket.attached() if not loss_in_tail else att      # (the autograd path may have replaced a .grad)
+        self.bucket.pack(local_loss, extra_in_place=loss_in_tail, attached=att)
         self.bucket.all_reduce()
-        self.bucket.unpack()
+        self.bucket.unpack(attached=att)
         n_par = len(self.bucket.params)
         if isinstance(self.optimizer, BucketAdam):
             # the kernel reads the reduced flags itself: untouched parameters are skipped on the device
-            self.optimizer.step()
+            self.optimizer.step(attached=att)
             loss_dev = self.bucket.tail[0].clone()
         else:
             pattern = (tuple(self.bucket._touched), bool(mine))
