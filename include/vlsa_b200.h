@@ -214,13 +214,16 @@ int vlsa_row_normalize(const void* X, int x_dtype, int64_t N, float* out, void* 
  * eps added to sqrt(v_hat)), amsgrad off.  Gradients and both moments are flat fp32 buffers of one layout (the all-reduce
  * bucket); `segments` is a DEVICE array of S records of vlsa_adam_segment_bytes() bytes:
  *     { float* param; int64 offset (floats, into the flat buffers); int64 n; float weight_decay; float lr; }
- * `step_count` [S] (device, float) holds the steps each tensor has taken and is incremented here; `flags` [S] (device, may be
- * NULL): a tensor whose flag is 0 received no gradient this step and is skipped — moments, count and decay untouched, as
- * torch.optim.Adam skips `grad is None` — decided on the device, so an optimizer step needs no device -> host read.
+ * `step_count_in` [S] (device, float) holds the steps each tensor has taken; the counts after this step are written to
+ * `step_count_out` [S], a DIFFERENT array (callers ping-pong two: no block can read a count another block already bumped, and
+ * the step stays one launch); `flags` [S] (device, may be NULL = every tensor has a gradient): a tensor whose flag is 0
+ * received no gradient this step and is skipped — moments, count and decay untouched, as torch.optim.Adam skips
+ * `grad is None` — decided on the device, so an optimizer step needs no device -> host read.
  * max_n = the largest n of the segments. */
 size_t vlsa_adam_segment_bytes(void);
 int vlsa_adam_step(const void* segments, int S, int64_t max_n, const float* grads_flat, float* exp_avg, float* exp_avg_sq,
-                   float* step_count, const float* flags, float beta1, float beta2, float eps, void* stream);
+                   const float* step_count_in, float* step_count_out, const float* flags, float beta1, float beta2, float eps,
+                   void* stream);
 
 /* Whole path with HOST buffers (what a caller holding CPU tensors — the reference's DataLoader output,
  * dataset/PatchWSI.py:197-215 + runner/vlsa_handler.py:205,322-330 — would call): stage the packed bags

@@ -53,8 +53,8 @@ _SIGNATURES = {
     "vlsa_logit_pool_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, C.c_int, c_f32p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_size_t, c_f32p, c_i64p, C.c_void_p]),
     "vlsa_adam_segment_bytes": (C.c_size_t, []),
-    "vlsa_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_float, C.c_float,
-                                 C.c_float, C.c_void_p]),
+    "vlsa_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_float,
+                                 C.c_float, C.c_float, C.c_void_p]),
     "vlsa_forward_host_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int, C.c_int]),
     "vlsa_feat_pool_workspace_bytes": (C.c_size_t, []),
     "vlsa_feat_pool_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, c_f32p, C.c_int, c_f32p, C.c_void_p,

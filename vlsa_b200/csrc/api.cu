@@ -287,15 +287,17 @@ int vlsa_debug_read_prof(long long* out_host) {          // development builds o
 size_t vlsa_adam_segment_bytes(void) { return sizeof(AdamSeg); }
 
 int vlsa_adam_step(const void* segments, int S, int64_t max_n, const float* grads_flat, float* exp_avg, float* exp_avg_sq,
-                   float* step_count, const float* flags, float beta1, float beta2, float eps, void* stream) {
-    if (S < 0 || max_n < 0 || !segments || !grads_flat || !exp_avg || !exp_avg_sq || !step_count) return VLSA_EINVAL;
+                   const float* step_count_in, float* step_count_out, const float* flags, float beta1, float beta2, float eps,
+                   void* stream) {
+    if (S < 0 || max_n < 0 || !segments || !grads_flat || !exp_avg || !exp_avg_sq || !step_count_in || !step_count_out ||
+        step_count_in == step_count_out)
+        return VLSA_EINVAL;
     if (S == 0 || max_n == 0) return 0;
     if (S > 65535) return VLSA_EUNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const dim3 grid(unsigned((max_n + 1023) / 1024), unsigned(S));
-    adam_step_kernel<<<grid, 256, 0, st>>>(static_cast<const AdamSeg*>(segments), grads_flat, exp_avg, exp_avg_sq, step_count,
-                                           flags, beta1, beta2, eps);
-    adam_count_kernel<<<(S + 127) / 128, 128, 0, st>>>(step_count, flags, S);
+    adam_step_kernel<<<grid, 256, 0, st>>>(static_cast<const AdamSeg*>(segments), grads_flat, exp_avg, exp_avg_sq, step_count_in,
+                                           step_count_out, flags, beta1, beta2, eps);
     return static_cast<int>(cudaGetLastError());
 }
 

@@ -17,14 +17,18 @@ struct AdamSeg {            // one parameter tensor (device array, 32 bytes)
     float lr;
 };
 
-// grid (ceil(max n / (256 * 4)), S) x 256.  step_count[s]: optimizer steps parameter s has taken so far (float, on the device).
-// Nobody writes step_count in this launch: adam_count_kernel bumps it afterwards.
+// grid (ceil(max n / (256 * 4)), S) x 256.  step_in[s]: optimizer steps parameter s has taken so far (float, on the device);
+// block x = 0 of every segment writes the new count to step_out[s] — a DIFFERENT array (the caller ping-pongs two), so no
+// block of this launch can read a count another block has already bumped.
 __global__ void __launch_bounds__(256) adam_step_kernel(const AdamSeg* __restrict__ segs, const float* __restrict__ grads,
                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                                                        const float* __restrict__ step_count, const float* __restrict__ flags,
-                                                        float beta1, float beta2, float eps) {
+                                                        const float* __restrict__ step_in, float* __restrict__ step_out,
+                                                        const float* __restrict__ flags, float beta1, float beta2, float eps) {
     const int s = blockIdx.y;
-    if (flags && flags[s] == 0.f) return;
+    const bool skip = flags && flags[s] == 0.f;
+    const float* step_count = step_in;
+    if (blockIdx.x == 0 && threadIdx.x == 0) step_out[s] = step_in[s] + (skip ? 0.f : 1.f);
+    if (skip) return;
     const AdamSeg sg = segs[s];
     const long long i0 = (long long)(blockIdx.x) * 1024 + threadIdx.x * 4;
     if (i0 >= sg.n) return;
@@ -48,11 +52,6 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamSeg* __restric
         exp_avg[sg.offset + i] = m;
         exp_avg_sq[sg.offset + i] = v;
     }
-}
-
-__global__ void adam_count_kernel(float* __restrict__ step_count, const float* __restrict__ flags, int S) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S && (!flags || flags[s] != 0.f)) step_count[s] += 1.f;
 }
 
 }  // namespace vlsa

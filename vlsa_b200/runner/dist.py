@@ -140,9 +140,16 @@ class FlatBucket:
                 n += 1
         return n
 
-    def pack(self, extra_values: torch.Tensor | None = None, extra_in_place: bool = False, attached: bool | None = None) -> None:
+    def begin_step(self) -> None:
+        """`zero()` without the memset, for steps whose kernels OVERWRITE every gradient of the bucket (the caller vouches for
+        it): resets the touched marks only."""
+        self._touched = [False] * len(self.params)
+
+    def pack(self, extra_values: torch.Tensor | None = None, extra_in_place: bool = False, attached: bool | None = None,
+             with_flags: bool = True) -> None:
         """`extra_in_place`: the caller's scalars were already written into `tail` (by a kernel).  `attached`: what
-        `self.attached()` returned earlier in this step (the check walks every parameter; a step asks once)."""
+        `self.attached()` returned earlier in this step (the check walks every parameter; a step asks once).  `with_flags=False`:
+        nobody will read the flags of this step (every parameter is known to have a gradient)."""
         if self._hooks and (self.attached() if attached is None else attached):
             # gradients already live here; the flags of a touched pattern are uploaded once and copied on the device after that
             if self.extra and not extra_in_place:
@@ -152,7 +159,7 @@ class FlatBucket:
                     vals = extra_values.reshape(-1).to(self.flat.dtype)
                     self.tail.zero_() if vals.numel() < self.extra else None
                     self.tail[: vals.numel()].copy_(vals)
-            if self.params:
+            if self.params and with_flags:
                 key = tuple(self._touched)
                 dev_flags = self._flag_cache.get(key)
                 if dev_flags is None:

@@ -36,7 +36,9 @@ class BucketAdam:
         dev = bucket.flat.device
         self.exp_avg = torch.zeros(bucket._grad_floats, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros_like(self.exp_avg)
-        self.step_count = torch.zeros(len(bucket.params), dtype=torch.float32, device=dev)
+        # per-tensor step counts, two arrays used alternately (the kernel reads one and writes the other)
+        self._steps = torch.zeros(2, max(len(bucket.params), 1), dtype=torch.float32, device=dev)
+        self._cur = 0
         self._seg_key = None
         self._segs = None
         self._max_n = max([p.numel() for p in bucket.params], default=0)
@@ -76,14 +78,21 @@ class BucketAdam:
             if tuple(g["betas"]) != tuple(g0["betas"]) or g["eps"] != g0["eps"]:
                 raise NotImplementedError("BucketAdam: betas / eps must be the same for every group")
         segs = self._segments()
+        src, dst = self._steps[self._cur], self._steps[1 - self._cur]
         rc = _lib.lib().vlsa_adam_step(segs.data_ptr(), len(bk.params), self._max_n, bk.flat.data_ptr(), self.exp_avg.data_ptr(),
-                                       self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), src.data_ptr(), dst.data_ptr(),
                                        bk.flags.data_ptr() if use_flags else None, float(g0["betas"][0]), float(g0["betas"][1]),
                                        float(g0["eps"]), ops._stream())
         _lib.check(rc, "vlsa_adam_step")
+        self._cur = 1 - self._cur
         # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on a tensor's version
         # counter, e.g. VLFAN.query_directions_cached) that they changed, as an in-place torch op would
         torch.autograd.graph.increment_version(bk.params)
+
+    @property
+    def step_count(self) -> torch.Tensor:
+        """Steps every tensor of the bucket has taken (float, on the device)."""
+        return self._steps[self._cur][: len(self.bucket.params)]
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         self.bucket.zero()
@@ -116,7 +125,7 @@ class BucketAdam:
             for k, v in saved.items():
                 if k != "params" and k in g:
                     g[k] = tuple(v) if k == "betas" else v
-        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.step_count.zero_()
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self._steps.zero_()
         for at, p in enumerate(self._order):
             st = sd["state"].get(at, sd["state"].get(str(at)))
             if st is None:
@@ -124,5 +133,5 @@ class BucketAdam:
             i, off, n = slot[id(p)]
             self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
             self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
-            self.step_count[i] = float(st["step"])
+            self._steps[self._cur, i] = float(st["step"])
         self._seg_key = None

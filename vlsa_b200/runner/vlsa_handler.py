@@ -224,11 +224,28 @@ class VLSAHandler:
                 and (self.bucket.attached() if attached is None else attached)
                 and not (self.objective.w_ifmle == 0.0 and self.objective.w_emd == 0.0))
 
-    def _fused_local_step(self, X, plan, t, e, n_sample):
-        """forward + loss + backward of this rank's bags; the three loss values land in the bucket tail."""
-        net, enc, bk = self.net, self.net.mil_encoder, self.bucket
+    def _taskres_residual(self):
+        """The residual rows of a plain (ungated) TaskRes prompt adapter, whose gradient is `ratio * dQ` — or None."""
+        enc = self.net.mil_encoder
         adapter = enc.Q if isinstance(enc.Q, PromptAdapter) else None
-        res = adapter.residual_features if adapter is not None and adapter.method == "TaskRes" and not enc.gated_query else None
+        if adapter is not None and adapter.method == "TaskRes" and not enc.gated_query:
+            return adapter, adapter.residual_features
+        return None, None
+
+    def _step_overwrites_all(self) -> bool:
+        """True when the fused step WRITES (not accumulates) the gradient of every parameter in the bucket — W, bias, logit_scale
+        by the kernels, the TaskRes residual by `ratio * dQ` — so that the bucket needs no memset before the step."""
+        enc = self.net.mil_encoder
+        _, res = self._taskres_residual()
+        written = {id(enc.visual_adapter.weight), id(enc.visual_adapter.bias), id(self.net.logit_scale)}
+        if res is not None:
+            written.add(id(res))
+        return all(id(p) in written for p in self.bucket.params)
+
+    def _fused_local_step(self, X, plan, t, e, n_sample, loss_out=None):
+        """forward + loss + backward of this rank's bags; the three loss values land in `loss_out` (default: the bucket tail)."""
+        net, enc, bk = self.net, self.net.mil_encoder, self.bucket
+        adapter, res = self._taskres_residual()
         if res is not None and res.requires_grad and res.grad is not None:
             # plain TaskRes rows (prompt_adapter.py:125-126): Q = ratio * residual + prompt, so d residual = ratio * dQ — one
             # kernel into the attached view instead of a trip through the autograd engine (same arithmetic, same bits)
@@ -243,7 +260,7 @@ class VLSAHandler:
         out = self._fused(X, plan, Qd, W, bias, T, ls, t, e, w_ifmle=self.objective.w_ifmle, w_emd=self.objective.w_emd,
                           alpha=self.objective.alpha, eps=self.objective.eps, norm=n_sample, scale=enc.coattn_scale_float(),
                           q_prenorm=prenorm, grad_out={k: p.grad for k, p in leaves.items() if p.requires_grad},
-                          loss_out=bk.tail)
+                          loss_out=bk.tail if loss_out is None else loss_out)
         for k, buf in (("W", out["dW"]), ("bias", out["db"]), ("logit_scale", out["dls"])):
             p = leaves[k]
             if not p.requires_grad:
@@ -251,7 +268,7 @@ class VLSAHandler:
             if out["wrote"][k]:
                 bk.mark_touched(p)                             # written in place of the zeroed view
             else:
-                p.grad.add_(buf.reshape(-1)[: p.numel()].view_as(p))
+                p.grad.copy_(buf.reshape(-1)[: p.numel()].view_as(p))      # the kernels' outputs are whole gradients
                 bk.mark_touched(p)
         if res is not None:
             torch.mul(out["dQ"], float(adapter.res_ratio), out=res.grad)
@@ -260,7 +277,8 @@ class VLSAHandler:
         if roots:
             torch.autograd.backward([z for z, _ in roots], [g for _, g in roots])
         in_tail = out["loss"].data_ptr() == bk.tail.data_ptr()
-        return out["logits"], (None if in_tail else out["loss"][:3].clone()), in_tail
+        own = loss_out is not None and out["loss"].data_ptr() == loss_out.data_ptr()
+        return out["logits"], (None if in_tail else (out["loss"][:3] if own else out["loss"][:3].clone())), in_tail
 
     def _query_div_term(self):
         """weight * query_div_loss() of this step, split evenly over the ranks (the bucket all-reduce sums it back)."""
@@ -272,15 +290,24 @@ class VLSAHandler:
     def _step(self, X, plan, lab, mine, n_sample, sync: bool = True, gather_preds: bool = True):
         """`lab`: labels of the local bags, [2, len(mine)] int64 on the device (`_labels`); `mine`: their positions among the
         `n_sample` bags of the step."""
-        self.bucket.zero()
         att = self.bucket.attached()                               # asked once per step (the check walks every parameter)
+        fused = bool(mine) and self._fused_ok(att)
+        single = self.world_size == 1
+        if fused and self._step_overwrites_all():
+            self.bucket.begin_step()                               # every gradient is overwritten below: no memset
+        else:
+            self.bucket.zero()
+            att = self.bucket.attached()
+            fused = bool(mine) and self._fused_ok(att)
         loss_in_tail = False
         local_loss = None
         extra = self._query_div_term()
         if mine:
-            if self._fused_ok(att):
+            if fused:
+                # one process: nothing rides an all-reduce, the losses go to a tensor of their own (no copy out of the bucket)
+                own_loss = torch.empty(3, dtype=torch.float32, device=self.device) if single else None
                 with torch.enable_grad():
-                    local_pred, local_loss, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample)
+                    local_pred, local_loss, loss_in_tail = self._fused_local_step(X, plan, lab[0], lab[1], n_sample, own_loss)
                 if extra is not None:
                     extra.backward()                               # accumulates on top of what the kernels wrote
                     (self.bucket.tail if loss_in_tail else local_loss)[0:1].add_(extra.detach().reshape(1))
@@ -299,14 +326,23 @@ class VLSAHandler:
             extra.backward()
             local_loss = extra.detach().reshape(1)
         # the one exchange of the step: gradients + losses in one flat bucket
-        att = att and self.bucket.attached() if not loss_in_tail else att      # (the autograd path may have replaced a .grad)
-        self.bucket.pack(local_loss, extra_in_place=loss_in_tail, attached=att)
+        if not fused:
+            att = att and self.bucket.attached()                   # (the autograd path may have replaced a .grad)
+        bucket_adam = isinstance(self.optimizer, BucketAdam)
+        # one process, every parameter has a gradient: nobody needs the flags (with several ranks they always travel: a rank
+        # without bags learns from the reduced flags which parameters the others touched)
+        need_flags = not (single and bucket_adam and bool(mine) and all(self.bucket._touched))
+        if fused and single and not need_flags:
+            loss_dev = local_loss[0]                               # the step's own tensor: nothing to pack, reduce or copy
+            self.optimizer.step(use_flags=False, attached=att)
+            return self._finish_step(loss_dev, local_pred, mine, n_sample, sync, gather_preds)
+        self.bucket.pack(local_loss, extra_in_place=loss_in_tail, attached=att, with_flags=need_flags)
         self.bucket.all_reduce()
         self.bucket.unpack(attached=att)
         n_par = len(self.bucket.params)
-        if isinstance(self.optimizer, BucketAdam):
+        if bucket_adam:
             # the kernel reads the reduced flags itself: untouched parameters are skipped on the device
-            self.optimizer.step(attached=att)
+            self.optimizer.step(use_flags=need_flags, attached=att)
             loss_dev = self.bucket.tail[0].clone()
         else:
             pattern = (tuple(self.bucket._touched), bool(mine))
@@ -324,6 +360,9 @@ class VLSAHandler:
                 loss_dev = tail[0]
             self.bucket.drop_untouched(flags)
             self.optimizer.step()
+        return self._finish_step(loss_dev, local_pred, mine, n_sample, sync, gather_preds)
+
+    def _finish_step(self, loss_dev, local_pred, mine, n_sample, sync, gather_preds):
         if not gather_preds:
             preds = None
         elif self.world_size == 1 and len(mine) == n_sample:
