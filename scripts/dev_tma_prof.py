@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from vlsa_b200 import ops, synth, _lib
 dev = torch.device("cuda:0")
-P, N, B = int(os.environ.get("DEV_P", 12)), 50000, 32
+P, N, B = int(os.environ.get("DEV_P", 12)), int(os.environ.get("DEV_N", 50000)), int(os.environ.get("DEV_B", 32))
 pr = synth.make_params(P, P, 1)
 X = torch.randn(N * B, 512, device=dev) * 1.1 + 0.7
 if os.environ.get('DEV_DTYPE') == 'bf16':
@@ -33,3 +33,4 @@ names = {0: "conv: wait landed | prod: wait empty", 1: "conv: group barrier | pr
 print(f"tiles per CTA: {tiles}")
 for k in range(19):
     print(f"  {names[k]:40s} {v[k]/tiles:9.1f} cycles / tile")
+print(f"block 0: Qn staged + TMEM allocated {v[22]/1e3:.1f} us, TMEM staged (warp 0) {v[23]/1e3:.1f} us, prologue {v[21]/1e3:.1f} us, kernel entry -> exit {v[20]/1e3:.1f} us")

@@ -87,6 +87,9 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
     using C = Bf16Cfg;
     constexpr int D = C::D, NP = C::NP, TR = C::TR;
     if (int(blockIdx.x) >= prm.total_chunks) return;
+#ifdef VLSA_TMA_PROF
+    unsigned long long prof_gt0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_gt0));
+#endif
 
     extern __shared__ unsigned char smem_raw[];
     unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
@@ -126,7 +129,9 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         mbar_fence_init();
     }
     if (warp == C::W_G1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+#ifndef VLSA_NO_TMAP_PREFETCH
     if (warp == C::W_TMA && lane == 0) tma_prefetch_desc(&tmap);
+#endif
     // ---- prologue: Qn = Q / max(|Q|, eps) staged as fp32 in the (still unused) ring, rows >= P are zero
     {
         float* qn = reinterpret_cast<float*>(ring);
@@ -144,6 +149,12 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef VLSA_TMA_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        g_tma_prof[22] = (long long)(t1 - prof_gt0);          // ns until Qn is staged in shared memory and TMEM is allocated
+    }
+#endif
     const uint32_t tmem = *tmem_ptr;
     if (warp < 4) {
         // TMEM lane 32 warp + lane: prototype 4 warp + (lane & 3); c = lane >> 2: bf16 term c % 3 of Qn (three terms: 24
@@ -155,21 +166,38 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
         for (int cb = 0; cb < 8; ++cb) {
             uint32_t v[32];
             const bool mine = c8 < 6 && (cb >> 2) == range;
+            // per-lane masks instead of a per-element ternary: the lanes of a warp differ in (mine, term), and the compiler turned
+            // the nested select into a divergent branch with a reconvergence point PER ELEMENT (256 of them: 20 us of every
+            // launch, measured with the prologue timestamps of the -DVLSA_TMA_PROF build)
+            const uint32_t m0 = (mine && term == 0) ? 0xffffffffu : 0u, m1 = (mine && term == 1) ? 0xffffffffu : 0u,
+                           m2 = (mine && term == 2) ? 0xffffffffu : 0u;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 uint32_t t0, t1, t2;
                 split_bf16x3(qrow[cb * 64 + 2 * i], qrow[cb * 64 + 2 * i + 1], t0, t1, t2);
-                v[i] = mine ? (term == 0 ? t0 : (term == 1 ? t1 : t2)) : 0u;
+                v[i] = (t0 & m0) | (t1 & m1) | (t2 & m2);
             }
             tmem_st32(tq + 32 * cb, v);
         }
         tmem_wait_st();
+#ifdef VLSA_TMA_PROF
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            g_tma_prof[23] = (long long)(t1 - prof_gt0);      // ns until warp 0 has staged its quadrant of Qn in TMEM
+        }
+#endif
     }
     // the async proxy (TMA) writes the ring next: order the generic-proxy staging reads / writes before it
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef VLSA_TMA_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        g_tma_prof[21] = (long long)(t1 - prof_gt0);          // ns spent in the prologue
+    }
+#endif
 
     if (warp >= C::W_CONV) {
         // =========================================================================== row norms
@@ -637,6 +665,12 @@ __global__ void __launch_bounds__(Bf16Cfg::THREADS, 1) agg_bf16_kernel(const Agg
     tc_fence_before();
     __syncthreads();
     if (warp == C::W_G1) tmem_dealloc(tmem, C::TMEM_COLS);
+#ifdef VLSA_TMA_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        g_tma_prof[20] = (long long)(t1 - prof_gt0);          // ns from kernel entry to exit, block 0
+    }
+#endif
 }
 
 }  // namespace vlsa
